@@ -1,0 +1,178 @@
+/*
+ * node_b200.h - C ABI of the B200-native dopri5 / ODE-Net hot path.
+ *
+ * Drop-in boundary for fabiocarrara/neural-ode-features: the reference binds this path by
+ * Python import (`from torchdiffeq import odeint_adjoint, odeint`, reference model.py:3); the
+ * package neural-ode-features_b200/torchdiffeq re-exports those two names and reaches the
+ * kernels below through ctypes.  Plain pointers and sizes only - no torch types.
+ *
+ * All pointers are DEVICE pointers unless named host_*.  `stream` is a cudaStream_t passed
+ * as void* (torch.cuda.current_stream().cuda_stream).  Every entry point only ENQUEUES work
+ * and returns a cudaError_t-compatible int (0 = success); none of them synchronises.
+ *
+ * File:line citations are relative to /root/reference/torchdiffeq/torchdiffeq/_impl/ unless
+ * they start with model.py.
+ */
+#ifndef NODE_B200_H_
+#define NODE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NODE_B200_ABI_VERSION 1
+#define NODE_MAX_SEG 8      /* members of a tuple state (adjoint uses 4: y, adj_y, adj_t, adj_p) */
+#define NODE_MAX_TRACE 192  /* attempted steps recorded for parity tests */
+
+/* dtype tags for the generic-callable route */
+#define NODE_F32 0
+#define NODE_F64 1
+
+/* status bits, raised as AssertionError by the Python boundary after the solve */
+#define NODE_ST_DT_UNDERFLOW 1  /* dopri5.py:100  t0 + dt > t0 */
+#define NODE_ST_NONFINITE    2  /* dopri5.py:102  non-finite values in state */
+#define NODE_ST_MAX_STEPS    4  /* dopri5.py:89   max_num_steps exceeded */
+#define NODE_ST_INTERP_RANGE 8  /* interp.py:58   t0 <= t <= t1 */
+#define NODE_ST_WATCHDOG     16 /* an in-kernel barrier wait timed out (never expected) */
+
+/*
+ * Device-resident controller block: the whole adaptive-step state machine of
+ * dopri5.py:77-122 + misc.py:84-170 lives here so that no host round trip is needed per
+ * step.  The host reads it back once per solve (fused route) or once per attempted step
+ * (generic-callable route, where the callable itself is host code).
+ */
+typedef struct node_ctl {
+  /* float64 time axis (solvers.py:28, dopri5.py:72-75) */
+  double t0, t1;          /* last ACCEPTED interval; outputs are interpolated inside it */
+  double dt;              /* size of the next attempt */
+  double t_attempt;       /* start of the attempt being / about to be evaluated (== t1) */
+  double dt_attempt;      /* its size */
+  double h0;              /* misc.py:128-131 first guess, kept in the state dtype */
+  double d1max;           /* misc.py:126 max over tuple members, kept for INIT_B */
+  double ratio[NODE_MAX_SEG]; /* misc.py:155-156 mean squared error ratio of the last attempt */
+  double rtol[NODE_MAX_SEG], atol[NODE_MAX_SEG];
+  double safety, ifactor, dfactor; /* as built by dopri5.py:72-74: rounded through torch's default dtype */
+  double expo;            /* misc.py:168 exponent 1/order, same rounding */
+  /* the same times rounded to the state dtype (rk_common.py:45-46, interp.py:54-56) */
+  double ts64[7];         /* [0] attempt start s, [1..6] s + alpha_i*h, state dtype f64 */
+  double h64;
+  float  ts32[7];
+  float  h32;
+  float  h0_32, pad0;
+  /* dense output bookkeeping (dopri5.py:85-92) */
+  double it_t0, it_t1;    /* interval the interpolant belongs to, float64 */
+  double it_h64;  float it_h32; int32_t it_cur;  /* its dt in state dtype; buffer that holds y0,f0 */
+  int32_t out_lo, out_hi; /* output indices [lo,hi) to emit from the step just accepted */
+  int32_t next_out, n_out;
+  /* counters */
+  int32_t n_attempt, n_accept, n_reject, nfe;
+  int32_t steps_this_advance, max_num_steps;
+  int32_t status, done, cur, accepted_last;
+  int32_t n_seg, dtype, tsign, reserved;
+  int64_t seg_numel[NODE_MAX_SEG]; /* GLOBAL element count per member (all shards) */
+  /* trace of attempted steps */
+  double tr_t[NODE_MAX_TRACE], tr_dt[NODE_MAX_TRACE], tr_ratio[NODE_MAX_TRACE];
+  int32_t tr_acc[NODE_MAX_TRACE];
+} node_ctl_t;
+
+int node_b200_abi_version(void);
+/* sizeof(node_ctl_t) and byte offsets of the fields the Python side reads, in the order
+ * documented in node_b200/native.py (CTL_FIELDS). Host function. */
+int node_b200_ctl_layout(int64_t* host_out, int capacity);
+
+/* ---- generic-callable route: building blocks (func is evaluated by the caller) ---------- */
+
+/* Zero-initialise the block and set tolerances / options (dopri5.py:60-75).
+ * host arrays rtol/atol have n_seg entries; seg_numel are GLOBAL counts. safety/ifactor/dfactor/expo
+ * are passed as the reference builds them: `torch.tensor(x)` in the DEFAULT dtype widened to float64
+ * (misc.py:37-44), i.e. (double)(float)0.9 etc. when the default dtype is float32. */
+int node_b200_ctl_init(node_ctl_t* ctl, int dtype, int n_seg, const double* host_rtol, const double* host_atol,
+                       const int64_t* host_seg_numel, double safety, double ifactor, double dfactor, double expo,
+                       int max_num_steps, int n_out, int tsign, void* stream);
+
+/* K2 - stage combination  out = y0 + sum_j (h*c_j)*k_j  (rk_common.py:49-51, misc.py:22-25).
+ * `which` selects the coefficient row: 0..5 = beta row of stage i+1, 6 = C_MID (dopri5.py:33-42),
+ * 7 = initial-step probe y0 + h0*f0 (misc.py:133). h is read from ctl. n_k pointers in ks. */
+int node_b200_rk_stage_combine(const node_ctl_t* ctl, int dtype, int which, void* out, const void* y0,
+                               const void* const* host_ks, int n_k, int64_t numel, void* stream);
+
+/* K3 - error estimate + per-member sum of squared ratios (rk_common.py:60, misc.py:146-157);
+ * never materialises y1_error. seg_off/seg_len (host arrays, elements) describe the members of
+ * the flat state. Writes partials[seg][block] (double) and sets a non-finite flag for |y0|.
+ * host_ks = k1..k7. */
+int node_b200_rk_error_norm(const node_ctl_t* ctl, int dtype, const void* y0, const void* y1,
+                            const void* const* host_ks, const int64_t* host_seg_off, const int64_t* host_seg_len,
+                            int n_seg, double* partials, int* nonfinite_flag, void* stream);
+
+/* K5 - initial step norms (misc.py:123-126,136): mode 0 writes sum((y0/scale)^2), sum((f0/scale)^2);
+ * mode 1 writes sum(((f1-f0)/scale)^2). partials layout [seg][2][block]. */
+int node_b200_init_norms(const node_ctl_t* ctl, int dtype, int mode, const void* y0, const void* f0, const void* f1,
+                         const int64_t* host_seg_off, const int64_t* host_seg_len, int n_seg,
+                         double* partials, void* stream);
+
+/* Fold per-block partials into sums[seg][2] in a fixed order (deterministic); this is the
+ * buffer a multi-GPU run all-reduces before the controller consumes it. */
+int node_b200_reduce_partials(const double* partials, int n_rows, double* sums, void* stream);
+
+/* K6 - device-side controller. mode 0: INIT_A (misc.py:123-131), 1: INIT_B (misc.py:136-143,
+ * dopri5.py:80-83), 2: STEP (dopri5.py:109-121, misc.py:160-170, dopri5.py:88-92 output
+ * scheduling). t_out: the requested times as float64 [n_out] (already sign-flipped if the
+ * caller integrates backwards, misc.py:184-187). */
+int node_b200_controller(node_ctl_t* ctl, int mode, const double* sums, const int* nonfinite_flag,
+                         const double* t_out, void* stream);
+
+/* K4 - dense output (dopri5.py:39-45, interp.py:5-65) for output indices [ctl.out_lo, ctl.out_hi):
+ * out[(idx*out_stride) + e] for e < numel. No-op when the range is empty. use_ctl_cur != 0:
+ * (y0,y1) and (f0,f1) are ping-pong buffers and ctl.it_cur says which one held the start of
+ * the accepted step (fused route); 0: they are taken as named. */
+int node_b200_interp_eval(const node_ctl_t* ctl, int dtype, const double* t_out, void* out, int64_t out_stride,
+                          const void* y0, const void* y1, const void* ymid, const void* f0, const void* f1,
+                          int64_t numel, int use_ctl_cur, void* stream);
+
+/* ---- fused route: recognised ODEfunc (model.py:326-348), fp32 NCHW ---------------------- */
+
+/* Bytes of workspace the fused solver needs for a [N,C,H,W] shard. Host function. */
+int64_t node_b200_fused_workspace_bytes(int N, int C, int H, int W);
+
+/* Pre-arrange the live parameters for the kernels: 3xTF32 hi/lo split weight tiles in the
+ * UMMA K-major 128B-swizzled layout, the position-dependent time map Tmap[c,h,w]
+ *  and packed GroupNorm affine terms. Pointers are the reference's own
+ * nn.Parameters (model.py:329-334): conv weights [C, C+1, 3, 3] with the time plane at
+ * input channel 0, biases [C], GroupNorm weight/bias [C]. */
+int node_b200_fused_prepare(void* workspace, int C, int H, int W,
+                            const float* conv1_w, const float* conv1_b, const float* conv2_w, const float* conv2_b,
+                            const float* gn1_w, const float* gn1_b, const float* gn2_w, const float* gn2_b,
+                            const float* gn3_w, const float* gn3_b, float eps, void* stream);
+
+/* One evaluation k = tsign * ODEfunc(tsign * t, y) on a [N,C,H,W] tensor (model.py:339-348);
+ * conv_mode 0 = tcgen05 3xTF32 (fp32 contract), 1 = tcgen05 1xTF32, 2 = SIMT fp32 FFMA. */
+int node_b200_odefunc_forward(void* workspace, const float* y, float t, float tsign, float* k,
+                              int N, int C, int H, int W, int conv_mode, void* stream);
+
+/* Whole forward solve of odeint(func, y0, t, rtol, atol, method='dopri5') for the recognised
+ * ODEfunc (odeint.py:20-76, solvers.py:25-33, dopri5.py:60-122): enqueues f0, the initial-step
+ * probe, and `n_steps_enqueue` attempted steps (each: fused 6-stage step kernel, controller,
+ * dense output); steps after ctl.done are no-ops. Call again with first_call=0 to enqueue more
+ * attempts if the host finds ctl.done == 0. out: [T, N, C, H, W]; out[0] = y0 (solvers.py:27).
+ * global_numel = N_global*C*H*W (differs from the shard's when the batch is sharded).
+ * t_out is a HOST array of T float64 times, strictly increasing; tsign = -1 integrates the
+ * time-reversed system f'(t, y) = -f(-t, y) (misc.py:184-187; the caller negates t). */
+int node_b200_fused_solve(void* workspace, const float* y0, const double* t_out, int T, double rtol, double atol,
+                          int N, int C, int H, int W, int64_t global_numel, float* out, int conv_mode,
+                          int tsign, int first_call, int n_steps_enqueue, void* stream);
+
+/* Multi-GPU stepping: phase 0 = f0 + INIT_A norms, 1 = INIT_A controller + probe + INIT_B norms,
+ * 2 = INIT_B controller, 3 = step kernel + norms, 4 = STEP controller + dense output. Between
+ * phases {0,1,3} and the next one the caller all-reduces node_b200_fused_sums(workspace). */
+int node_b200_fused_phase(void* workspace, int phase, const float* y0, const double* t_out, int T, double rtol,
+                          double atol, int N, int C, int H, int W, int64_t global_numel, float* out,
+                          int conv_mode, int tsign, void* stream);
+double* node_b200_fused_sums(void* workspace);       /* device pointer, 2*NODE_MAX_SEG doubles */
+node_ctl_t* node_b200_fused_ctl(void* workspace);    /* device pointer to the controller block */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NODE_B200_H_ */

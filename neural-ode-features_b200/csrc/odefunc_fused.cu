@@ -1,0 +1,705 @@
+// K1 + fused Runge-Kutta step for the recognised ODE-Net dynamics (reference model.py:326-348):
+//   f(t, x) = GN3( conv2_t( relu(GN2( conv1_t( relu(GN1(x)) ) )) ) )
+// One CTA owns a group of whole images, so GroupNorm statistics and both convolutions are
+// CTA-local and the six dopri5 stages of an attempted step (rk_common.py:49-52) run inside ONE
+// kernel launch with no grid-wide synchronisation; the only cross-image quantity, the error norm
+// (misc.py:146-157), leaves the kernel as one float64 partial per CTA.
+//
+// Convolution = implicit GEMM  D[pixel, cout] = sum_tap A_tap[pixel, cin] * W_tap[cout, cin]:
+//   * A_tap is the GN+ReLU'd activation shifted by the tap (zero outside the image), produced on
+//     the fly from shared memory and written straight into TENSOR MEMORY (tcgen05.st) - with
+//     N = 64 an SS-mode MMA would be shared-memory-bandwidth bound, so A lives in TMEM (TS mode);
+//   * W_tap tiles were pre-split into TF32 hi/lo parts and pre-swizzled (128B, K-major) once per
+//     solve; they stream L2 -> shared memory through the TMA engine (cp.async.bulk + mbarrier) in
+//     a 4-deep ring that runs ahead across conv / stage boundaries;
+//   * tcgen05.mma kind::tf32, M=128 x N=64 x K=8, accumulators in TMEM; the fp32 contract is met
+//     with the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate);
+//   * the time channel is folded into a position dependent bias t*Tmap[c,h,w],
+//     added with the conv bias in the TMEM->shared epilogue.
+// conv_mode 2 swaps the tensor-core engine for a plain fp32 FFMA engine (same kernel family).
+#include "node_common.cuh"
+#include "ptx.cuh"
+
+namespace node {
+
+constexpr int kC = 64;                 // channels of the fused kernels (n_filters=64)
+constexpr int kGroups = 32;            // GroupNorm(min(32, C), C)
+constexpr int kCpg = kC / kGroups;     // channels per group
+constexpr int kFThreads = 256;
+constexpr int kNW = 4;                 // weight ring depth (taps)
+constexpr int kWTileBytes = 2 * 2 * 64 * 128;  // hi/lo x kblock x 64 rows x 128 B = 32 KB per tap
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 128;          // up to two 128-row accumulators of 64 columns
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int kPartialBlocksF = 296;
+constexpr int kMaxGrid = 148;
+
+enum { MODE_F0 = 0, MODE_PROBE = 1, MODE_STEP = 2, MODE_EVAL = 3 };
+
+struct FusedWs {
+  node_ctl_t* ctl; double* sums; int* nonfinite; double* partials; double* t_out;
+  float* wtiles;  // [2 conv][9 tap][hi/lo][2 kblock][64 cout][32 cin] swizzled
+  float* wraw;    // [2][C][C+1][9] copies of the live weights (SIMT engine)
+  float* tmap;    // [2][C][HW]
+  float* bias;    // [2][C]
+  float* gn;      // [3][2][C] gamma, beta
+  float* Y[2]; float* F[2]; float* K[5]; float* YMID;
+};
+
+struct Geo { int N, H, W, HW, G, MT, ngroups; };
+
+struct FusedArgs {
+  FusedWs w; Geo g;
+  int mode, conv_mode;
+  const float* y_in; float* k_out; float* out0;
+  float t_explicit, tsign, eps;
+};
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+constexpr int kMaxT = 1024;
+
+static int64_t ws_layout(void* base, int N, int C, int H, int W, FusedWs* out) {
+  const int64_t E = (int64_t)N * C * H * W;
+  const int64_t HW = (int64_t)H * W;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 1024); return r; };
+  const int64_t o_ctl = take(sizeof(node_ctl_t));
+  const int64_t o_sums = take(sizeof(double) * 2 * NODE_MAX_SEG);
+  const int64_t o_nf = take(sizeof(int));
+  const int64_t o_part = take(sizeof(double) * 2 * NODE_MAX_SEG * kPartialBlocksF);
+  const int64_t o_tout = take(sizeof(double) * kMaxT);
+  const int64_t o_wt = take((int64_t)2 * 9 * kWTileBytes);
+  const int64_t o_wraw = take((int64_t)2 * C * (C + 1) * 9 * 4);
+  const int64_t o_tmap = take((int64_t)2 * C * HW * 4);
+  const int64_t o_bias = take((int64_t)2 * C * 4);
+  const int64_t o_gn = take((int64_t)6 * C * 4);
+  int64_t o_state[10];
+  for (int i = 0; i < 10; ++i) o_state[i] = take(E * 4);
+  if (out != nullptr) {
+    char* b = (char*)base;
+    out->ctl = (node_ctl_t*)(b + o_ctl); out->sums = (double*)(b + o_sums); out->nonfinite = (int*)(b + o_nf);
+    out->partials = (double*)(b + o_part); out->t_out = (double*)(b + o_tout);
+    out->wtiles = (float*)(b + o_wt); out->wraw = (float*)(b + o_wraw); out->tmap = (float*)(b + o_tmap);
+    out->bias = (float*)(b + o_bias); out->gn = (float*)(b + o_gn);
+    out->Y[0] = (float*)(b + o_state[0]); out->Y[1] = (float*)(b + o_state[1]);
+    out->F[0] = (float*)(b + o_state[2]); out->F[1] = (float*)(b + o_state[3]);
+    for (int i = 0; i < 5; ++i) out->K[i] = (float*)(b + o_state[4 + i]);
+    out->YMID = (float*)(b + o_state[9]);
+  }
+  return o;
+}
+
+static bool make_geo(int N, int C, int H, int W, Geo* g) {
+  if (C != kC || N < 1 || H < 1 || W < 1) return false;
+  const int HW = H * W;
+  if (HW > 256) return false;
+  g->N = N; g->H = H; g->W = W; g->HW = HW;
+  g->G = HW <= 128 ? 128 / HW : 1;
+  g->MT = (g->G * HW + 127) / 128;
+  g->ngroups = (N + g->G - 1) / g->G;
+  return true;
+}
+
+// ---- parameter preparation -------------------------------------------------------------------
+__global__ void k_prepare(FusedWs w, int H, int W, const float* c1w, const float* c1b, const float* c2w, const float* c2b,
+                          const float* g1w, const float* g1b, const float* g2w, const float* g2b, const float* g3w,
+                          const float* g3b) {
+  const int HW = H * W;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const float* cw[2] = {c1w, c2w};
+  const float* cb[2] = {c1b, c2b};
+  // weight tiles: hi = rna_tf32(w), lo = w - hi; K-major rows of 32 cin (128 B), 16-byte chunks XOR-swizzled by row%8
+  for (int i = tid; i < 2 * 9 * 2 * 2 * 64 * 32; i += nth) {
+    int r = i;
+    const int j = r % 32; r /= 32;
+    const int co = r % 64; r /= 64;
+    const int kb = r % 2; r /= 2;
+    const int part = r % 2; r /= 2;
+    const int tap = r % 9; r /= 9;
+    const int cv = r;
+    const int cin = kb * 32 + j;
+    const float v = cw[cv][((int64_t)co * (kC + 1) + cin + 1) * 9 + tap];
+    const float hi = __uint_as_float(ptx::tf32_rna(v));
+    const float val = part ? (v - hi) : hi;
+    const int chunk = (j >> 2) ^ (co & 7);
+    const int64_t dst = ((((int64_t)(cv * 9 + tap) * 2 + part) * 2 + kb) * 64 + co) * 32 + chunk * 4 + (j & 3);
+    w.wtiles[dst] = val;
+  }
+  for (int i = tid; i < 2 * kC * (kC + 1) * 9; i += nth) {
+    const int cv = i / (kC * (kC + 1) * 9);
+    w.wraw[i] = cw[cv][i - cv * kC * (kC + 1) * 9];
+  }
+  // Tmap[c,h,w] = sum over taps that stay inside the (zero padded) image of W[c, 0, tap]
+  for (int i = tid; i < 2 * kC * HW; i += nth) {
+    const int p = i % HW, co = (i / HW) % kC, cv = i / (HW * kC);
+    const int h = p / W, x = p % W;
+    float s = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, xx = x + tap % 3 - 1;
+      if (hh >= 0 && hh < H && xx >= 0 && xx < W) s += cw[cv][((int64_t)co * (kC + 1)) * 9 + tap];
+    }
+    w.tmap[i] = s;
+  }
+  for (int i = tid; i < 2 * kC; i += nth) w.bias[i] = cb[i / kC][i % kC];
+  const float* gp[6] = {g1w, g1b, g2w, g2b, g3w, g3b};
+  for (int i = tid; i < 6 * kC; i += nth) w.gn[i] = gp[i / kC][i % kC];
+}
+
+// ---- device pieces of the fused kernel -----------------------------------------------------------
+struct Smem {
+  uint32_t wslot;      // shared address of weight ring (tc engine)
+  float* zbuf;         // [G][C][HW] activations / conv output
+  float* zpad;         // SIMT engine: zero padded copy [G][C][(H+2)(W+2)]
+  uint32_t bar_w;      // kNW mbarriers (8 B each)
+  uint32_t bar_mma;    // 2 mbarriers
+  double* scratch;     // 32 doubles
+  float* coef;         // [8][8] h*coefficient table
+  uint32_t* tmem_slot;
+};
+
+struct Pipe {          // uniform across the CTA
+  uint32_t g_item, g_tap, w_issued, w_total, tmem;
+  bool timeout;
+};
+
+// GroupNorm over (image, group) cells of kCpg*HW contiguous floats + affine (+ReLU), in place.
+__device__ __forceinline__ void gn_apply(float* z, int gact, int HW, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, bool relu, float sign) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = kCpg * HW;
+  const float inv_n = 1.0f / (float)n;
+  for (int cell = warp; cell < gact * kGroups; cell += kFThreads / 32) {
+    float* p = z + (int64_t)cell * n;
+    const int c0 = (cell % kGroups) * kCpg;
+    float v[16];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = lane + 32 * u;
+      v[u] = i < n ? p[i] : 0.f;
+      s += v[u];
+    }
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = lane + 32 * u;
+      const float d = i < n ? v[u] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float var = warp_sum(q) * inv_n;
+    const float rstd = 1.0f / sqrtf(var + eps);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int i = lane + 32 * u;
+      if (i < n) {
+        const int c = c0 + i / HW;
+        const float a = rstd * gamma[c];
+        const float b = beta[c] - a * mean;
+        float r = fmaf(v[u], a, b);
+        if (relu) r = fmaxf(r, 0.f);
+        p[i] = r * sign;
+      }
+    }
+  }
+}
+
+// fp32 FFMA engine: z <- conv3x3(z) + bias + t*Tmap, via a zero padded copy.
+__device__ void conv_simt(const Smem& sm, const Geo& g, int gact, const float* __restrict__ wraw,
+                          const float* __restrict__ bias, const float* __restrict__ tmap, float t) {
+  const int tid = threadIdx.x;
+  const int PW = g.W + 2, PHW = (g.H + 2) * PW, HW = g.HW;
+  const int rows = gact * HW;
+  for (int i = tid; i < gact * kC * PHW; i += kFThreads) sm.zpad[i] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < gact * kC * HW; i += kFThreads) {
+    const int p = i % HW, ic = i / HW;
+    sm.zpad[ic * PHW + (p / g.W + 1) * PW + (p % g.W + 1)] = sm.zbuf[i];
+  }
+  __syncthreads();
+  const int co0 = (tid >> 4) * 4, pl = tid & 15;
+  int off[16];
+  float acc[16][4];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int m = pl + 16 * u;
+    const int mm = m < rows ? m : 0;
+    const int img = mm / HW, p = mm % HW;
+    off[u] = img * kC * PHW + (p / g.W + 1) * PW + (p % g.W + 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
+  }
+  for (int ci = 0; ci < kC; ++ci) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int toff = ci * PHW + (tap / 3 - 1) * PW + (tap % 3 - 1);
+      float wv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wv[q] = wraw[((co0 + q) * (kC + 1) + ci + 1) * 9 + tap];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float v = sm.zpad[off[u] + toff];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[u][q] = fmaf(v, wv[q], acc[u][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int m = pl + 16 * u;
+    if (m < rows) {
+      const int img = m / HW, p = m % HW;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = co0 + q;
+        sm.zbuf[(img * kC + co) * HW + p] = acc[u][q] + fmaf(t, tmap[co * HW + p], bias[co]);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Thread 0: keep the weight ring `ahead` taps ahead of the consumer. Ring slot x&3 of tap x was last
+// read by the MMAs of tap x-4, which are known complete once tap (x-2)'s predecessor wait passed.
+__device__ __forceinline__ void issue_weights(const Smem& sm, Pipe& pp, const float* __restrict__ wtiles, uint32_t upto) {
+  while (pp.w_issued <= upto && pp.w_issued < pp.w_total) {
+    const uint32_t x = pp.w_issued;
+    const uint32_t bar = sm.bar_w + 8 * (x & (kNW - 1));
+    ptx::mbar_expect_tx(bar, kWTileBytes);
+    ptx::bulk_g2s(sm.wslot + (x & (kNW - 1)) * kWTileBytes, (const char*)wtiles + (size_t)(x % 18) * kWTileBytes, kWTileBytes, bar);
+    ++pp.w_issued;
+  }
+}
+
+// tcgen05 engine: z <- conv3x3(z) + bias + t*Tmap.
+__device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const float* __restrict__ wtiles,
+                        const float* __restrict__ bias, const float* __restrict__ tmap, float t, bool split3) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int HW = g.HW, rows = gact * HW;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    for (int mt = 0; mt < g.MT; ++mt) {
+      // the A stage (and, two taps back, a weight slot) is free once the MMAs of item-2 completed
+      if (pp.g_item >= 2) {
+        if (!ptx::mbar_wait(sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1)) pp.timeout = true;
+      }
+      ptx::tc_fence_after();
+      if (mt == 0 && tid == 0) issue_weights(sm, pp, wtiles, pp.g_tap + 2);
+      __syncwarp();
+      // ---- build A_tap rows [mt*128, mt*128+128) in tensor memory
+      const int m = mt * 128 + q * 32 + lane;
+      bool valid = m < rows;
+      const int mm = valid ? m : 0;
+      const int img = mm / HW, p = mm % HW;
+      const int hh = p / g.W + dy, xx = p % g.W + dx;
+      valid = valid && hh >= 0 && hh < g.H && xx >= 0 && xx < g.W;
+      const float* src = sm.zbuf + (img * kC + hf * 32) * HW + (valid ? hh * g.W + xx : 0);
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = valid ? src[j * HW] : 0.f;
+        hi[j] = ptx::tf32_rna(v);
+        lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
+      }
+      const uint32_t colbase = kAccCols + (pp.g_item & 1) * 128;
+      const uint32_t taddr = pp.tmem + ((uint32_t)(q * 32) << 16) + colbase + hf * 32;
+      ptx::tmem_st32(taddr, hi);
+      if (split3) ptx::tmem_st32(taddr + 64, lo);
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t slot = pp.g_tap & (kNW - 1);
+        if (mt == 0) {
+          if (!ptx::mbar_wait(sm.bar_w + 8 * slot, (pp.g_tap / kNW) & 1)) pp.timeout = true;
+        }
+        ptx::tc_fence_after();
+        const uint32_t d = pp.tmem + mt * 64;
+        const uint32_t wbase = sm.wslot + slot * kWTileBytes;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t a_hi = pp.tmem + colbase + kb * 32 + ks * 8;
+            const uint64_t b_hi = ptx::make_desc_sw128(wbase + kb * 8192 + ks * 32);
+            const uint32_t first = (tap == 0 && kb == 0 && ks == 0) ? 0u : 1u;
+            if (split3) {
+              const uint64_t b_lo = ptx::make_desc_sw128(wbase + 16384 + kb * 8192 + ks * 32);
+              ptx::mma_tf32_ts(d, a_hi + 64, b_hi, kIdesc, first);
+              ptx::mma_tf32_ts(d, a_hi, b_lo, kIdesc, 1u);
+              ptx::mma_tf32_ts(d, a_hi, b_hi, kIdesc, 1u);
+            } else {
+              ptx::mma_tf32_ts(d, a_hi, b_hi, kIdesc, first);
+            }
+          }
+        }
+        ptx::tc_commit(sm.bar_mma + 8 * (pp.g_item & 1));
+      }
+      __syncwarp();
+      ++pp.g_item;
+    }
+    ++pp.g_tap;
+  }
+  // accumulators complete when the last item's commit lands
+  {
+    const uint32_t last = pp.g_item - 1;
+    if (!ptx::mbar_wait(sm.bar_mma + 8 * (last & 1), (last >> 1) & 1)) pp.timeout = true;
+  }
+  ptx::tc_fence_after();
+  // ---- epilogue: TMEM -> (+bias + t*Tmap) -> shared, [img][cout][pixel]
+  for (int mt = 0; mt < g.MT; ++mt) {
+    const int m = mt * 128 + q * 32 + lane;
+    uint32_t v[32];
+    ptx::tmem_ld32(pp.tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + hf * 32, v);
+    ptx::tc_wait_ld();
+    if (m < rows) {
+      const int img = m / HW, p = m % HW;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int co = hf * 32 + j;
+        sm.zbuf[(img * kC + co) * HW + p] = __uint_as_float(v[j]) + fmaf(t, tmap[co * HW + p], bias[co]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFThreads, 1) k_fused(const FusedArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  using A = Arith<float>;
+  const Geo g = a.g;
+  const FusedWs& w = a.w;
+  const int tid = threadIdx.x;
+  const bool tc = a.conv_mode != 2;
+  node_ctl_t* ctl = w.ctl;
+
+  if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform: partials keep their last (unused) values
+
+  // ---- carve shared memory
+  Smem sm;
+  {
+    const uint32_t s0 = ptx::smem_u32(smem_raw);
+    const uint32_t al = (s0 + 1023u) & ~1023u;
+    uint8_t* base = smem_raw + (al - s0);
+    size_t o = 0;
+    sm.wslot = al;
+    if (tc) o += (size_t)kNW * kWTileBytes;
+    sm.zbuf = reinterpret_cast<float*>(base + o);
+    o += (size_t)g.G * kC * g.HW * 4;
+    sm.zpad = reinterpret_cast<float*>(base + o);
+    if (!tc) o += (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
+    o = (o + 15) & ~(size_t)15;
+    sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
+    sm.coef = reinterpret_cast<float*>(base + o); o += 64 * 4;
+    sm.bar_w = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_mma = al + (uint32_t)o; o += 16;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
+  }
+
+  const int my_groups = (int)blockIdx.x < g.ngroups ? (g.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nevals = a.mode == MODE_STEP ? 6 : 1;
+  Pipe pp;
+  pp.g_item = 0; pp.g_tap = 0; pp.w_issued = 0; pp.w_total = (uint32_t)(my_groups * nevals * 18); pp.tmem = 0; pp.timeout = false;
+
+  if (tc) {
+    if (tid == 0) {
+      for (int i = 0; i < kNW; ++i) ptx::mbar_init(sm.bar_w + 8 * i, 1);
+      ptx::mbar_init(sm.bar_mma, 1);
+      ptx::mbar_init(sm.bar_mma + 8, 1);
+      ptx::fence_mbar_init();
+    }
+    if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    pp.tmem = *sm.tmem_slot;
+  }
+
+  // ---- h * coefficient table: rows 0..5 stage betas, 6 = C_MID, 7 = C_ERR (misc.py:22-25: (h*c)*k)
+  const float h = a.mode == MODE_STEP ? ctl->h32 : (a.mode == MODE_PROBE ? ctl->h0_32 : 0.f);
+  if (tid < 64) {
+    const int r = tid >> 3, j = tid & 7;
+    double c = 0.0;
+    if (r < 7) c = j < 7 ? kCoef(r, j) : 0.0; else c = j < 7 ? kCErr(j) : 0.0;
+    sm.coef[tid] = A::mul(h, (float)c);
+  }
+  __syncthreads();
+
+  const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
+  float* Ycur = w.Y[cur]; float* Ynew = w.Y[cur ^ 1];
+  float* Fcur = w.F[cur]; float* Fnew = w.F[cur ^ 1];
+  const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
+  const int64_t img_elems = (int64_t)kC * g.HW;
+  double acc0 = 0.0, acc1 = 0.0;
+  bool bad = false;
+
+  for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+    const int img0 = grp * g.G;
+    const int gact = min(g.G, g.N - img0);
+    const int64_t gbase = (int64_t)img0 * img_elems;
+    const int cnt = gact * (int)img_elems;
+
+    for (int ev = 0; ev < nevals; ++ev) {
+      // ---- prologue: stage input into shared memory (rk_common.py:49-51)
+      if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
+        for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
+          const float4 y = *reinterpret_cast<const float4*>(a.y_in + gbase + i);
+          *reinterpret_cast<float4*>(sm.zbuf + i) = y;
+          if (a.mode == MODE_F0) {
+            *reinterpret_cast<float4*>(Ycur + gbase + i) = y;
+            if (a.out0 != nullptr) *reinterpret_cast<float4*>(a.out0 + gbase + i) = y;
+          }
+        }
+      } else {
+        const int row = a.mode == MODE_PROBE ? 7 : ev;
+        const int nk = a.mode == MODE_PROBE ? 1 : ev + 1;
+        const float* cf = a.mode == MODE_PROBE ? nullptr : sm.coef + row * 8;
+        for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
+          float y[4], s[4] = {0.f, 0.f, 0.f, 0.f}, kv[4];
+          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Ycur + gbase + i);
+          for (int j = 0; j < nk; ++j) {
+            if (j == 1 && row == 5) continue;            // beta_62 == 0
+            const float hc = cf ? cf[j] : h;             // probe: y0 + h0*f0 (misc.py:133)
+            const float* src = j == 0 ? Fcur : w.K[j - 1];
+            *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>(src + gbase + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[e] = A::add(s[e], A::mul(hc, kv[e]));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) y[e] = A::add(y[e], s[e]);
+          *reinterpret_cast<float4*>(sm.zbuf + i) = *reinterpret_cast<float4*>(y);
+          if (a.mode == MODE_STEP && ev == 5) *reinterpret_cast<float4*>(Ynew + gbase + i) = *reinterpret_cast<float4*>(y);
+        }
+      }
+      __syncthreads();
+
+      // ---- the dynamics (model.py:339-348)
+      const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
+      const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
+      gn_apply(sm.zbuf, gact, g.HW, w.gn + 0 * kC, w.gn + 1 * kC, a.eps, true, 1.f);
+      __syncthreads();
+      for (int cv = 0; cv < 2; ++cv) {
+        if (tc) conv_tc(sm, pp, g, gact, w.wtiles, w.bias + cv * kC, w.tmap + (int64_t)cv * kC * g.HW, t, a.conv_mode == 0);
+        else conv_simt(sm, g, gact, w.wraw + (int64_t)cv * kC * (kC + 1) * 9, w.bias + cv * kC, w.tmap + (int64_t)cv * kC * g.HW, t);
+        gn_apply(sm.zbuf, gact, g.HW, w.gn + (2 * cv + 2) * kC, w.gn + (2 * cv + 3) * kC, a.eps, cv == 0, cv == 0 ? 1.f : a.tsign);
+        __syncthreads();
+      }
+
+      // ---- k_{ev+2} -> global
+      float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : Fnew) : (a.mode == MODE_F0 ? Fcur : (a.mode == MODE_EVAL ? a.k_out : nullptr));
+      if (kdst != nullptr) {
+        for (int i = tid * 4; i < cnt; i += kFThreads * 4)
+          *reinterpret_cast<float4*>(kdst + gbase + i) = *reinterpret_cast<const float4*>(sm.zbuf + i);
+      }
+      __syncthreads();
+    }
+
+    // ---- per-group epilogues: norms that feed the controller
+    if (a.mode == MODE_F0) {               // misc.py:121-126
+      for (int i = tid; i < cnt; i += kFThreads) {
+        const float y = a.y_in[gbase + i];
+        const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+        const float u = A::div(y, scale), v = A::div(sm.zbuf[i], scale);
+        acc0 += (double)A::mul(u, u);
+        acc1 += (double)A::mul(v, v);
+      }
+    } else if (a.mode == MODE_PROBE) {     // misc.py:136
+      for (int i = tid; i < cnt; i += kFThreads) {
+        const float y = Ycur[gbase + i];
+        const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+        const float u = A::div(A::sub(sm.zbuf[i], Fcur[gbase + i]), scale);
+        acc0 += (double)A::mul(u, u);
+      }
+    } else if (a.mode == MODE_STEP) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
+      const float* ce = sm.coef + 7 * 8;
+      const float* cm = sm.coef + 6 * 8;
+      for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
+        float y0[4], y1[4], kv[4], e[4] = {0.f, 0.f, 0.f, 0.f}, md[4] = {0.f, 0.f, 0.f, 0.f};
+        *reinterpret_cast<float4*>(y0) = *reinterpret_cast<const float4*>(Ycur + gbase + i);
+        *reinterpret_cast<float4*>(y1) = *reinterpret_cast<const float4*>(Ynew + gbase + i);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          if (j == 1) continue;
+          if (j == 6) *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>(sm.zbuf + i);
+          else *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>((j == 0 ? Fcur : w.K[j - 1]) + gbase + i);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            e[u] = A::add(e[u], A::mul(ce[j], kv[u]));
+            md[u] = A::add(md[u], A::mul(cm[j], kv[u]));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          bad |= !isfinite(y0[u]);
+          const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0[u]), fabsf(y1[u]))));
+          const float qv = A::div(e[u], tol);
+          acc0 += (double)A::mul(qv, qv);
+          md[u] = A::add(y0[u], md[u]);
+        }
+        *reinterpret_cast<float4*>(w.YMID + gbase + i) = *reinterpret_cast<float4*>(md);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (a.mode != MODE_EVAL) {
+    if (bad) atomicOr(w.nonfinite, 1);
+    const double r0 = block_sum(acc0, sm.scratch);
+    const double r1 = block_sum(acc1, sm.scratch);
+    if (tid == 0) {
+      w.partials[blockIdx.x] = r0;
+      w.partials[kPartialBlocksF + blockIdx.x] = r1;
+    }
+  }
+  if (pp.timeout && tid == 0) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
+  if (tc) {
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid < 32) ptx::tmem_dealloc(pp.tmem, kTmemCols);
+  }
+}
+
+// controller wrapper that first folds the fused kernel's per-CTA partials in a fixed order
+__global__ void k_fold_partials(const double* __restrict__ partials, double* __restrict__ sums, int* nonfinite_keep) {
+  const int row = blockIdx.x;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < kPartialBlocksF; b += 32) v += partials[(int64_t)row * kPartialBlocksF + b];
+  v = warp_sum(v);
+  if (threadIdx.x == 0) sums[row] = v;
+  (void)nonfinite_keep;
+}
+
+static size_t fused_smem_bytes(const Geo& g, int conv_mode) {
+  size_t o = 1024;
+  if (conv_mode != 2) o += (size_t)kNW * kWTileBytes;
+  o += (size_t)g.G * kC * g.HW * 4;
+  if (conv_mode == 2) o += (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
+  o += 16 + 32 * 8 + 64 * 4 + 8 * kNW + 16 + 16;
+  return o;
+}
+
+static int launch_fused(const FusedArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NODE_CUDA_OK(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = fused_smem_bytes(a.g, a.conv_mode);
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  const int grid = a.g.ngroups < kMaxGrid ? a.g.ngroups : kMaxGrid;
+  k_fused<<<grid, kFThreads, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace node
+
+using namespace node;
+
+extern "C" int node_b200_controller(node_ctl_t* ctl, int mode, const double* sums, const int* nonfinite_flag,
+                                    const double* t_out, void* stream);
+extern "C" int node_b200_interp_eval(const node_ctl_t* ctl, int dtype, const double* t_out, void* out, int64_t out_stride,
+                                     const void* y0, const void* y1, const void* ymid, const void* f0, const void* f1,
+                                     int64_t numel, int use_ctl_cur, void* stream);
+extern "C" int node_b200_ctl_init(node_ctl_t* ctl, int dtype, int n_seg, const double* rtol, const double* atol,
+                                  const int64_t* seg_numel, double safety, double ifactor, double dfactor, double expo,
+                                  int max_num_steps, int n_out, int tsign, void* stream);
+
+extern "C" int64_t node_b200_fused_workspace_bytes(int N, int C, int H, int W) {
+  Geo g;
+  if (!make_geo(N, C, H, W, &g)) return -1;
+  return ws_layout(nullptr, N, C, H, W, nullptr);
+}
+
+extern "C" int node_b200_fused_prepare(void* workspace, int C, int H, int W, const float* c1w, const float* c1b,
+                                       const float* c2w, const float* c2b, const float* g1w, const float* g1b,
+                                       const float* g2w, const float* g2b, const float* g3w, const float* g3b,
+                                       float eps, void* stream) {
+  Geo g;
+  if (!make_geo(1, C, H, W, &g)) return (int)cudaErrorInvalidValue;
+  FusedWs w;
+  ws_layout(workspace, 1, C, H, W, &w);   // the parameter region does not depend on N
+  (void)eps;
+  k_prepare<<<148, 256, 0, (cudaStream_t)stream>>>(w, H, W, c1w, c1b, c2w, c2b, g1w, g1b, g2w, g2b, g3w, g3b);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int node_b200_odefunc_forward(void* workspace, const float* y, float t, float tsign, float* k, int N, int C,
+                                         int H, int W, int conv_mode, void* stream) {
+  FusedArgs a{};
+  if (!make_geo(N, C, H, W, &a.g)) return (int)cudaErrorInvalidValue;
+  ws_layout(workspace, N, C, H, W, &a.w);
+  a.mode = MODE_EVAL; a.conv_mode = conv_mode; a.y_in = y; a.k_out = k; a.t_explicit = t; a.tsign = tsign; a.eps = 1e-5f;
+  return launch_fused(a, (cudaStream_t)stream);
+}
+
+extern "C" double* node_b200_fused_sums(void* workspace) {
+  FusedWs w; ws_layout(workspace, 1, kC, 1, 4, &w); return w.sums;
+}
+extern "C" node_ctl_t* node_b200_fused_ctl(void* workspace) {
+  FusedWs w; ws_layout(workspace, 1, kC, 1, 4, &w); return w.ctl;
+}
+
+// phases: 0 = f0 (+INIT_A norms), 1 = INIT_A controller + probe (+INIT_B norms), 2 = INIT_B controller,
+//         3 = step kernel (+error norm), 4 = STEP controller + dense output.
+extern "C" int node_b200_fused_phase(void* workspace, int phase, const float* y0, const double* t_host, int T, double rtol,
+                                     double atol, int N, int C, int H, int W, int64_t global_numel, float* out,
+                                     int conv_mode, int tsign, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  FusedArgs a{};
+  if (!make_geo(N, C, H, W, &a.g) || T < 1 || T > kMaxT) return (int)cudaErrorInvalidValue;
+  ws_layout(workspace, N, C, H, W, &a.w);
+  const int64_t E = (int64_t)N * C * H * W;
+  a.conv_mode = conv_mode; a.eps = 1e-5f; a.tsign = tsign < 0 ? -1.f : 1.f;
+  const int nrows = 2;
+  switch (phase) {
+    case 0: {
+      const int64_t ne[1] = {global_numel};
+      const double rt[1] = {rtol}, at[1] = {atol};
+      NODE_CUDA_OK((cudaError_t)node_b200_ctl_init(a.w.ctl, NODE_F32, 1, rt, at, ne, (double)0.9f, 10.0, (double)0.2f, (double)0.2f, 2147483647, T, 1, stream));
+      NODE_CUDA_OK(cudaMemcpyAsync(a.w.t_out, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+      NODE_CUDA_OK(cudaMemsetAsync(a.w.partials, 0, sizeof(double) * 2 * NODE_MAX_SEG * kPartialBlocksF, st));
+      NODE_CUDA_OK(cudaMemsetAsync(a.w.nonfinite, 0, sizeof(int), st));
+      a.mode = MODE_F0; a.y_in = y0; a.out0 = out; a.t_explicit = (float)t_host[0];
+      NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
+      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
+      return (int)cudaGetLastError();
+    }
+    case 1: {
+      NODE_CUDA_OK((cudaError_t)node_b200_controller(a.w.ctl, 0, a.w.sums, nullptr, a.w.t_out, stream));
+      a.mode = MODE_PROBE;
+      NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
+      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
+      return (int)cudaGetLastError();
+    }
+    case 2:
+      return node_b200_controller(a.w.ctl, 1, a.w.sums, nullptr, a.w.t_out, stream);
+    case 3: {
+      a.mode = MODE_STEP;
+      NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
+      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
+      return (int)cudaGetLastError();
+    }
+    case 4: {
+      NODE_CUDA_OK((cudaError_t)node_b200_controller(a.w.ctl, 2, a.w.sums, a.w.nonfinite, a.w.t_out, stream));
+      return node_b200_interp_eval(a.w.ctl, NODE_F32, a.w.t_out, out, E, a.w.Y[0], a.w.Y[1], a.w.YMID, a.w.F[0], a.w.F[1], E, 1, stream);
+    }
+    default:
+      return (int)cudaErrorInvalidValue;
+  }
+}
+
+extern "C" int node_b200_fused_solve(void* workspace, const float* y0, const double* t_host, int T, double rtol, double atol,
+                                     int N, int C, int H, int W, int64_t global_numel, float* out, int conv_mode,
+                                     int tsign, int first_call, int n_steps_enqueue, void* stream) {
+  if (first_call) {
+    for (int ph = 0; ph < 3; ++ph)
+      NODE_CUDA_OK((cudaError_t)node_b200_fused_phase(workspace, ph, y0, t_host, T, rtol, atol, N, C, H, W, global_numel, out, conv_mode, tsign, stream));
+  }
+  for (int s = 0; s < n_steps_enqueue; ++s) {
+    NODE_CUDA_OK((cudaError_t)node_b200_fused_phase(workspace, 3, y0, t_host, T, rtol, atol, N, C, H, W, global_numel, out, conv_mode, tsign, stream));
+    NODE_CUDA_OK((cudaError_t)node_b200_fused_phase(workspace, 4, y0, t_host, T, rtol, atol, N, C, H, W, global_numel, out, conv_mode, tsign, stream));
+  }
+  return 0;
+}

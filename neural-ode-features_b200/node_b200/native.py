@@ -1,0 +1,160 @@
+"""ctypes binding of libnode_b200.so (the C ABI declared in include/node_b200.h).
+
+There is no fallback: if the shared library is missing, stale (ABI mismatch) or the tensors are
+not on a CUDA device, the solver raises.  Build with `python __graft_entry__.py build` (or
+`python -c "import __graft_entry__ as g; g.build()"`) - nvcc cross-compiles for sm_100a.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libnode_b200.so')
+ABI_VERSION = 1
+
+F32, F64 = 0, 1
+ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_INTERP_RANGE, ST_WATCHDOG = 1, 2, 4, 8, 16
+
+# order of the values returned by node_b200_ctl_layout (csrc/rk_kernels.cu)
+CTL_FIELDS = (
+    'sizeof', 'partial_blocks', 'max_seg', 'max_trace',
+    't0', 't1', 'dt', 'ratio', 'ts64', 'ts32', 'h64', 'h32', 'out_lo', 'out_hi', 'next_out',
+    'n_attempt', 'n_accept', 'n_reject', 'nfe', 'status', 'done', 'cur', 'accepted_last',
+    'tr_t', 'tr_dt', 'tr_ratio', 'tr_acc', 'h0', 'h0_32', 'it_t0', 'it_t1',
+)
+
+EXPORTS = (
+    'node_b200_abi_version', 'node_b200_ctl_layout', 'node_b200_ctl_init', 'node_b200_rk_stage_combine',
+    'node_b200_rk_error_norm', 'node_b200_init_norms', 'node_b200_reduce_partials', 'node_b200_controller',
+    'node_b200_interp_eval', 'node_b200_fused_workspace_bytes', 'node_b200_fused_prepare',
+    'node_b200_odefunc_forward', 'node_b200_fused_solve', 'node_b200_fused_phase', 'node_b200_fused_sums',
+    'node_b200_fused_ctl',
+)
+
+_lib = None
+_layout = None
+
+_vp, _i, _i64, _d, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_float
+
+
+def _declare(lib):
+    lib.node_b200_abi_version.restype = _i
+    lib.node_b200_ctl_layout.argtypes = [_vp, _i]
+    lib.node_b200_ctl_init.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _d, _d, _d, _d, _i, _i, _i, _vp]
+    lib.node_b200_rk_stage_combine.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _i, _i64, _vp]
+    lib.node_b200_rk_error_norm.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]
+    lib.node_b200_init_norms.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]
+    lib.node_b200_reduce_partials.argtypes = [_vp, _i, _vp, _vp]
+    lib.node_b200_controller.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+    lib.node_b200_interp_eval.argtypes = [_vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]
+    lib.node_b200_fused_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.node_b200_fused_workspace_bytes.restype = _i64
+    lib.node_b200_fused_prepare.argtypes = [_vp, _i, _i, _i] + [_vp] * 10 + [_f, _vp]
+    lib.node_b200_odefunc_forward.argtypes = [_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _vp]
+    lib.node_b200_fused_solve.argtypes = [_vp, _vp, _vp, _i, _d, _d, _i, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_fused_phase.argtypes = [_vp, _i, _vp, _vp, _i, _d, _d, _i, _i, _i, _i, _i64, _vp, _i, _i, _vp]
+    lib.node_b200_fused_sums.argtypes = [_vp]
+    lib.node_b200_fused_sums.restype = _vp
+    lib.node_b200_fused_ctl.argtypes = [_vp]
+    lib.node_b200_fused_ctl.restype = _vp
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it cannot serve."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'node_b200: native library %s is missing. There is no CPU or PyTorch fallback for the '
+                'dopri5 hot path; build it with `python __graft_entry__.py build`.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        missing = [n for n in EXPORTS if not hasattr(handle, n)]
+        if missing:
+            raise RuntimeError('node_b200: %s lacks symbols %s - rebuild it' % (LIB_PATH, missing))
+        _declare(handle)
+        if handle.node_b200_abi_version() != ABI_VERSION:
+            raise RuntimeError('node_b200: ABI mismatch - rebuild %s' % LIB_PATH)
+        _lib = handle
+    return _lib
+
+
+def layout():
+    global _layout
+    if _layout is None:
+        buf = (ctypes.c_int64 * 64)()
+        n = lib().node_b200_ctl_layout(ctypes.cast(buf, _vp), 64)
+        assert n == len(CTL_FIELDS), 'ctl layout mismatch between native.py and rk_kernels.cu'
+        _layout = dict(zip(CTL_FIELDS, list(buf)[:n]))
+    return _layout
+
+
+def check(err, what):
+    if err != 0:
+        raise RuntimeError('node_b200: %s failed with CUDA error %d' % (what, err))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def host_f64(values):
+    return np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+
+
+def host_i64(values):
+    return np.ascontiguousarray(np.asarray(values, dtype=np.int64))
+
+
+def np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class CtlView(object):
+    """Host snapshot of the device controller block (one D2H copy + sync)."""
+
+    def __init__(self, ctl_dev_u8):
+        self.raw = ctl_dev_u8.cpu().numpy()
+        self.L = layout()
+
+    def _get(self, name, dtype, count=1):
+        off = self.L[name]
+        v = np.frombuffer(self.raw, dtype=dtype, count=count, offset=off)
+        return v if count > 1 else v[0].item()
+
+    def i32(self, name):
+        return self._get(name, np.int32)
+
+    def f64(self, name, count=1):
+        return self._get(name, np.float64, count)
+
+    def trace(self):
+        n = min(self.i32('n_attempt'), self.L['max_trace'])
+        return dict(
+            t=self.f64('tr_t', self.L['max_trace'])[:n].copy(),
+            dt=self.f64('tr_dt', self.L['max_trace'])[:n].copy(),
+            ratio=self.f64('tr_ratio', self.L['max_trace'])[:n].copy(),
+            accepted=self._get('tr_acc', np.int32, self.L['max_trace'])[:n].astype(bool),
+        )
+
+
+def raise_for_status(status):
+    """Same exception type and wording as the reference's asserts (dopri5.py:89,100,102; interp.py:58)."""
+    if status == 0:
+        return
+    if status & ST_WATCHDOG:
+        raise RuntimeError('node_b200: an in-kernel barrier wait timed out (status %d)' % status)
+    if status & ST_DT_UNDERFLOW:
+        raise AssertionError('underflow in dt')
+    if status & ST_NONFINITE:
+        raise AssertionError('non-finite values in state `y`')
+    if status & ST_MAX_STEPS:
+        raise AssertionError('max_num_steps exceeded')
+    if status & ST_INTERP_RANGE:
+        raise AssertionError('invalid interpolation, fails `t0 <= t <= t1`')
+    raise AssertionError('solver failed with status %d' % status)

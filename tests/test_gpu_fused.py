@@ -1,0 +1,146 @@
+"""GPU: the fused sm_100a route (recognised ODEfunc) against the reference's golden vectors -
+identical NFE and accept/reject sequence, dt trace to 1e-5, outputs to 1e-4 relative (BASELINE
+north_star), top-1 identical - through the reference-facing API (ODENet / ODEBlock / odeint)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_odefunc, odefunc_params
+from oracle import dopri5_port, odefunc_port
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL_OUT = 1e-4          # fp32 contract of BASELINE.json north_star
+CASES = ['cifar_res_n8', 'cifar_res_n7_tol1e-4', 'mnist_conv_n9', 'mnist_res_n5', 'cifar_oneshot_n3', 'mnist_oneshot_n3']
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('name', CASES)
+def test_fused_dynamics_kernel(native_lib, golden, monkeypatch, name, mode):
+    from node_b200 import solver
+    monkeypatch.setenv('NODE_B200_CONV', mode)
+    g = golden(name)
+    func = load_odefunc(g, DEV)
+    h0 = torch.from_numpy(g['h0']).to(DEV)
+    k = solver.odefunc_forward(func, 0.37, h0)
+    torch.cuda.synchronize()
+    assert rel(k.cpu(), torch.from_numpy(g['f037'])) < 2e-5
+    # reversed-time wrapper: -f(-t, y)
+    p = odefunc_params(g)
+    kr = solver.odefunc_forward(func, 0.25, h0, tsign=-1.0)
+    ref = -odefunc_port.odefunc_forward(p, torch.tensor(-0.25), torch.from_numpy(g['h0']))
+    assert rel(kr.cpu(), ref) < 2e-5
+
+
+def test_tf32_single_pass_mode_is_reported_separately(native_lib, golden, monkeypatch):
+    from node_b200 import solver
+    monkeypatch.setenv('NODE_B200_CONV', 'tf32')
+    g = golden('cifar_res_n8')
+    k = solver.odefunc_forward(load_odefunc(g, DEV), 0.37, torch.from_numpy(g['h0']).to(DEV))
+    e = rel(k.cpu(), torch.from_numpy(g['f037']))
+    assert 2e-5 < e < 5e-3, e        # 1xTF32 is outside the fp32 contract, by about this much
+
+
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('name', CASES)
+def test_fused_solve_matches_reference(native_lib, golden, monkeypatch, name, mode):
+    from node_b200 import odeint, solver
+    monkeypatch.setenv('NODE_B200_CONV', mode)
+    g = golden(name)
+    func = load_odefunc(g, DEV)
+    h0, t, tol = torch.from_numpy(g['h0']).to(DEV), torch.from_numpy(g['t']).to(DEV), float(g['tol'])
+    with torch.no_grad():
+        out = odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')
+    st = dict(solver.last_stats)
+    assert st['route'] == 'fused' and st['status'] == 0
+    assert st['nfe'] == int(g['nfe']) == func.nfe                   # identical NFE, counted on the module
+    assert list(st['trace']['accepted']) == list(g['tr_acc'])       # identical accept/reject sequence
+    np.testing.assert_allclose(st['trace']['dt'], g['tr_dt'], rtol=1e-5)
+    np.testing.assert_allclose(st['trace']['t'], g['tr_t'], rtol=1e-5, atol=1e-12)
+    assert rel(out.cpu(), torch.from_numpy(g['out'])) < TOL_OUT
+    assert torch.equal(out[0], h0)                                  # solvers.py:27
+
+
+def test_fused_multi_time_dense_output(native_lib, golden):
+    """ICMR feature extraction: 10 output times cost no extra evaluations (dopri5.py:85-92)."""
+    from node_b200 import odeint, solver
+    g = golden('cifar_res_n8_t10')
+    func = load_odefunc(g, DEV)
+    h0, t = torch.from_numpy(g['h0']).to(DEV), torch.from_numpy(g['t']).to(DEV)
+    with torch.no_grad():
+        out = odeint(func, h0, t, rtol=1e-3, atol=1e-3, method='dopri5')
+    assert out.shape == (10,) + tuple(h0.shape)
+    assert solver.last_stats['nfe'] == int(g['nfe']) == 26
+    assert rel(out.cpu(), torch.from_numpy(g['out'])) < TOL_OUT
+    for i in range(10):
+        assert rel(out[i].cpu(), torch.from_numpy(g['out'][i])) < 2 * TOL_OUT
+
+
+@pytest.mark.parametrize('name,in_ch,size,ds', [('cifar_res_n128', 3, 32, 'residual'), ('mnist_conv_n128', 1, 28, 'convolution')])
+def test_odenet_end_to_end_batch128(native_lib, golden, name, in_ch, size, ds):
+    """BASELINE configs 1/2 at the reference batch size, from seeds: logits, top-1, NFE, dt trace."""
+    from node_b200 import models, solver
+    g = golden(name)
+    torch.manual_seed(int(g['seed']))
+    net = models.ODENet(in_ch, n_filters=64, downsample=ds, tol=1e-3).eval()
+    x = torch.rand(int(g['N']), in_ch, size, size)
+    net, x = net.to(DEV), x.to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                        # fp32 contract for the downsampler convs
+    try:
+        with torch.no_grad():
+            logits = net(x)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    st = dict(solver.last_stats)
+    ref = torch.from_numpy(g['logits'])
+    assert st['route'] == 'fused' and net.nfe() == int(g['nfe'])
+    assert list(st['trace']['accepted']) == list(g['tr_acc'])
+    np.testing.assert_allclose(st['trace']['dt'], g['tr_dt'], rtol=1e-5)
+    assert rel(logits.cpu(), ref) < TOL_OUT
+    assert torch.equal(logits.argmax(1).cpu(), ref.argmax(1))       # top-1 identical
+
+
+def test_fused_reversed_time(native_lib, golden):
+    """Decreasing t integrates -f(-t, y) (misc.py:184-187); checked against the oracle."""
+    from node_b200 import odeint, solver
+    g = golden('cifar_res_n8')
+    func = load_odefunc(g, DEV)
+    p = odefunc_params(g)
+    y1 = torch.from_numpy(g['out'][-1])
+    t = torch.tensor([1.0, 0.5])
+    tr = dopri5_port.Trace()
+    with torch.no_grad():
+        ref = dopri5_port.dopri5_solve(lambda a, b: odefunc_port.odefunc_forward(p, a, b), y1, t, 1e-3, 1e-3, trace=tr)
+        out = odeint(func, y1.to(DEV), t.to(DEV), rtol=1e-3, atol=1e-3, method='dopri5')
+    st = solver.last_stats
+    assert st['route'] == 'fused' and st['nfe'] == tr.nfe
+    assert list(st['trace']['accepted']) == [s[2] for s in tr.steps]
+    assert rel(out.cpu(), ref) < TOL_OUT
+
+
+def test_adjoint_gradients_match_reference(native_lib, golden):
+    """odeint_adjoint: forward by the fused route, backward = reverse-time augmented system
+    (adjoint.py:23-102); gradients against the reference's own adjoint."""
+    from node_b200 import odeint_adjoint
+    g = golden('adjoint_cifar_n4')
+    func = load_odefunc(g, DEV).train()
+    h0 = torch.from_numpy(g['h0']).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(g['t']).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        out = odeint_adjoint(func, h0, t, rtol=1e-3, atol=1e-3, method='dopri5')
+        nfe_f, func.nfe = func.nfe, 0
+        out.backward(torch.from_numpy(g['grad_out']).to(DEV))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert nfe_f == int(g['nfe_f']) and func.nfe == int(g['nfe_b'])
+    assert rel(out.detach().cpu(), torch.from_numpy(g['out'])) < TOL_OUT
+    assert rel(h0.grad.cpu(), torch.from_numpy(g['grad_y0'])) < 1e-3
+    flat = torch.cat([q.grad.reshape(-1) for q in func.parameters()])
+    assert rel(flat.cpu(), torch.from_numpy(g['grad_params'])) < 1e-3
