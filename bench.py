@@ -1,0 +1,330 @@
+"""bench.py - headline benchmark of the B200-native ODE-Net dopri5 hot path.
+
+Metric (BASELINE.json): CIFAR-10 ODENet dopri5 (tol 1e-3) forward, images/s, synthetic 32x32
+batches, random-init weights, fp32 contract (3xTF32 tensor-core convolution).  A "step" is one
+ODENet forward over one per-GPU batch; weak scaling (per-GPU batch fixed, the error norm is
+all-reduced over the GLOBAL batch every attempted step).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port), host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'neural-ode-features_b200'), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+FLOP_PER_IMG_PER_NFE_PER_PIXEL = 147456          # 2 convs x 2*9*64*64, algorithmic
+TOL = 1e-3
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], bf16=p['bf16_tflops'], bf16_sus=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    src='measured')
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src='fallback')
+
+
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.strip().lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return None
+        busy = [c for c in sm if c >= 0.5 * max(sm)] or sm
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def build_model(device, adjoint=False):
+    from node_b200 import models
+    torch.manual_seed(0)
+    net = models.ODENet(3, n_filters=64, downsample='residual', tol=TOL, adjoint=adjoint).eval()
+    return net.to(device)
+
+
+def cpu_forward_rate(sample, min_seconds, threads):
+    """The reference's CPU path (torch-CPU restatement = same ATen kernels, all host threads)."""
+    from oracle import dopri5_port, odefunc_port
+    torch.set_num_threads(threads)
+    net = build_model('cpu')
+    p = {k: v.detach() for k, v in odefunc_port.params_from_module(net.odeblock.odefunc).items()}
+    func = lambda t, y: odefunc_port.odefunc_forward(p, t, y)
+    net.odeblock.odeint = lambda f, y0, t, **kw: dopri5_port.dopri5_solve(func, y0, t, kw['rtol'], kw['atol'])
+    x = torch.rand(sample, 3, 32, 32)
+    times = []
+    with torch.no_grad():
+        net(x)                                   # warm-up
+        t_all = time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            net(x)
+            times.append(time.perf_counter() - t0)
+            if (time.perf_counter() - t_all >= min_seconds and len(times) >= 2) or len(times) >= 20:
+                break
+    return sample / statistics.median(times), times
+
+
+def run_reference(args):
+    """--impl reference: rank 0 alone times the CPU path; other ranks exit."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    from oracle import dopri5_port, odefunc_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample = min(args.batch, args.cpu_sample)
+    net = build_model('cpu')
+    p = {k: v.detach() for k, v in odefunc_port.params_from_module(net.odeblock.odefunc).items()}
+    func = lambda t, y: odefunc_port.odefunc_forward(p, t, y)
+    net.odeblock.odeint = lambda f, y0, t, **kw: dopri5_port.dopri5_solve(func, y0, t, kw['rtol'], kw['atol'])
+    x = torch.rand(sample, 3, 32, 32)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            net(x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            net(x)
+        dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = dict(impl='reference', metric='CIFAR-10 ODENet dopri5 forward throughput', value=v, unit='images/s', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32', data='synthetic',
+                config=workload_config(args, sample_note='reference arm: %d-image sample per step on host CPU' % sample),
+                cpu_baseline=dict(value=v, unit='images/s', cores=threads, kind='port',
+                                  sample='%d images per step, %d steps, torch-CPU restatement of the reference (oracle/)' % (sample, args.steps)),
+                e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, sample_note=None):
+    c = dict(workload='cfg2: CIFAR-10 ODENet(3, n_filters=64, downsample=residual, tol=1e-3).eval() forward, '
+                      'synthetic 32x32 batches', per_gpu_batch=args.batch, global_batch=args.batch * args.gpus,
+             solver='dopri5 rtol=atol=1e-3', conv_mode=os.environ.get('NODE_B200_CONV', 'tf32x3'),
+             downsample_classifier='plain PyTorch fp32 (cudnn.allow_tf32=False)', parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
+             l2='inputs larger than L2 (state %d MB per tensor, ~10 live tensors)' % (args.batch * 64 * 64 * 4 // 2 ** 20))
+    if sample_note:
+        c['sample'] = sample_note
+    return c
+
+
+def rk_roofline(device, pk):
+    """HBM roofline of the standalone RK kernels (generic route): stage-6 combination and error norm."""
+    import ctypes
+    from node_b200 import native
+    import numpy as np
+    lib = native.lib()
+    n = 32 * 1024 * 1024                                  # 128 MiB per tensor, 9 tensors >> L2
+    bufs = [torch.randn(n, device=device) for _ in range(9)]
+    L = native.layout()
+    ctl = torch.zeros(L['sizeof'], dtype=torch.uint8, device=device)
+    native.check(lib.node_b200_ctl_init(native.ptr(ctl), native.F32, 1, native.host_f64([TOL]),
+                                        native.host_f64([TOL]), native.host_i64([n]),
+                                        0.9, 10.0, 0.2, 0.2, 100, 2, 1, native.stream_ptr()), 'ctl_init')
+    off = L['h32']
+    ctl[off:off + 4] = torch.frombuffer(bytearray(np.float32(0.1).tobytes()), dtype=torch.uint8).to(device)
+    ks = (ctypes.c_void_p * 7)(*[b.data_ptr() for b in bufs[:7]])
+    partials = torch.zeros(2 * L['max_seg'] * L['partial_blocks'], dtype=torch.float64, device=device)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    seg = (native.host_i64([0]), native.host_i64([n]), 1)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in ev:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return statistics.median(a.elapsed_time(b) for a, b in ev) * 1e-3
+
+    t_comb = timed(lambda: lib.node_b200_rk_stage_combine(native.ptr(ctl), native.F32, 5, native.ptr(bufs[8]), native.ptr(bufs[7]),
+                                                          ks, 6, n, native.stream_ptr()))
+    t_err = timed(lambda: lib.node_b200_rk_error_norm(native.ptr(ctl), native.F32, native.ptr(bufs[7]), native.ptr(bufs[8]), ks, *seg,
+                                                      native.ptr(partials), native.ptr(flag), native.stream_ptr()))
+    comb_bytes = 7 * n * 4            # y0 + k1,k3..k6 read, y7 written (beta_62 = 0)
+    err_bytes = 8 * n * 4             # k1,k3..k7, y0, y1 read; nothing written
+    return dict(stage_combine=dict(bound='hbm', achieved=comb_bytes / t_comb / 1e9, peak=pk['hbm'], unit='GB/s',
+                                   frac=comb_bytes / t_comb / 1e9 / pk['hbm'], bytes_per_launch=comb_bytes, ms=t_comb * 1e3),
+                error_norm=dict(bound='hbm', achieved=err_bytes / t_err / 1e9, peak=pk['hbm'], unit='GB/s',
+                                frac=err_bytes / t_err / 1e9 / pk['hbm'], bytes_per_launch=err_bytes, ms=t_err * 1e3),
+                peak_source=pk['src'], note='E = 32Mi fp32 per tensor (9 tensors, 1.1 GiB) so every pass streams from HBM')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('NODE_B200_BENCH_BATCH', 4096)), help='per-GPU batch')
+    ap.add_argument('--cpu-sample', type=int, default=1024)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    import __graft_entry__ as entry
+    entry.build()
+    from node_b200 import solver, distributed as nd
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        nd.enable()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pk = peaks()
+
+    net = build_model(dev)
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(B, 3, 32, 32, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    logits_host = torch.empty(B, 10).pin_memory()
+    solver.PROFILE_STEP_EVENTS = []
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(step_fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            step_fn()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    launches = [0]
+
+    def step_resident():
+        with torch.no_grad():
+            net(x_dev)
+        launches[0] += solver.last_stats.get('launches', 0)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            logits_host.copy_(net(xd), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    solver.PROFILE_STEP_EVENTS = []
+    launches[0] = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_res = timed_loop(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    step_events = solver.PROFILE_STEP_EVENTS
+    solver.PROFILE_STEP_EVENTS = None
+    n_launch = launches[0]
+    stats = dict(solver.last_stats)
+    for _ in range(2):
+        step_e2e()
+    t_e2e = timed_loop(step_e2e, args.steps)
+
+    # ODE block alone (the hot path proper), state resident
+    with torch.no_grad():
+        h0 = net.downsample(x_dev)
+    t_ode = timed_loop(lambda: net.odeblock(h0), args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = world * B * args.steps
+    value = total / t_res
+    # dominant kernel: the fused 6-stage step kernel (tensor bound)
+    k_ms = [a.elapsed_time(b) for a, b in step_events]
+    k_avg = statistics.mean(k_ms) * 1e-3 if k_ms else float('nan')
+    flops_per_launch = 6 * B * FLOP_PER_IMG_PER_NFE_PER_PIXEL * 64
+    tf32_peak = pk['bf16_sus'] / 2
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('k_fused_step_dram_bytes_per_launch')
+    roof = dict(bound='tensor', kernel='k_fused (6 dopri5 stages = 12 implicit-GEMM convs per launch)',
+                achieved=flops_per_launch / k_avg / 1e12, peak=tf32_peak, unit='TFLOP/s',
+                frac=flops_per_launch / k_avg / 1e12 / tf32_peak, traffic=traffic,
+                flops_per_launch=flops_per_launch, launch_ms=k_avg * 1e3, launches_timed=len(k_ms),
+                share_of_step=sum(k_ms) * 1e-3 / t_res,
+                peak_note='TF32 dense peak taken as 1/2 of %s sustained bf16 (%s); algorithmic FLOPs counted once although '
+                          '3xTF32 issues 3 MMAs' % (pk['bf16_sus'], pk['src']))
+    line = dict(metric='CIFAR-10 ODENet dopri5 forward throughput', value=value, unit='images/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * t_res / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f32', data='synthetic', config=workload_config(args),
+                e2e=dict(value=total / t_e2e, unit='images/s', h2d_bytes_per_step=x_host.numel() * 4,
+                         d2h_bytes_per_step=logits_host.numel() * 4),
+                gpu_launches=n_launch, clocks=clocks, roofline=roof,
+                odeblock=dict(images_per_s=total / t_ode, ms_per_step=1e3 * t_ode / args.steps, nfe=stats.get('nfe'),
+                              n_accept=stats.get('n_accept'), n_reject=stats.get('n_reject')))
+    if world == 1:
+        line['roofline_rk'] = rk_roofline(dev, pk)
+        if not args.skip_cpu:
+            threads = os.cpu_count() or 1
+            rate, times = cpu_forward_rate(min(B, args.cpu_sample), args.cpu_seconds, threads)
+            line['cpu_baseline'] = dict(value=rate, unit='images/s', cores=threads, kind='port',
+                                        sample='%d-image batches, %d forwards (median), torch-CPU restatement of the reference '
+                                               'solver + dynamics (oracle/), same seeds' % (min(B, args.cpu_sample), len(times)))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

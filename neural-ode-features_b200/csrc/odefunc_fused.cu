@@ -282,7 +282,7 @@ __device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const 
     for (int mt = 0; mt < g.MT; ++mt) {
       // the A stage (and, two taps back, a weight slot) is free once the MMAs of item-2 completed
       if (pp.g_item >= 2) {
-        if (!ptx::mbar_wait(sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1)) pp.timeout = true;
+        if (!pp.timeout && !ptx::mbar_wait(sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1)) pp.timeout = true;
       }
       ptx::tc_fence_after();
       if (mt == 0 && tid == 0) issue_weights(sm, pp, wtiles, pp.g_tap + 2);
@@ -312,7 +312,7 @@ __device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const 
       if (tid == 0) {
         const uint32_t slot = pp.g_tap & (kNW - 1);
         if (mt == 0) {
-          if (!ptx::mbar_wait(sm.bar_w + 8 * slot, (pp.g_tap / kNW) & 1)) pp.timeout = true;
+          if (!pp.timeout && !ptx::mbar_wait(sm.bar_w + 8 * slot, (pp.g_tap / kNW) & 1)) pp.timeout = true;
         }
         ptx::tc_fence_after();
         const uint32_t d = pp.tmem + mt * 64;
@@ -344,7 +344,7 @@ __device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const 
   // accumulators complete when the last item's commit lands
   {
     const uint32_t last = pp.g_item - 1;
-    if (!ptx::mbar_wait(sm.bar_mma + 8 * (last & 1), (last >> 1) & 1)) pp.timeout = true;
+    if (!pp.timeout && !ptx::mbar_wait(sm.bar_mma + 8 * (last & 1), (last >> 1) & 1)) pp.timeout = true;
   }
   ptx::tc_fence_after();
   // ---- epilogue: TMEM -> (+bias + t*Tmap) -> shared, [img][cout][pixel]

@@ -28,7 +28,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait; returns false on timeout (caller records NODE_ST_WATCHDOG and carries on).
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+  for (uint32_t spin = 0; spin < (1u << 20); ++spin)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
 }

@@ -104,15 +104,15 @@ def ptr(t):
 
 
 def host_f64(values):
-    return np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+    """Host array of doubles that OWNS its memory: pass the returned object itself as the argument so
+    it stays alive for the duration of the call (a bare .ctypes.data of a temporary would dangle)."""
+    vals = [float(v) for v in np.asarray(values, dtype=np.float64).reshape(-1)]
+    return (ctypes.c_double * max(len(vals), 1))(*vals)
 
 
 def host_i64(values):
-    return np.ascontiguousarray(np.asarray(values, dtype=np.int64))
-
-
-def np_ptr(a):
-    return ctypes.c_void_p(a.ctypes.data)
+    vals = [int(v) for v in np.asarray(values, dtype=np.int64).reshape(-1)]
+    return (ctypes.c_int64 * max(len(vals), 1))(*vals)
 
 
 class CtlView(object):

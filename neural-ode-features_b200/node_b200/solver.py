@@ -27,7 +27,10 @@ _KNOWN_METHODS = ('explicit_adams', 'fixed_adams', 'adams', 'tsit5', 'dopri5', '
 _DOPRI5_OPTIONS = ('first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps')
 CONV_MODES = {'tf32x3': 0, 'tf32': 1, 'simt': 2}
 
-last_stats = {}          # filled after every solve: nfe, n_accept, n_reject, trace, route
+last_stats = {}          # filled after every solve: nfe, n_accept, n_reject, trace, route, launches
+# bench.py sets this to a list: the fused route then records a (start, end) CUDA-event pair around
+# every launch of the 6-stage step kernel on the launching stream (roofline timing, live)
+PROFILE_STEP_EVENTS = None
 _t_cache = {}
 _ws_cache = {}
 _step_guess = {}
@@ -153,6 +156,7 @@ class FusedWorkspace(object):
         self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.shape = (N, C, H, W)
         self.param_key = None
+        self.param_key_fresh = False
         L = native.layout()
         ctl_ptr = native.lib().node_b200_fused_ctl(native.ptr(self.buf))
         off = ctl_ptr - self.buf.data_ptr()
@@ -170,6 +174,7 @@ class FusedWorkspace(object):
                                                   1e-5, native.stream_ptr())
         native.check(err, 'fused_prepare')
         self.param_key = key
+        self.param_key_fresh = True
 
 
 def fused_workspace(device, N, C, H, W):
@@ -211,46 +216,64 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     group = dist_state.group()
     th = native.host_f64(t_host)
     E = y.numel()
-    common = (native.np_ptr(th), T, float(rtol), float(atol), N, C, H, W)
-    if group is None:
+    common = (th, T, float(rtol), float(atol), N, C, H, W)
+    launches = 7 + (1 if ws.param_key_fresh else 0)
+    ws.param_key_fresh = False
+    events = PROFILE_STEP_EVENTS
+    if group is None and events is None:
         guess = _step_guess.get(id(_unwrap(func)), 8)
         first = 1
         while True:
             err = lib.node_b200_fused_solve(native.ptr(ws.buf), native.ptr(y), *common, E, native.ptr(out), conv_mode,
                                             int(tsign), first, guess, native.stream_ptr())
             native.check(err, 'fused_solve')
+            launches += 4 * guess
             view = native.CtlView(ws.ctl)
             if view.i32('done'):
                 break
             first, guess = 0, 4
-        _step_guess[id(_unwrap(func))] = view.i32('n_attempt') + 1
     else:
-        E_glob = dist_state.global_numel(E, y.device)
+        sharded = group is not None
+        E_glob = dist_state.global_numel(E, y.device) if sharded else E
 
         def phase(ph):
             native.check(lib.node_b200_fused_phase(native.ptr(ws.buf), ph, native.ptr(y), *common, E_glob, native.ptr(out),
                                                    conv_mode, int(tsign), native.stream_ptr()), 'fused_phase %d' % ph)
 
-        phase(0); dist_state.all_reduce_sum(ws.sums)
-        phase(1); dist_state.all_reduce_sum(ws.sums)
+        def reduce():
+            if sharded:
+                dist_state.all_reduce_sum(ws.sums)
+
+        phase(0); reduce()
+        phase(1); reduce()
         phase(2)
-        guess = _step_guess.get(id(func), 8)
+        guess = _step_guess.get(id(_unwrap(func)), 8)
+        mine = []
         while True:
             for _ in range(guess):
-                phase(3); dist_state.all_reduce_sum(ws.sums)
+                if events is not None:
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); phase(3); b.record()
+                    mine.append((a, b))
+                else:
+                    phase(3)
+                reduce()
                 phase(4)
+            launches += 4 * guess
             view = native.CtlView(ws.ctl)
             if view.i32('done'):       # identical on every rank: the controller consumed identical sums
                 break
             guess = 4
-        _step_guess[id(func)] = view.i32('n_attempt') + 1
+        if events is not None:         # keep only launches that did work (steps after `done` are no-ops)
+            events.extend(mine[:view.i32('n_attempt')])
+    _step_guess[id(_unwrap(func))] = view.i32('n_attempt') + 1
     nfe = view.i32('nfe')
     target = _unwrap(func)
     if hasattr(target, 'nfe'):
         target.nfe += nfe              # model.py:340 counts one per evaluation; callers read it (train.py:49)
     last_stats.clear()
     last_stats.update(route='fused', nfe=nfe, n_accept=view.i32('n_accept'), n_reject=view.i32('n_reject'),
-                      status=view.i32('status'), trace=view.trace())
+                      status=view.i32('status'), trace=view.trace(), launches=launches)
     native.raise_for_status(view.i32('status'))
     return out
 
@@ -287,7 +310,7 @@ class _GenericSolve(object):
         self.partials = torch.zeros(2 * L['max_seg'] * L['partial_blocks'], dtype=torch.float64, device=self.device)
         self.sums = torch.zeros(2 * L['max_seg'], dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.t_dev = torch.from_numpy(self.t_host).to(self.device)
+        self.t_dev = torch.tensor([float(v) for v in t_host], dtype=torch.float64, device=self.device)
         self.out = torch.empty(self.T, self.L, dtype=self.dtype, device=self.device)
         self.seg_off = native.host_i64(self.offs)
         self.seg_len = native.host_i64(self.lens)
@@ -297,8 +320,8 @@ class _GenericSolve(object):
         numel = native.host_i64([dist_state.global_numel(n, self.device) if dist_state.group() is not None else n
                                  for n in self.lens])
         err = native.lib().node_b200_ctl_init(
-            native.ptr(self.ctl), self.code, nseg, native.np_ptr(native.host_f64(rt)), native.np_ptr(native.host_f64(at)),
-            native.np_ptr(numel), _dflt(opts.get('safety', 0.9)), _dflt(opts.get('ifactor', 10.0)),
+            native.ptr(self.ctl), self.code, nseg, native.host_f64(rt), native.host_f64(at),
+            numel, _dflt(opts.get('safety', 0.9)), _dflt(opts.get('ifactor', 10.0)),
             _dflt(opts.get('dfactor', 0.2)), _dflt(1 / 5), int(opts.get('max_num_steps', 2 ** 31 - 1)), self.T, 1,
             native.stream_ptr())
         native.check(err, 'ctl_init')
@@ -338,7 +361,7 @@ class _GenericSolve(object):
         lib, sp = native.lib(), native.stream_ptr()
         Y0, Y1, F0, F1, K2, YMID, YI = 0, 1, 2, 3, 4, 9, 10
         nseg = len(self.lens)
-        segs = (native.np_ptr(self.seg_off), native.np_ptr(self.seg_len), nseg)
+        segs = (self.seg_off, self.seg_len, nseg)
         ctl = native.ptr(self.ctl)
         t0d = torch.tensor(self.t_host[0], dtype=self.dtype, device=self.device)
         self._eval(t0d, Y0, F0)                                               # dopri5.py:78
