@@ -281,7 +281,11 @@ def main():
     # ODE block alone (the hot path proper), state resident
     with torch.no_grad():
         h0 = net.downsample(x_dev)
-    t_ode = timed_loop(lambda: net.odeblock(h0), args.steps)
+    def step_ode():
+        with torch.no_grad():
+            net.odeblock(h0)
+
+    t_ode = timed_loop(step_ode, args.steps)
 
     if rank != 0:
         if world > 1:

@@ -26,7 +26,7 @@ constexpr int kC = 64;                 // channels of the fused kernels (n_filte
 constexpr int kGroups = 32;            // GroupNorm(min(32, C), C)
 constexpr int kCpg = kC / kGroups;     // channels per group
 constexpr int kFThreads = 256;
-constexpr int kNW = 4;                 // weight ring depth (taps)
+
 constexpr int kWTileBytes = 2 * 2 * 64 * 128;  // hi/lo x kblock x 64 rows x 128 B = 32 KB per tap
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 128;          // up to two 128-row accumulators of 64 columns
@@ -50,7 +50,7 @@ struct Geo { int N, H, W, HW, G, MT, ngroups; };
 
 struct FusedArgs {
   FusedWs w; Geo g;
-  int mode, conv_mode;
+  int mode, conv_mode, nw;
   const float* y_in; float* k_out; float* out0;
   float t_explicit, tsign, eps;
 };
@@ -146,77 +146,136 @@ __global__ void k_prepare(FusedWs w, int H, int W, const float* c1w, const float
 }
 
 // ---- device pieces of the fused kernel -----------------------------------------------------------
+// Shape policy: the common feature-map sizes are compiled with constant H, W (index arithmetic folds
+// into immediates); Shape<0,0> reads them from the launch arguments.
+template <int H_, int W_>
+struct Shape {
+  int h, w;
+  __device__ __forceinline__ explicit Shape(const Geo& g) : h(g.H), w(g.W) {}
+  __device__ __forceinline__ int H() const { return H_ > 0 ? H_ : h; }
+  __device__ __forceinline__ int W() const { return W_ > 0 ? W_ : w; }
+  __device__ __forceinline__ int HW() const { return H_ > 0 ? H_ * W_ : h * w; }
+  // values per lane of a GroupNorm cell (2 channels x HW floats over 32 lanes); compile-time bound for registers
+  static constexpr int kNper = H_ > 0 ? (2 * H_ * W_ + 31) / 32 : 16;
+  static constexpr int kCellBatch = kNper <= 4 ? 4 : 1;   // cells a warp reduces concurrently (ILP across shuffles)
+};
+
 struct Smem {
   uint32_t wslot;      // shared address of weight ring (tc engine)
-  float* zbuf;         // [G][C][HW] activations / conv output
+  float* zbuf;         // [G][C][HW] activations / conv output; holds the TF32 "hi" part while a conv runs
+  float* zlo;          // tc engine: [G][C][HW] residual "lo" part (a - hi)
   float* zpad;         // SIMT engine: zero padded copy [G][C][(H+2)(W+2)]
-  uint32_t bar_w;      // kNW mbarriers (8 B each)
-  uint32_t bar_mma;    // 2 mbarriers
+  uint32_t bar_w;      // nw mbarriers (8 B each): weight tile landed (TMA complete_tx)
+  uint32_t bar_mma;    // 2 mbarriers: MMAs that read A stage s retired (tcgen05.commit)
+  uint32_t bar_afull;  // 2 mbarriers: A stage s written by all 256 worker threads
   double* scratch;     // 32 doubles
   float* coef;         // [8][8] h*coefficient table
   uint32_t* tmem_slot;
 };
 
-struct Pipe {          // uniform across the CTA
-  uint32_t g_item, g_tap, w_issued, w_total, tmem;
+struct Pipe {          // replicated, uniform: workers and the issuer walk the same item schedule
+  uint32_t g_item, g_tap, w_issued, w_total, tmem, nw;
   bool timeout;
 };
 
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void pipe_wait(Pipe& pp, uint32_t bar, uint32_t parity) {
+  if (!pp.timeout && !ptx::mbar_wait(bar, parity)) pp.timeout = true;
+}
+
 // GroupNorm over (image, group) cells of kCpg*HW contiguous floats + affine (+ReLU), in place.
-__device__ __forceinline__ void gn_apply(float* z, int gact, int HW, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float eps, bool relu, float sign) {
+// split: additionally break the result into TF32 hi (kept in z) and the fp32 residual lo (3xTF32 operands).
+template <class S>
+__device__ __forceinline__ void gn_apply(const S& sh, float* z, float* zlo, int gact, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, bool relu, float sign, bool split) {
+  constexpr int NP = S::kNper, CB = S::kCellBatch;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = sh.HW();
   const int n = kCpg * HW;
   const float inv_n = 1.0f / (float)n;
-  for (int cell = warp; cell < gact * kGroups; cell += kFThreads / 32) {
-    float* p = z + (int64_t)cell * n;
-    const int c0 = (cell % kGroups) * kCpg;
-    float v[16];
-    float s = 0.f;
+  const int ncell = gact * kGroups;
+  for (int cell0 = warp * CB; cell0 < ncell; cell0 += (kFThreads / 32) * CB) {
+    float v[CB][NP], s[CB], q[CB];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int i = lane + 32 * u;
-      v[u] = i < n ? p[i] : 0.f;
-      s += v[u];
+    for (int b = 0; b < CB; ++b) {
+      s[b] = 0.f;
+      const float* p = z + (cell0 + b) * n;
+      const bool live = cell0 + b < ncell;
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        const int i = lane + 32 * u;
+        v[b][u] = (live && i < n) ? p[i] : 0.f;
+        s[b] += v[b][u];
+      }
     }
-    const float mean = warp_sum(s) * inv_n;
-    float q = 0.f;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int i = lane + 32 * u;
-      const float d = i < n ? v[u] - mean : 0.f;
-      q = fmaf(d, d, q);
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int b = 0; b < CB; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
     }
-    const float var = warp_sum(q) * inv_n;
-    const float rstd = 1.0f / sqrtf(var + eps);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int i = lane + 32 * u;
-      if (i < n) {
-        const int c = c0 + i / HW;
-        const float a = rstd * gamma[c];
-        const float b = beta[c] - a * mean;
-        float r = fmaf(v[u], a, b);
-        if (relu) r = fmaxf(r, 0.f);
-        p[i] = r * sign;
+    for (int b = 0; b < CB; ++b) {
+      s[b] *= inv_n;                                   // mean
+      q[b] = 0.f;
+#pragma unroll
+      for (int u = 0; u < NP; ++u) {
+        const int i = lane + 32 * u;
+        const float d = i < n ? v[b][u] - s[b] : 0.f;
+        q[b] = fmaf(d, d, q[b]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int b = 0; b < CB; ++b) q[b] += __shfl_xor_sync(0xffffffffu, q[b], o);
+    }
+#pragma unroll
+    for (int b = 0; b < CB; ++b) {
+      const int cell = cell0 + b;
+      if (cell < ncell) {
+        const int c0 = (cell % kGroups) * kCpg;
+        const float rstd = 1.0f / sqrtf(q[b] * inv_n + eps);
+        const float a0 = rstd * gamma[c0], a1 = rstd * gamma[c0 + 1];
+        const float b0 = beta[c0] - a0 * s[b], b1 = beta[c0 + 1] - a1 * s[b];
+        float* p = z + cell * n;
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+          const int i = lane + 32 * u;
+          if (i < n) {
+            const bool second = i >= HW;               // kCpg == 2 channels per group
+            float r = fmaf(v[b][u], second ? a1 : a0, second ? b1 : b0);
+            if (relu) r = fmaxf(r, 0.f);
+            r *= sign;
+            if (split) {
+              const float hi = __uint_as_float(ptx::tf32_rna(r));
+              p[i] = hi;
+              zlo[cell * n + i] = r - hi;
+            } else {
+              p[i] = r;
+            }
+          }
+        }
       }
     }
   }
 }
+static_assert(kCpg == 2, "gn_apply assumes two channels per group (64 filters, 32 groups)");
 
-// fp32 FFMA engine: z <- conv3x3(z) + bias + t*Tmap, via a zero padded copy.
-__device__ void conv_simt(const Smem& sm, const Geo& g, int gact, const float* __restrict__ wraw,
+// fp32 FFMA engine: z <- conv3x3(z) + bias + t*Tmap, via a zero padded copy. Workers only.
+template <class S>
+__device__ void conv_simt(const S& sh, const Smem& sm, int gact, const float* __restrict__ wraw,
                           const float* __restrict__ bias, const float* __restrict__ tmap, float t) {
   const int tid = threadIdx.x;
-  const int PW = g.W + 2, PHW = (g.H + 2) * PW, HW = g.HW;
+  const int Wd = sh.W(), HW = sh.HW();
+  const int PW = Wd + 2, PHW = (sh.H() + 2) * PW;
   const int rows = gact * HW;
   for (int i = tid; i < gact * kC * PHW; i += kFThreads) sm.zpad[i] = 0.f;
-  __syncthreads();
+  worker_sync();
   for (int i = tid; i < gact * kC * HW; i += kFThreads) {
     const int p = i % HW, ic = i / HW;
-    sm.zpad[ic * PHW + (p / g.W + 1) * PW + (p % g.W + 1)] = sm.zbuf[i];
+    sm.zpad[ic * PHW + (p / Wd + 1) * PW + (p % Wd + 1)] = sm.zbuf[i];
   }
-  __syncthreads();
+  worker_sync();
   const int co0 = (tid >> 4) * 4, pl = tid & 15;
   int off[16];
   float acc[16][4];
@@ -225,10 +284,11 @@ __device__ void conv_simt(const Smem& sm, const Geo& g, int gact, const float* _
     const int m = pl + 16 * u;
     const int mm = m < rows ? m : 0;
     const int img = mm / HW, p = mm % HW;
-    off[u] = img * kC * PHW + (p / g.W + 1) * PW + (p % g.W + 1);
+    off[u] = img * kC * PHW + (p / Wd + 1) * PW + (p % Wd + 1);
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
   }
+#pragma unroll 1
   for (int ci = 0; ci < kC; ++ci) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -256,76 +316,46 @@ __device__ void conv_simt(const Smem& sm, const Geo& g, int gact, const float* _
       }
     }
   }
-  __syncthreads();
+  worker_sync();
 }
 
-// Thread 0: keep the weight ring `ahead` taps ahead of the consumer. Ring slot x&3 of tap x was last
-// read by the MMAs of tap x-4, which are known complete once tap (x-2)'s predecessor wait passed.
-__device__ __forceinline__ void issue_weights(const Smem& sm, Pipe& pp, const float* __restrict__ wtiles, uint32_t upto) {
-  while (pp.w_issued <= upto && pp.w_issued < pp.w_total) {
-    const uint32_t x = pp.w_issued;
-    const uint32_t bar = sm.bar_w + 8 * (x & (kNW - 1));
-    ptx::mbar_expect_tx(bar, kWTileBytes);
-    ptx::bulk_g2s(sm.wslot + (x & (kNW - 1)) * kWTileBytes, (const char*)wtiles + (size_t)(x % 18) * kWTileBytes, kWTileBytes, bar);
-    ++pp.w_issued;
-  }
-}
-
-// tcgen05 engine: z <- conv3x3(z) + bias + t*Tmap.
-__device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const float* __restrict__ wtiles,
-                        const float* __restrict__ bias, const float* __restrict__ tmap, float t, bool split3) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, hf = warp >> 2;
-  const int HW = g.HW, rows = gact * HW;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    for (int mt = 0; mt < g.MT; ++mt) {
-      // the A stage (and, two taps back, a weight slot) is free once the MMAs of item-2 completed
-      if (pp.g_item >= 2) {
-        if (!pp.timeout && !ptx::mbar_wait(sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1)) pp.timeout = true;
-      }
-      ptx::tc_fence_after();
-      if (mt == 0 && tid == 0) issue_weights(sm, pp, wtiles, pp.g_tap + 2);
-      __syncwarp();
-      // ---- build A_tap rows [mt*128, mt*128+128) in tensor memory
-      const int m = mt * 128 + q * 32 + lane;
-      bool valid = m < rows;
-      const int mm = valid ? m : 0;
-      const int img = mm / HW, p = mm % HW;
-      const int hh = p / g.W + dy, xx = p % g.W + dx;
-      valid = valid && hh >= 0 && hh < g.H && xx >= 0 && xx < g.W;
-      const float* src = sm.zbuf + (img * kC + hf * 32) * HW + (valid ? hh * g.W + xx : 0);
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = valid ? src[j * HW] : 0.f;
-        hi[j] = ptx::tf32_rna(v);
-        lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
-      }
-      const uint32_t colbase = kAccCols + (pp.g_item & 1) * 128;
-      const uint32_t taddr = pp.tmem + ((uint32_t)(q * 32) << 16) + colbase + hf * 32;
-      ptx::tmem_st32(taddr, hi);
-      if (split3) ptx::tmem_st32(taddr + 64, lo);
-      ptx::tc_wait_st();
-      ptx::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        const uint32_t slot = pp.g_tap & (kNW - 1);
+// ---- tcgen05 engine, issuer side (warp 8, one elected lane) --------------------------------------
+// Walks the item schedule (group, evaluation, conv, tap, M tile): keeps the weight ring fed through the TMA
+// engine, waits for the workers' A stage, issues the MMAs and commits them to the stage's mbarrier.
+__device__ void issuer_loop(const Smem& sm, Pipe& pp, int n_conv, int MT, const float* __restrict__ wtiles, bool split3) {
+#pragma unroll 1
+  for (int cv = 0; cv < n_conv; ++cv) {
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
         if (mt == 0) {
-          if (!pp.timeout && !ptx::mbar_wait(sm.bar_w + 8 * slot, (pp.g_tap / kNW) & 1)) pp.timeout = true;
+          // slot (g_tap + nw - 2) % nw was last read by tap g_tap - 2: its MMAs must have retired
+          if (pp.g_item >= 2) pipe_wait(pp, sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1);
+          const uint32_t upto = pp.g_tap + pp.nw - 2;
+          while (pp.w_issued <= upto && pp.w_issued < pp.w_total) {
+            const uint32_t x = pp.w_issued, slot = x % pp.nw, bar = sm.bar_w + 8 * slot;
+            ptx::mbar_expect_tx(bar, kWTileBytes);
+            ptx::bulk_g2s(sm.wslot + slot * kWTileBytes, (const char*)wtiles + (size_t)(x % 18) * kWTileBytes, kWTileBytes, bar);
+            ++pp.w_issued;
+          }
         }
+        pipe_wait(pp, sm.bar_afull + 8 * (pp.g_item & 1), (pp.g_item >> 1) & 1);
+        const uint32_t slot = pp.g_tap % pp.nw;
+        if (mt == 0) pipe_wait(pp, sm.bar_w + 8 * slot, (pp.g_tap / pp.nw) & 1);
         ptx::tc_fence_after();
         const uint32_t d = pp.tmem + mt * 64;
-        const uint32_t wbase = sm.wslot + slot * kWTileBytes;
+        const uint32_t a0 = pp.tmem + kAccCols + (pp.g_item & 1) * 128;
+        const uint64_t b0 = ptx::make_desc_sw128(sm.wslot + slot * kWTileBytes);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t a_hi = pp.tmem + colbase + kb * 32 + ks * 8;
-            const uint64_t b_hi = ptx::make_desc_sw128(wbase + kb * 8192 + ks * 32);
+            const uint32_t a_hi = a0 + kb * 32 + ks * 8;
+            const uint64_t b_hi = b0 + (uint64_t)((kb * 8192 + ks * 32) >> 4);   // start-address field, 16 B units
             const uint32_t first = (tap == 0 && kb == 0 && ks == 0) ? 0u : 1u;
             if (split3) {
-              const uint64_t b_lo = ptx::make_desc_sw128(wbase + 16384 + kb * 8192 + ks * 32);
+              const uint64_t b_lo = b_hi + (uint64_t)(16384 >> 4);
               ptx::mma_tf32_ts(d, a_hi + 64, b_hi, kIdesc, first);
               ptx::mma_tf32_ts(d, a_hi, b_lo, kIdesc, 1u);
               ptx::mma_tf32_ts(d, a_hi, b_hi, kIdesc, 1u);
@@ -335,8 +365,55 @@ __device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const 
           }
         }
         ptx::tc_commit(sm.bar_mma + 8 * (pp.g_item & 1));
+        ++pp.g_item;
       }
-      __syncwarp();
+      ++pp.g_tap;
+    }
+  }
+}
+
+// ---- tcgen05 engine, worker side: z <- conv3x3(z) + bias + t*Tmap ---------------------------------
+// Input: TF32 hi part in zbuf, residual in zlo (see gn_apply). Each worker thread owns one A row (pixel) and
+// half of the K columns of every item; stages hand over through mbarriers only (no CTA-wide barrier per item).
+template <class S>
+__device__ void conv_tc(const S& sh, const Smem& sm, Pipe& pp, int MT, int gact, const float* __restrict__ bias,
+                        const float* __restrict__ tmap, float t, bool split3) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, hf = warp >> 2;
+  const int HW = sh.HW(), Wd = sh.W(), Ht = sh.H();
+  const int rows = gact * HW;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int m = mt * 128 + q * 32 + lane;
+      bool valid = m < rows;
+      const int mm = valid ? m : 0;
+      const int img = mm / HW, p = mm % HW;
+      const int hh = p / Wd + dy, xx = p % Wd + dx;
+      valid = valid && hh >= 0 && hh < Ht && xx >= 0 && xx < Wd;
+      const int base = (img * kC + hf * 32) * HW + (valid ? hh * Wd + xx : 0);
+      uint32_t r[32];
+      {
+        const float* src = sm.zbuf + base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = valid ? __float_as_uint(src[j * HW]) : 0u;
+      }
+      // the A stage is free once the MMAs of item-2 retired
+      if (pp.g_item >= 2) pipe_wait(pp, sm.bar_mma + 8 * (pp.g_item & 1), ((pp.g_item >> 1) - 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = pp.tmem + ((uint32_t)(q * 32) << 16) + kAccCols + (pp.g_item & 1) * 128 + hf * 32;
+      ptx::tmem_st32(taddr, r);
+      if (split3) {
+        const float* src = sm.zlo + base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = valid ? __float_as_uint(src[j * HW]) : 0u;
+        ptx::tmem_st32(taddr + 64, r);
+      }
+      ptx::tc_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(sm.bar_afull + 8 * (pp.g_item & 1));
       ++pp.g_item;
     }
     ++pp.g_tap;
@@ -344,35 +421,78 @@ __device__ void conv_tc(const Smem& sm, Pipe& pp, const Geo& g, int gact, const 
   // accumulators complete when the last item's commit lands
   {
     const uint32_t last = pp.g_item - 1;
-    if (!pp.timeout && !ptx::mbar_wait(sm.bar_mma + 8 * (last & 1), (last >> 1) & 1)) pp.timeout = true;
+    pipe_wait(pp, sm.bar_mma + 8 * (last & 1), (last >> 1) & 1);
   }
   ptx::tc_fence_after();
   // ---- epilogue: TMEM -> (+bias + t*Tmap) -> shared, [img][cout][pixel]
-  for (int mt = 0; mt < g.MT; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int m = mt * 128 + q * 32 + lane;
     uint32_t v[32];
     ptx::tmem_ld32(pp.tmem + ((uint32_t)(q * 32) << 16) + mt * 64 + hf * 32, v);
     ptx::tc_wait_ld();
     if (m < rows) {
       const int img = m / HW, p = m % HW;
+      float* dst = sm.zbuf + (img * kC + hf * 32) * HW + p;
+      const float* tm = tmap + hf * 32 * HW + p;
+      const float* bs = bias + hf * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int co = hf * 32 + j;
-        sm.zbuf[(img * kC + co) * HW + p] = __uint_as_float(v[j]) + fmaf(t, tmap[co * HW + p], bias[co]);
-      }
+      for (int j = 0; j < 32; ++j) dst[j * HW] = __uint_as_float(v[j]) + fmaf(t, tm[j * HW], bs[j]);
     }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  worker_sync();
 }
 
-__global__ void __launch_bounds__(kFThreads, 1) k_fused(const FusedArgs a) {
+// Stage input z = y + sum_j (h*c_j) k_j for NK source tensors (rk_common.py:49-51), all loads of a chunk pair in
+// flight before the first use (the sources are L2 resident: latency, not bandwidth, is what needs hiding).
+template <int NK>
+__device__ __forceinline__ void stage_input(float* zbuf, const float* y, const float* const (&src)[6], const float (&hc)[6],
+                                            float* ynew, int64_t gbase, int cnt) {
+  using A = Arith<float>;
+  const int tid = threadIdx.x;
+  for (int i0 = tid * 4; i0 < cnt; i0 += kFThreads * 8) {
+    float4 yv[2], kv[2][NK > 0 ? NK : 1];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + c * kFThreads * 4;
+      if (i < cnt) {
+        yv[c] = *reinterpret_cast<const float4*>(y + gbase + i);
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[c][j] = *reinterpret_cast<const float4*>(src[j] + gbase + i);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + c * kFThreads * 4;
+      if (i < cnt) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < NK; ++j) {
+          const float k4[4] = {kv[c][j].x, kv[c][j].y, kv[c][j].z, kv[c][j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[e] = A::add(s[e], A::mul(hc[j], k4[e]));
+        }
+        const float4 r = make_float4(A::add(yv[c].x, s[0]), A::add(yv[c].y, s[1]), A::add(yv[c].z, s[2]), A::add(yv[c].w, s[3]));
+        *reinterpret_cast<float4*>(zbuf + i) = r;
+        if (ynew != nullptr) *reinterpret_cast<float4*>(ynew + gbase + i) = r;
+      }
+    }
+  }
+}
+
+constexpr int kBlock = kFThreads + 32;   // 8 worker warps + 1 issuer warp
+
+template <int H_, int W_>
+__global__ void __launch_bounds__(kBlock, 1) k_fused(const FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   using A = Arith<float>;
   const Geo g = a.g;
+  const Shape<H_, W_> sh(g);
   const FusedWs& w = a.w;
   const int tid = threadIdx.x;
   const bool tc = a.conv_mode != 2;
+  const bool worker = tid < kFThreads;
+  const int HW = sh.HW();
   node_ctl_t* ctl = w.ctl;
 
   if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform: partials keep their last (unused) values
@@ -385,32 +505,37 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused(const FusedArgs a) {
     uint8_t* base = smem_raw + (al - s0);
     size_t o = 0;
     sm.wslot = al;
-    if (tc) o += (size_t)kNW * kWTileBytes;
+    if (tc) o += (size_t)a.nw * kWTileBytes;
     sm.zbuf = reinterpret_cast<float*>(base + o);
-    o += (size_t)g.G * kC * g.HW * 4;
-    sm.zpad = reinterpret_cast<float*>(base + o);
-    if (!tc) o += (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
+    o += (size_t)g.G * kC * HW * 4;
+    sm.zlo = reinterpret_cast<float*>(base + o);
+    sm.zpad = sm.zlo;
+    if (tc) o += (size_t)g.G * kC * HW * 4; else o += (size_t)g.G * kC * (sh.H() + 2) * (sh.W() + 2) * 4;
     o = (o + 15) & ~(size_t)15;
     sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.coef = reinterpret_cast<float*>(base + o); o += 64 * 4;
-    sm.bar_w = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_w = al + (uint32_t)o; o += 8 * 4;
     sm.bar_mma = al + (uint32_t)o; o += 16;
+    sm.bar_afull = al + (uint32_t)o; o += 16;
     sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
   }
 
   const int my_groups = (int)blockIdx.x < g.ngroups ? (g.ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int nevals = a.mode == MODE_STEP ? 6 : 1;
   Pipe pp;
-  pp.g_item = 0; pp.g_tap = 0; pp.w_issued = 0; pp.w_total = (uint32_t)(my_groups * nevals * 18); pp.tmem = 0; pp.timeout = false;
+  pp.g_item = 0; pp.g_tap = 0; pp.w_issued = 0; pp.w_total = (uint32_t)(my_groups * nevals * 18); pp.tmem = 0;
+  pp.nw = (uint32_t)a.nw; pp.timeout = false;
 
   if (tc) {
     if (tid == 0) {
-      for (int i = 0; i < kNW; ++i) ptx::mbar_init(sm.bar_w + 8 * i, 1);
-      ptx::mbar_init(sm.bar_mma, 1);
-      ptx::mbar_init(sm.bar_mma + 8, 1);
+      for (int i = 0; i < a.nw; ++i) ptx::mbar_init(sm.bar_w + 8 * i, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(sm.bar_mma + 8 * i, 1);
+        ptx::mbar_init(sm.bar_afull + 8 * i, kFThreads);
+      }
       ptx::fence_mbar_init();
     }
-    if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+    if (tid >= kFThreads) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -427,121 +552,149 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused(const FusedArgs a) {
   }
   __syncthreads();
 
-  const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
-  float* Ycur = w.Y[cur]; float* Ynew = w.Y[cur ^ 1];
-  float* Fcur = w.F[cur]; float* Fnew = w.F[cur ^ 1];
-  const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
-  const int64_t img_elems = (int64_t)kC * g.HW;
+  const bool split3 = a.conv_mode == 0;
   double acc0 = 0.0, acc1 = 0.0;
   bool bad = false;
 
-  for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
-    const int img0 = grp * g.G;
-    const int gact = min(g.G, g.N - img0);
-    const int64_t gbase = (int64_t)img0 * img_elems;
-    const int cnt = gact * (int)img_elems;
-
-    for (int ev = 0; ev < nevals; ++ev) {
-      // ---- prologue: stage input into shared memory (rk_common.py:49-51)
-      if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
-        for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
-          const float4 y = *reinterpret_cast<const float4*>(a.y_in + gbase + i);
-          *reinterpret_cast<float4*>(sm.zbuf + i) = y;
-          if (a.mode == MODE_F0) {
-            *reinterpret_cast<float4*>(Ycur + gbase + i) = y;
-            if (a.out0 != nullptr) *reinterpret_cast<float4*>(a.out0 + gbase + i) = y;
-          }
-        }
-      } else {
-        const int row = a.mode == MODE_PROBE ? 7 : ev;
-        const int nk = a.mode == MODE_PROBE ? 1 : ev + 1;
-        const float* cf = a.mode == MODE_PROBE ? nullptr : sm.coef + row * 8;
-        for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
-          float y[4], s[4] = {0.f, 0.f, 0.f, 0.f}, kv[4];
-          *reinterpret_cast<float4*>(y) = *reinterpret_cast<const float4*>(Ycur + gbase + i);
-          for (int j = 0; j < nk; ++j) {
-            if (j == 1 && row == 5) continue;            // beta_62 == 0
-            const float hc = cf ? cf[j] : h;             // probe: y0 + h0*f0 (misc.py:133)
-            const float* src = j == 0 ? Fcur : w.K[j - 1];
-            *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>(src + gbase + i);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) s[e] = A::add(s[e], A::mul(hc, kv[e]));
-          }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) y[e] = A::add(y[e], s[e]);
-          *reinterpret_cast<float4*>(sm.zbuf + i) = *reinterpret_cast<float4*>(y);
-          if (a.mode == MODE_STEP && ev == 5) *reinterpret_cast<float4*>(Ynew + gbase + i) = *reinterpret_cast<float4*>(y);
-        }
+  if (!worker) {
+    // ===== issuer warp: TMA weight ring + MMA issue for every item of this CTA's schedule =====
+    if (tc) {
+      for (int it = 0; it < my_groups * nevals; ++it) {
+        if (tid == kFThreads) issuer_loop(sm, pp, 2, g.MT, w.wtiles, split3);
+        __syncwarp();
       }
-      __syncthreads();
-
-      // ---- the dynamics (model.py:339-348)
-      const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
-      const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
-      gn_apply(sm.zbuf, gact, g.HW, w.gn + 0 * kC, w.gn + 1 * kC, a.eps, true, 1.f);
-      __syncthreads();
-      for (int cv = 0; cv < 2; ++cv) {
-        if (tc) conv_tc(sm, pp, g, gact, w.wtiles, w.bias + cv * kC, w.tmap + (int64_t)cv * kC * g.HW, t, a.conv_mode == 0);
-        else conv_simt(sm, g, gact, w.wraw + (int64_t)cv * kC * (kC + 1) * 9, w.bias + cv * kC, w.tmap + (int64_t)cv * kC * g.HW, t);
-        gn_apply(sm.zbuf, gact, g.HW, w.gn + (2 * cv + 2) * kC, w.gn + (2 * cv + 3) * kC, a.eps, cv == 0, cv == 0 ? 1.f : a.tsign);
-        __syncthreads();
-      }
-
-      // ---- k_{ev+2} -> global
-      float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : Fnew) : (a.mode == MODE_F0 ? Fcur : (a.mode == MODE_EVAL ? a.k_out : nullptr));
-      if (kdst != nullptr) {
-        for (int i = tid * 4; i < cnt; i += kFThreads * 4)
-          *reinterpret_cast<float4*>(kdst + gbase + i) = *reinterpret_cast<const float4*>(sm.zbuf + i);
-      }
-      __syncthreads();
     }
+  } else {
+    // ===== worker warps =====
+    const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
+    float* Ycur = w.Y[cur]; float* Ynew = w.Y[cur ^ 1];
+    float* Fcur = w.F[cur]; float* Fnew = w.F[cur ^ 1];
+    const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
+    const int img_elems = kC * HW;
 
-    // ---- per-group epilogues: norms that feed the controller
-    if (a.mode == MODE_F0) {               // misc.py:121-126
-      for (int i = tid; i < cnt; i += kFThreads) {
-        const float y = a.y_in[gbase + i];
-        const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-        const float u = A::div(y, scale), v = A::div(sm.zbuf[i], scale);
-        acc0 += (double)A::mul(u, u);
-        acc1 += (double)A::mul(v, v);
+#pragma unroll 1
+    for (int grp = blockIdx.x; grp < g.ngroups; grp += gridDim.x) {
+      const int img0 = grp * g.G;
+      const int gact = min(g.G, g.N - img0);
+      const int64_t gbase = (int64_t)img0 * img_elems;
+      const int cnt = gact * img_elems;
+
+#pragma unroll 1
+      for (int ev = 0; ev < nevals; ++ev) {
+        // ---- prologue: stage input into shared memory (rk_common.py:49-51)
+        if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
+          for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
+            const float4 y = *reinterpret_cast<const float4*>(a.y_in + gbase + i);
+            *reinterpret_cast<float4*>(sm.zbuf + i) = y;
+            if (a.mode == MODE_F0) {
+              *reinterpret_cast<float4*>(Ycur + gbase + i) = y;
+              if (a.out0 != nullptr) *reinterpret_cast<float4*>(a.out0 + gbase + i) = y;
+            }
+          }
+        } else {
+          // sources in reference order k1, k2, ... with zero coefficients dropped (beta_62 = 0)
+          const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
+          float hc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          int nk = 0;
+          if (a.mode == MODE_PROBE) {
+            hc[0] = h; nk = 1;                                    // y0 + h0*f0 (misc.py:133)
+          } else {
+            for (int j = 0; j <= ev; ++j) {
+              if (j == 1 && ev == 5) continue;
+              src[nk] = j == 0 ? Fcur : w.K[j - 1];
+              hc[nk] = sm.coef[ev * 8 + j];
+              ++nk;
+            }
+          }
+          float* ynew = (a.mode == MODE_STEP && ev == 5) ? Ynew : nullptr;
+          switch (nk) {
+            case 1: stage_input<1>(sm.zbuf, Ycur, src, hc, ynew, gbase, cnt); break;
+            case 2: stage_input<2>(sm.zbuf, Ycur, src, hc, ynew, gbase, cnt); break;
+            case 3: stage_input<3>(sm.zbuf, Ycur, src, hc, ynew, gbase, cnt); break;
+            case 4: stage_input<4>(sm.zbuf, Ycur, src, hc, ynew, gbase, cnt); break;
+            default: stage_input<5>(sm.zbuf, Ycur, src, hc, ynew, gbase, cnt); break;
+          }
+        }
+        worker_sync();
+
+        // ---- the dynamics (model.py:339-348)
+        const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
+        const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
+        gn_apply(sh, sm.zbuf, sm.zlo, gact, w.gn + 0 * kC, w.gn + 1 * kC, a.eps, true, 1.f, tc);
+        worker_sync();
+#pragma unroll 1
+        for (int cv = 0; cv < 2; ++cv) {
+          if (tc) conv_tc(sh, sm, pp, g.MT, gact, w.bias + cv * kC, w.tmap + cv * kC * HW, t, split3);
+          else conv_simt(sh, sm, gact, w.wraw + cv * kC * (kC + 1) * 9, w.bias + cv * kC, w.tmap + cv * kC * HW, t);
+          gn_apply(sh, sm.zbuf, sm.zlo, gact, w.gn + (2 * cv + 2) * kC, w.gn + (2 * cv + 3) * kC, a.eps, cv == 0,
+                   cv == 0 ? 1.f : a.tsign, tc && cv == 0);
+          worker_sync();
+        }
+
+        // ---- k_{ev+2} -> global
+        float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : Fnew) : (a.mode == MODE_F0 ? Fcur : (a.mode == MODE_EVAL ? a.k_out : nullptr));
+        if (kdst != nullptr) {
+          for (int i = tid * 4; i < cnt; i += kFThreads * 4)
+            *reinterpret_cast<float4*>(kdst + gbase + i) = *reinterpret_cast<const float4*>(sm.zbuf + i);
+        }
+        if (!(a.mode == MODE_STEP && ev == 5)) worker_sync();   // the step epilogue below reads zbuf, nothing overwrites it
       }
-    } else if (a.mode == MODE_PROBE) {     // misc.py:136
-      for (int i = tid; i < cnt; i += kFThreads) {
-        const float y = Ycur[gbase + i];
-        const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-        const float u = A::div(A::sub(sm.zbuf[i], Fcur[gbase + i]), scale);
-        acc0 += (double)A::mul(u, u);
-      }
-    } else if (a.mode == MODE_STEP) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
-      const float* ce = sm.coef + 7 * 8;
-      const float* cm = sm.coef + 6 * 8;
-      for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
-        float y0[4], y1[4], kv[4], e[4] = {0.f, 0.f, 0.f, 0.f}, md[4] = {0.f, 0.f, 0.f, 0.f};
-        *reinterpret_cast<float4*>(y0) = *reinterpret_cast<const float4*>(Ycur + gbase + i);
-        *reinterpret_cast<float4*>(y1) = *reinterpret_cast<const float4*>(Ynew + gbase + i);
+
+      // ---- per-group epilogues: norms that feed the controller
+      if (a.mode == MODE_F0) {               // misc.py:121-126
+        for (int i = tid; i < cnt; i += kFThreads) {
+          const float y = a.y_in[gbase + i];
+          const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+          const float u = A::div(y, scale), v = A::div(sm.zbuf[i], scale);
+          acc0 += (double)A::mul(u, u);
+          acc1 += (double)A::mul(v, v);
+        }
+      } else if (a.mode == MODE_PROBE) {     // misc.py:136
+        for (int i = tid; i < cnt; i += kFThreads) {
+          const float y = Ycur[gbase + i];
+          const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+          const float u = A::div(A::sub(sm.zbuf[i], Fcur[gbase + i]), scale);
+          acc0 += (double)A::mul(u, u);
+        }
+      } else if (a.mode == MODE_STEP) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
+        const float* ce = sm.coef + 7 * 8;
+        const float* cm = sm.coef + 6 * 8;
+        float part = 0.f;
+        for (int i = tid * 4; i < cnt; i += kFThreads * 4) {
+          float4 ld[7];
+          ld[0] = *reinterpret_cast<const float4*>(Ycur + gbase + i);
+          ld[1] = *reinterpret_cast<const float4*>(Ynew + gbase + i);
+          ld[2] = *reinterpret_cast<const float4*>(Fcur + gbase + i);
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          if (j == 1) continue;
-          if (j == 6) *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>(sm.zbuf + i);
-          else *reinterpret_cast<float4*>(kv) = *reinterpret_cast<const float4*>((j == 0 ? Fcur : w.K[j - 1]) + gbase + i);
+          for (int j = 2; j < 6; ++j) ld[j + 1] = *reinterpret_cast<const float4*>(w.K[j - 1] + gbase + i);
+          const float4 k7 = *reinterpret_cast<const float4*>(sm.zbuf + i);
+          const float y0[4] = {ld[0].x, ld[0].y, ld[0].z, ld[0].w}, y1[4] = {ld[1].x, ld[1].y, ld[1].z, ld[1].w};
+          float e[4] = {0.f, 0.f, 0.f, 0.f}, md[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            if (j == 1) continue;
+            const float4 kq = j == 6 ? k7 : (j == 0 ? ld[2] : ld[j + 1]);
+            const float kv[4] = {kq.x, kq.y, kq.z, kq.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              e[u] = A::add(e[u], A::mul(ce[j], kv[u]));
+              md[u] = A::add(md[u], A::mul(cm[j], kv[u]));
+            }
+          }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            e[u] = A::add(e[u], A::mul(ce[j], kv[u]));
-            md[u] = A::add(md[u], A::mul(cm[j], kv[u]));
+            bad |= !isfinite(y0[u]);
+            const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0[u]), fabsf(y1[u]))));
+            const float qv = A::div(e[u], tol);
+            part += A::mul(qv, qv);
+            md[u] = A::add(y0[u], md[u]);
           }
+          *reinterpret_cast<float4*>(w.YMID + gbase + i) = make_float4(md[0], md[1], md[2], md[3]);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          bad |= !isfinite(y0[u]);
-          const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0[u]), fabsf(y1[u]))));
-          const float qv = A::div(e[u], tol);
-          acc0 += (double)A::mul(qv, qv);
-          md[u] = A::add(y0[u], md[u]);
-        }
-        *reinterpret_cast<float4*>(w.YMID + gbase + i) = *reinterpret_cast<float4*>(md);
+        acc0 += (double)part;                 // <= 32 terms per thread per group in fp32, groups and threads in fp64
       }
+      worker_sync();
     }
-    __syncthreads();
   }
 
   if (a.mode != MODE_EVAL) {
@@ -553,11 +706,11 @@ __global__ void __launch_bounds__(kFThreads, 1) k_fused(const FusedArgs a) {
       w.partials[kPartialBlocksF + blockIdx.x] = r1;
     }
   }
-  if (pp.timeout && tid == 0) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
+  if (pp.timeout && (tid == 0 || tid == kFThreads)) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
   if (tc) {
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid < 32) ptx::tmem_dealloc(pp.tmem, kTmemCols);
+    if (tid >= kFThreads) ptx::tmem_dealloc(pp.tmem, kTmemCols);
   }
 }
 
@@ -571,26 +724,39 @@ __global__ void k_fold_partials(const double* __restrict__ partials, double* __r
   (void)nonfinite_keep;
 }
 
-static size_t fused_smem_bytes(const Geo& g, int conv_mode) {
+static size_t fused_smem_bytes(const Geo& g, int conv_mode, int nw) {
   size_t o = 1024;
-  if (conv_mode != 2) o += (size_t)kNW * kWTileBytes;
-  o += (size_t)g.G * kC * g.HW * 4;
-  if (conv_mode == 2) o += (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
-  o += 16 + 32 * 8 + 64 * 4 + 8 * kNW + 16 + 16;
+  if (conv_mode != 2) o += (size_t)nw * kWTileBytes + (size_t)2 * g.G * kC * g.HW * 4;
+  else o += (size_t)g.G * kC * g.HW * 4 + (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
+  o += 16 + 32 * 8 + 64 * 4 + 8 * 4 + 16 + 16 + 16;
   return o;
 }
 
-static int launch_fused(const FusedArgs& a, cudaStream_t st) {
+template <int H_, int W_>
+static int launch_shape(const FusedArgs& a, size_t smem, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NODE_CUDA_OK(cudaFuncSetAttribute(k_fused<H_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = fused_smem_bytes(a.g, a.conv_mode);
+  k_fused<H_, W_><<<grid, kBlock, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+static int launch_fused(FusedArgs a, cudaStream_t st) {
+  // deepest weight ring (2..4 taps) that fits beside the activation buffers
+  a.nw = 4;
+  while (a.nw > 2 && fused_smem_bytes(a.g, a.conv_mode, a.nw) > 227 * 1024) --a.nw;
+  const size_t smem = fused_smem_bytes(a.g, a.conv_mode, a.nw);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   const int grid = a.g.ngroups < kMaxGrid ? a.g.ngroups : kMaxGrid;
-  k_fused<<<grid, kFThreads, smem, st>>>(a);
-  return (int)cudaGetLastError();
+  const int H = a.g.H, W = a.g.W;
+  if (H == 8 && W == 8) return launch_shape<8, 8>(a, smem, grid, st);
+  if (H == 6 && W == 6) return launch_shape<6, 6>(a, smem, grid, st);
+  if (H == 7 && W == 7) return launch_shape<7, 7>(a, smem, grid, st);
+  if (H == 14 && W == 14) return launch_shape<14, 14>(a, smem, grid, st);
+  if (H == 16 && W == 16) return launch_shape<16, 16>(a, smem, grid, st);
+  return launch_shape<0, 0>(a, smem, grid, st);
 }
 
 }  // namespace node

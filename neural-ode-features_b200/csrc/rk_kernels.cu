@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(kThreads) k_stage_combine(const node_ctl_t* __
                                                             const T* __restrict__ y0, KPtrs ks, int64_t n) {
   using A = Arith<T>;
   constexpr int V = Vec<T>::n;
-  const T h = row == 7 ? (sizeof(T) == 4 ? (T)ctl->h0_32 : (T)ctl->h0) : ctl_h<T>(ctl);
+  // row 7: probe step h0; row 6 (dense-output mid-point) runs AFTER the controller accepted the step, when
+  // ctl->h* already hold the next attempt's size, so it takes the accepted step's h saved in it_h*.
+  const T h = row == 7 ? (sizeof(T) == 4 ? (T)ctl->h0_32 : (T)ctl->h0)
+            : row == 6 ? (sizeof(T) == 4 ? (T)ctl->it_h32 : (T)ctl->it_h64) : ctl_h<T>(ctl);
   T hc[7];
   int src[7];
   int nk = 0;
@@ -395,7 +398,7 @@ extern "C" int node_b200_ctl_layout(int64_t* o, int cap) {
       offsetof(node_ctl_t, nfe), offsetof(node_ctl_t, status), offsetof(node_ctl_t, done), offsetof(node_ctl_t, cur),
       offsetof(node_ctl_t, accepted_last), offsetof(node_ctl_t, tr_t), offsetof(node_ctl_t, tr_dt),
       offsetof(node_ctl_t, tr_ratio), offsetof(node_ctl_t, tr_acc), offsetof(node_ctl_t, h0), offsetof(node_ctl_t, h0_32),
-      offsetof(node_ctl_t, it_t0), offsetof(node_ctl_t, it_t1)};
+      offsetof(node_ctl_t, it_t0), offsetof(node_ctl_t, it_t1), offsetof(node_ctl_t, it_h64), offsetof(node_ctl_t, it_h32)};
   const int n = (int)(sizeof(v) / sizeof(v[0]));
   for (int i = 0; i < n && i < cap; ++i) o[i] = v[i];
   return n;

@@ -22,7 +22,7 @@ CTL_FIELDS = (
     'sizeof', 'partial_blocks', 'max_seg', 'max_trace',
     't0', 't1', 'dt', 'ratio', 'ts64', 'ts32', 'h64', 'h32', 'out_lo', 'out_hi', 'next_out',
     'n_attempt', 'n_accept', 'n_reject', 'nfe', 'status', 'done', 'cur', 'accepted_last',
-    'tr_t', 'tr_dt', 'tr_ratio', 'tr_acc', 'h0', 'h0_32', 'it_t0', 'it_t1',
+    'tr_t', 'tr_dt', 'tr_ratio', 'tr_acc', 'h0', 'h0_32', 'it_t0', 'it_t1', 'it_h64', 'it_h32',
 )
 
 EXPORTS = (

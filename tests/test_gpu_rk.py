@@ -52,6 +52,8 @@ def test_stage_combine_and_error_norm_match_reference_arithmetic(native_lib, dty
     ctl, code = _ctl(native, dtype, 1e-3, 1e-3, [numel])
     _poke(ctl, native, 'h32', float(h), np.float32)
     _poke(ctl, native, 'h64', float(h), np.float64)
+    _poke(ctl, native, 'it_h32', float(h), np.float32)
+    _poke(ctl, native, 'it_h64', float(h), np.float64)
     dy0, dks = y0.to(DEV), [k.to(DEV) for k in ks]
     out = torch.empty_like(dy0)
     for row in range(6):
@@ -120,9 +122,19 @@ def _run_generic(f, y0, t, rtol=1e-7, atol=1e-9, **kw):
     return out, dict(solver.last_stats)
 
 
+@pytest.fixture
+def default_f64():
+    """The reference's own tests run with torch.set_default_dtype(float64) (odeint_tests.py:9); the
+    controller constants are built in the default dtype (dopri5.py:72-74), so the golden traces were too."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(prev)
+
+
 @pytest.mark.parametrize('ode', ['constant', 'linear', 'sine'])
 @pytest.mark.parametrize('direction', ['fwd', 'rev'])
-def test_generic_route_f64_matches_reference_outputs(native_lib, golden, ode, direction):
+def test_generic_route_f64_matches_reference_outputs(native_lib, golden, default_f64, ode, direction):
     """The reference's own analytic problems (torchdiffeq/tests/problems.py, odeint_tests.py:54-67,104-118)."""
     g = golden('generic_f64')
     key = '%s_%s' % (ode, direction)
@@ -140,7 +152,7 @@ def test_generic_route_f64_matches_reference_outputs(native_lib, golden, ode, di
     assert torch.equal(out[0], y0)
 
 
-def test_generic_route_tuple_state_and_single_time_point(native_lib, golden):
+def test_generic_route_tuple_state_and_single_time_point(native_lib, golden, default_f64):
     g = golden('generic_f64')
     A = torch.from_numpy(g['tuple.A']).to(DEV)
     y0, z0, t = (torch.from_numpy(g['tuple.' + k]).to(DEV) for k in ('y0', 'z0', 't'))
