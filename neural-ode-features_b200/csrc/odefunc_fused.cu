@@ -17,88 +17,9 @@
 //   * the time channel is folded into a position dependent bias t*Tmap[c,h,w],
 //     added with the conv bias in the TMEM->shared epilogue.
 // conv_mode 2 swaps the tensor-core engine for a plain fp32 FFMA engine (same kernel family).
-#include "node_common.cuh"
-#include "ptx.cuh"
+#include "fused_common.cuh"
 
 namespace node {
-
-constexpr int kC = 64;                 // channels of the fused kernels (n_filters=64)
-constexpr int kGroups = 32;            // GroupNorm(min(32, C), C)
-constexpr int kCpg = kC / kGroups;     // channels per group
-constexpr int kFThreads = 256;
-
-constexpr int kWTileBytes = 2 * 2 * 64 * 128;  // hi/lo x kblock x 64 rows x 128 B = 32 KB per tap
-constexpr int kTmemCols = 512;
-constexpr int kAccCols = 128;          // up to two 128-row accumulators of 64 columns
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr int kPartialBlocksF = 296;
-constexpr int kMaxGrid = 148;
-
-enum { MODE_F0 = 0, MODE_PROBE = 1, MODE_STEP = 2, MODE_EVAL = 3 };
-
-struct FusedWs {
-  node_ctl_t* ctl; double* sums; int* nonfinite; double* partials; double* t_out;
-  float* wtiles;  // [2 conv][9 tap][hi/lo][2 kblock][64 cout][32 cin] swizzled
-  float* wraw;    // [2][C][C+1][9] copies of the live weights (SIMT engine)
-  float* tmap;    // [2][C][HW]
-  float* bias;    // [2][C]
-  float* gn;      // [3][2][C] gamma, beta
-  float* Y[2]; float* F[2]; float* K[5]; float* YMID;
-};
-
-struct Geo { int N, H, W, HW, G, MT, ngroups; };
-
-struct FusedArgs {
-  FusedWs w; Geo g;
-  int mode, conv_mode, nw;
-  const float* y_in; float* k_out; float* out0;
-  float t_explicit, tsign, eps;
-};
-
-static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
-constexpr int kMaxT = 1024;
-
-static int64_t ws_layout(void* base, int N, int C, int H, int W, FusedWs* out) {
-  const int64_t E = (int64_t)N * C * H * W;
-  const int64_t HW = (int64_t)H * W;
-  int64_t o = 0;
-  auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 1024); return r; };
-  const int64_t o_ctl = take(sizeof(node_ctl_t));
-  const int64_t o_sums = take(sizeof(double) * 2 * NODE_MAX_SEG);
-  const int64_t o_nf = take(sizeof(int));
-  const int64_t o_part = take(sizeof(double) * 2 * NODE_MAX_SEG * kPartialBlocksF);
-  const int64_t o_tout = take(sizeof(double) * kMaxT);
-  const int64_t o_wt = take((int64_t)2 * 9 * kWTileBytes);
-  const int64_t o_wraw = take((int64_t)2 * C * (C + 1) * 9 * 4);
-  const int64_t o_tmap = take((int64_t)2 * C * HW * 4);
-  const int64_t o_bias = take((int64_t)2 * C * 4);
-  const int64_t o_gn = take((int64_t)6 * C * 4);
-  int64_t o_state[10];
-  for (int i = 0; i < 10; ++i) o_state[i] = take(E * 4);
-  if (out != nullptr) {
-    char* b = (char*)base;
-    out->ctl = (node_ctl_t*)(b + o_ctl); out->sums = (double*)(b + o_sums); out->nonfinite = (int*)(b + o_nf);
-    out->partials = (double*)(b + o_part); out->t_out = (double*)(b + o_tout);
-    out->wtiles = (float*)(b + o_wt); out->wraw = (float*)(b + o_wraw); out->tmap = (float*)(b + o_tmap);
-    out->bias = (float*)(b + o_bias); out->gn = (float*)(b + o_gn);
-    out->Y[0] = (float*)(b + o_state[0]); out->Y[1] = (float*)(b + o_state[1]);
-    out->F[0] = (float*)(b + o_state[2]); out->F[1] = (float*)(b + o_state[3]);
-    for (int i = 0; i < 5; ++i) out->K[i] = (float*)(b + o_state[4 + i]);
-    out->YMID = (float*)(b + o_state[9]);
-  }
-  return o;
-}
-
-static bool make_geo(int N, int C, int H, int W, Geo* g) {
-  if (C != kC || N < 1 || H < 1 || W < 1) return false;
-  const int HW = H * W;
-  if (HW > 256) return false;
-  g->N = N; g->H = H; g->W = W; g->HW = HW;
-  g->G = HW <= 128 ? 128 / HW : 1;
-  g->MT = (g->G * HW + 127) / 128;
-  g->ngroups = (N + g->G - 1) / g->G;
-  return true;
-}
 
 // ---- parameter preparation -------------------------------------------------------------------
 __global__ void k_prepare(FusedWs w, int H, int W, const float* c1w, const float* c1b, const float* c2w, const float* c2b,
@@ -490,7 +411,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_fused(const FusedArgs a) {
   const Shape<H_, W_> sh(g);
   const FusedWs& w = a.w;
   const int tid = threadIdx.x;
-  const bool tc = a.conv_mode != 2;
+  const bool tc = a.conv_mode != CONV_SIMT;
   const bool worker = tid < kFThreads;
   const int HW = sh.HW();
   node_ctl_t* ctl = w.ctl;
@@ -552,7 +473,7 @@ __global__ void __launch_bounds__(kBlock, 1) k_fused(const FusedArgs a) {
   }
   __syncthreads();
 
-  const bool split3 = a.conv_mode == 0;
+  const bool split3 = a.conv_mode == CONV_TF32X3;
   double acc0 = 0.0, acc1 = 0.0;
   bool bad = false;
 
@@ -726,7 +647,7 @@ __global__ void k_fold_partials(const double* __restrict__ partials, double* __r
 
 static size_t fused_smem_bytes(const Geo& g, int conv_mode, int nw) {
   size_t o = 1024;
-  if (conv_mode != 2) o += (size_t)nw * kWTileBytes + (size_t)2 * g.G * kC * g.HW * 4;
+  if (conv_mode != CONV_SIMT) o += (size_t)nw * kWTileBytes + (size_t)2 * g.G * kC * g.HW * 4;
   else o += (size_t)g.G * kC * g.HW * 4 + (size_t)g.G * kC * (g.H + 2) * (g.W + 2) * 4;
   o += 16 + 32 * 8 + 64 * 4 + 8 * 4 + 16 + 16 + 16;
   return o;
@@ -744,6 +665,10 @@ static int launch_shape(const FusedArgs& a, size_t smem, int grid, cudaStream_t 
 }
 
 static int launch_fused(FusedArgs a, cudaStream_t st) {
+  if (a.conv_mode == CONV_F16X3 || a.conv_mode == CONV_F16) {
+    if (step_engine_supports(a.g.H, a.g.W)) return launch_step_engine(a, st);
+    a.conv_mode = a.conv_mode == CONV_F16X3 ? CONV_TF32X3 : CONV_TF32;   // shapes the f16 engine does not tile
+  }
   // deepest weight ring (2..4 taps) that fits beside the activation buffers
   a.nw = 4;
   while (a.nw > 2 && fused_smem_bytes(a.g, a.conv_mode, a.nw) > 227 * 1024) --a.nw;
@@ -788,7 +713,8 @@ extern "C" int node_b200_fused_prepare(void* workspace, int C, int H, int W, con
   ws_layout(workspace, 1, C, H, W, &w);   // the parameter region does not depend on N
   (void)eps;
   k_prepare<<<148, 256, 0, (cudaStream_t)stream>>>(w, H, W, c1w, c1b, c2w, c2b, g1w, g1b, g2w, g2b, g3w, g3b);
-  return (int)cudaGetLastError();
+  NODE_CUDA_OK(cudaGetLastError());
+  return launch_prepare16(w, H, W, c1w, c2w, g1w, g1b, g2w, g2b, (cudaStream_t)stream);
 }
 
 extern "C" int node_b200_odefunc_forward(void* workspace, const float* y, float t, float tsign, float* k, int N, int C,

@@ -84,6 +84,31 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
   return u;
 }
 
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16/bf16 operands, fp32 accumulate), issued by ONE thread.
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices; LBO = byte distance between core
+// matrices adjacent in K, SBO = byte distance between 8-row groups.  With rows stored contiguously at a
+// 16-byte pitch (SBO = 128) the start address may point at ANY row: a conv tap is a row offset.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 #define NODE_R32(v, o) "=r"(v[o+0]),"=r"(v[o+1]),"=r"(v[o+2]),"=r"(v[o+3]),"=r"(v[o+4]),"=r"(v[o+5]),"=r"(v[o+6]),"=r"(v[o+7])
 #define NODE_I32(v, o) "r"(v[o+0]),"r"(v[o+1]),"r"(v[o+2]),"r"(v[o+3]),"r"(v[o+4]),"r"(v[o+5]),"r"(v[o+6]),"r"(v[o+7])
 
@@ -93,6 +118,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : NODE_R32(v, 0), NODE_R32(v, 8), NODE_R32(v, 16), NODE_R32(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
+#define NODE_R16(v) "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : NODE_R16(v)
       : "r"(taddr)
       : "memory");
 }

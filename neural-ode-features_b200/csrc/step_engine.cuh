@@ -1,0 +1,616 @@
+// f16-split engine of the fused ODE-Net route (reference model.py:326-348 inside rk_common.py:49-52).
+//
+// Same contract as odefunc_fused.cu (one launch = f0 / initial-step probe / all six dopri5 stages of
+// an attempted step / one plain evaluation), different mapping to the SM:
+//
+//   * one worker THREAD owns one position of a zero-padded image strip and keeps its 64 channels in
+//     registers from the Runge-Kutta stage input to k_i: stage combination, the three GroupNorms,
+//     both ReLUs and both convolution epilogues never leave the register file; GroupNorm statistics
+//     are warp transpose-reductions (+ one shared-memory fold across the warps of an image);
+//   * the 3x3 convolution is an implicit GEMM whose A operand the tensor core reads STRAIGHT from
+//     shared memory (SS-mode tcgen05.mma): the normalised activation is written once per conv as a
+//     K-major, un-swizzled image [k-chunk][position][8 halves] in which images are separated by a
+//     shared zero column / zero row, so a conv tap is nothing but a row offset in the A descriptor -
+//     no per-tap staging by the threads (that staging bound the previous engine, profiles/r01a);
+//   * fp32 contract by operand splitting in FP16 (same 11-bit significands as TF32, twice the MMA
+//     rate and half the bytes): a = a_hi + a_lo, w = w_hi + w_lo after exact power-of-two scaling,
+//     D = a_hi*[w_hi ; w_lo] (one N=128 MMA) + a_lo*w_hi (one N=64 MMA), fp32 accumulation in TMEM;
+//   * weight tiles (16 KB per tap: hi and lo halves, UMMA SWIZZLE_128B image) stream L2 -> shared
+//     through the TMA engine into a 4-deep ring shared by two independent worker slots: while the
+//     tensor core runs the taps of one slot the other slot's threads do epilogue / GroupNorm work.
+#pragma once
+#include <cuda_fp16.h>
+#include "fused_common.cuh"
+
+namespace node {
+
+constexpr int kNW = 4;                    // weight ring depth (taps)
+constexpr int kWGap = 2;                  // a ring slot is refilled once the tap two back has retired
+
+template <int H_, int W_>
+struct Tile {
+  static constexpr int H = H_, W = W_, HW = H_ * W_;
+  static constexpr int Wp = W_ + 1;                 // row pitch: one shared zero column
+  static constexpr int IS = (H_ + 1) * Wp;          // image stride: one shared zero row
+  static constexpr int SPAN = (H_ - 1) * Wp + W_;   // positions from an image's first to its last pixel
+  static constexpr int MT = SPAN <= 256 ? 2 : (SPAN + 127) / 128;   // 128-row M tiles per super-tile
+  static constexpr int P = MT * 128;                // positions = worker threads of a slot
+  static constexpr int G = (P - SPAN) / IS + 1;     // images per super-tile
+  static constexpr int HALO = Wp + 1;
+  static constexpr int R = P + 2 * HALO;            // rows of the A image
+  static constexpr int LBO = R * 16;                // bytes between k-chunks (8 halves) of the A image
+  static constexpr int A_PART = 8 * LBO;            // hi or lo part
+  static constexpr int NWARP = P / 32;
+  static_assert(IS >= 32, "a warp may straddle at most two images");
+  static_assert(MT * 128 <= 512, "accumulators exceed tensor memory");
+};
+
+__host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
+  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
+         (size_t)NSLOT * G * 32 * 8 + 3 * 32 * 16 + 2 * 64 * 4 + 2 * 9 * 64 * 4 + 64 * 4 + 32 * 8 + 16 * 8 + 64;
+}
+
+struct StepSmem {
+  uint32_t wring;        // shared address of the weight ring
+  uint32_t abase;        // shared address of slot 0's A image (hi part)
+  float* part;           // [NSLOT][NWARP][2][32] warp partials of the GroupNorm reductions
+  float2* stat;          // [NSLOT][G][32] (mean, rstd)
+  float4* gnp;           // [3][32] (gamma0, gamma1, beta0, beta1) per group
+  float* bias;           // [2][64]
+  float* tmapc;          // [2][9][64]
+  float* coef;           // [8][8] h * coefficient table
+  double* scratch;       // 32 doubles
+  uint32_t bar_wfull, bar_wfree, bar_aready, bar_acc;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ void slot_sync(int slot, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(nthreads) : "memory");
+}
+
+// Sum 32 per-lane values across the warp; lane L returns the total of u[L] (31 shuffles).
+__device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? u[i] : u[i + 16], keep = up ? u[i + 16] : u[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? b[i] : b[i + 4], keep = up ? b[i + 4] : b[i];
+      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? c[i] : c[i + 2], keep = up ? c[i + 2] : c[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// Per-thread constants of a worker.
+struct Who {
+  int slot, wt, warp, lane;      // slot, position in the strip, warp within the slot
+  int img_l, cls;                // image within the super-tile, Tmap border class
+  bool inimg;                    // the position is a pixel (not padding)
+  bool straddle, isB;            // the warp holds two images; this lane belongs to the second
+  int pix;                       // h*W + w
+};
+
+// One GroupNorm reduction round: u[g] summed over every pixel of the image -> result[img][g] through `fin`.
+template <class T, class Fin>
+__device__ __forceinline__ void gn_reduce(const StepSmem& sm, const Who& me, float (&u)[32], Fin fin) {
+  float* part = sm.part + (me.slot * T::NWARP + me.warp) * 64;
+  if (!me.straddle) {
+    part[me.lane] = xreduce32(u, me.lane);
+  } else {
+    float v[32];
+#pragma unroll
+    for (int g = 0; g < 32; ++g) v[g] = me.isB ? 0.f : u[g];
+    part[me.lane] = xreduce32(v, me.lane);
+#pragma unroll
+    for (int g = 0; g < 32; ++g) v[g] = me.isB ? u[g] : 0.f;
+    part[32 + me.lane] = xreduce32(v, me.lane);
+  }
+  slot_sync(me.slot, T::P);
+  if (me.wt < T::G * 32) {
+    const int img = me.wt >> 5, g = me.wt & 31;
+    const float* pp = sm.part + me.slot * T::NWARP * 64;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < T::NWARP; ++w) {
+      const int ia = (w * 32) / T::IS, ib = (w * 32 + 31) / T::IS;
+      if (ia == img) tot += pp[w * 64 + g];
+      if (ib != ia && ib == img) tot += pp[w * 64 + 32 + g];
+    }
+    fin(sm.stat + (me.slot * T::G + img) * 32 + g, tot);
+  }
+  slot_sync(me.slot, T::P);
+}
+
+// GroupNorm statistics of x (64 channels of this thread's pixel) over the whole image: two passes
+// (mean, then squared deviations) like the reference's native_group_norm; leaves (mean, rstd) in sm.stat.
+template <class T>
+__device__ __forceinline__ void gn_stats(const StepSmem& sm, const Who& me, const float (&x)[64], bool valid, float eps) {
+  constexpr float inv_n = 1.0f / (float)(kCpg * T::HW);
+  float u[32];
+#pragma unroll
+  for (int g = 0; g < 32; ++g) u[g] = x[2 * g] + x[2 * g + 1];          // x is zero on padding
+  gn_reduce<T>(sm, me, u, [&](float2* dst, float tot) { dst->x = tot * inv_n; });
+  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
+#pragma unroll
+  for (int g = 0; g < 32; ++g) {
+    const float m = st[g].x;
+    const float d0 = x[2 * g] - m, d1 = x[2 * g + 1] - m;
+    u[g] = valid ? fmaf(d0, d0, d1 * d1) : 0.f;
+  }
+  gn_reduce<T>(sm, me, u, [&](float2* dst, float tot) { dst->y = 1.0f / sqrtf(tot * inv_n + eps); });
+}
+
+// relu(GN(x)) * scale split into fp16 hi + lo and written as this position's row of the A image.
+template <class T>
+__device__ __forceinline__ void gn_apply_to_A(const StepSmem& sm, const Who& me, const float (&x)[64], int n, float scale,
+                                              bool valid, bool split) {
+  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
+  const float4* gp = sm.gnp + n * 32;
+  const uint32_t row = sm.abase + me.slot * 2 * T::A_PART + (T::HALO + me.wt) * 16;
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = kc * 4 + j;
+      const float2 s = st[g];
+      const float4 p = gp[g];
+      const float a0 = s.y * p.x, a1 = s.y * p.y;
+      const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+      const float r0 = fmaxf(fmaf(x[2 * g], a0, b0), 0.f) * scale;
+      const float r1 = fmaxf(fmaf(x[2 * g + 1], a1, b1), 0.f) * scale;
+      const __half2 h = __floats2half2_rn(r0, r1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    if (valid) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + kc * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      if (split)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + kc * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+  }
+}
+
+// Hand the A image to the issuer, wait for the accumulators, x <- acc/scale + bias + t*Tmap.
+template <class T>
+__device__ __forceinline__ void conv_exchange(const StepSmem& sm, const Who& me, float (&x)[64], uint32_t tmem, uint32_t& njob,
+                                              bool& timeout, int cv, float inv_scale, float t, bool split) {
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncwarp();
+  if (me.lane == 0) ptx::mbar_arrive(sm.bar_aready + 8 * me.slot);
+  if (!timeout && !ptx::mbar_wait(sm.bar_acc + 8 * me.slot, njob & 1)) timeout = true;
+  ++njob;
+  ptx::tc_fence_after();
+  const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128);
+  const float* bs = sm.bias + cv * 64;
+  const float* tm = sm.tmapc + (cv * 9 + me.cls) * 64;
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t v0[16], v1[16];
+    ptx::tmem_ld16(taddr + c0, v0);
+    if (split) ptx::tmem_ld16(taddr + 64 + c0, v1);
+    ptx::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float acc = __uint_as_float(v0[j]);
+      if (split) acc += __uint_as_float(v1[j]);
+      x[c0 + j] = fmaf(acc, inv_scale, fmaf(t, tm[c0 + j], bs[c0 + j]));
+    }
+  }
+  ptx::tc_fence_before();
+}
+
+// x = y + sum_j (h*c_j) k_j over NK sources (rk_common.py:49-51), reference rounding and order.
+template <int HW, int NK>
+__device__ __forceinline__ void stage_in(float (&x)[64], const float* __restrict__ y, const float* const (&src)[6],
+                                         const float (&hc)[6], float* __restrict__ ynew, size_t goff, bool valid) {
+  using A = Arith<float>;
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 4) {
+    float yv[4], kv[NK][4];
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        yv[i] = y[goff + (size_t)(c0 + i) * HW];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) kv[j][i] = src[j][goff + (size_t)(c0 + i) * HW];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float r = 0.f;
+      if (valid) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[j][i]));
+        r = A::add(yv[i], s);
+        if (ynew != nullptr) ynew[goff + (size_t)(c0 + i) * HW] = r;
+      }
+      x[c0 + i] = r;
+    }
+  }
+}
+
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
+template <int H_, int W_, int NSLOT>
+__global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const FusedArgs a) {
+  using T = Tile<H_, W_>;
+  using A = Arith<float>;
+  constexpr int HW = T::HW, P = T::P, NWORK = NSLOT * P;
+  extern __shared__ uint8_t smem_raw[];
+  const FusedWs& w = a.w;
+  node_ctl_t* ctl = w.ctl;
+  const int tid = threadIdx.x;
+  const bool worker = tid < NWORK;
+
+  if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform
+
+  // ---- carve shared memory
+  StepSmem sm;
+  {
+    const uint32_t s0 = ptx::smem_u32(smem_raw);
+    const uint32_t al = (s0 + 1023u) & ~1023u;
+    uint8_t* base = smem_raw + (al - s0);
+    size_t o = 0;
+    sm.wring = al; o += (size_t)kNW * kW16TileBytes;
+    sm.abase = al + (uint32_t)o; o += (size_t)NSLOT * 2 * T::A_PART;
+    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 64 * 4;
+    sm.stat = reinterpret_cast<float2*>(base + o); o += (size_t)NSLOT * T::G * 32 * 8;
+    sm.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
+    sm.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
+    sm.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * 64 * 4;
+    sm.coef = reinterpret_cast<float*>(base + o); o += 64 * 4;
+    sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
+    sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_aready = al + (uint32_t)o; o += 8 * 2;
+    sm.bar_acc = al + (uint32_t)o; o += 8 * 2;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
+    // zero the A images once: padding rows / columns are never written again
+    uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);
+    for (int i = tid; i < NSLOT * 2 * T::A_PART / 16; i += blockDim.x) az[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < 3 * 32; i += blockDim.x) {
+    const int n = i / 32, g = i % 32;
+    sm.gnp[i] = make_float4(w.gn[(2 * n) * kC + 2 * g], w.gn[(2 * n) * kC + 2 * g + 1], w.gn[(2 * n + 1) * kC + 2 * g],
+                            w.gn[(2 * n + 1) * kC + 2 * g + 1]);
+  }
+  for (int i = tid; i < 2 * 64; i += blockDim.x) sm.bias[i] = w.bias[i];
+  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.tmapc[i] = w.tmapc[i];
+  const float h = a.mode == MODE_STEP ? ctl->h32 : (a.mode == MODE_PROBE ? ctl->h0_32 : 0.f);
+  if (tid < 64) {   // rows 0..5 stage betas, 6 = C_MID, 7 = C_ERR (misc.py:22-25: (h*c)*k)
+    const int r = tid >> 3, j = tid & 7;
+    double c = 0.0;
+    if (r < 7) c = j < 7 ? kCoef(r, j) : 0.0; else c = j < 7 ? kCErr(j) : 0.0;
+    sm.coef[tid] = A::mul(h, (float)c);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_aready + 8 * i, T::NWARP); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
+    ptx::fence_mbar_init();
+  }
+  if (!worker) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *sm.tmem_slot;
+
+  // ---- super-tile schedule: stream u = (cta, slot) takes super-tiles u, u + stride, ...
+  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int stride = gridDim.x * NSLOT;
+  const int nevals = a.mode == MODE_STEP ? 6 : 1;
+  const bool split = a.conv_mode == CONV_F16X3;
+  bool timeout = false;
+  double acc0 = 0.0, acc1 = 0.0;
+  bool bad = false;
+
+  if (!worker) {
+    // ===== issuer warp: TMA weight ring + every tcgen05.mma of this CTA =====
+    if (tid == NWORK) {
+      int nst[2] = {0, 0};
+      for (int s = 0; s < NSLOT; ++s) {
+        const int u = blockIdx.x * NSLOT + s;
+        nst[s] = u < NST ? (NST - u + stride - 1) / stride : 0;
+      }
+      const uint32_t jobs_full = (uint32_t)nst[NSLOT - 1] * nevals * 2 * NSLOT;   // rounds in which every slot works
+      const uint32_t jobs = (uint32_t)(nst[0] + (NSLOT > 1 ? nst[1] : 0)) * nevals * 2;
+      const uint32_t total = jobs * 9;
+      uint32_t issued = 0, tapx = 0, njob[2] = {0, 0};
+      const uint32_t id128 = idesc_f16(128), id64 = idesc_f16(64);
+#pragma unroll 1
+      for (uint32_t job = 0; job < jobs; ++job) {
+        const int s = job < jobs_full ? (int)(job % NSLOT) : 0;
+        if (!timeout && !ptx::mbar_wait(sm.bar_aready + 8 * s, njob[s] & 1)) timeout = true;
+        ++njob[s];
+        ptx::tc_fence_after();
+        const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          while (issued < total && issued <= tapx + (kNW - kWGap)) {
+            const uint32_t slot = issued % kNW;
+            if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
+            const uint32_t j = issued / 9, tp = issued % 9;
+            const uint32_t cv = j < jobs_full ? (j / NSLOT) & 1 : (j - jobs_full) & 1;
+            ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
+            ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w.w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                          sm.bar_wfull + 8 * slot);
+            ++issued;
+          }
+          const uint32_t slot = tapx % kNW;
+          if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
+          ptx::tc_fence_after();
+          const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
+          const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+#pragma unroll
+          for (int mt = 0; mt < T::MT; ++mt) {
+            const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
+            const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
+              const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
+              const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
+              if (split) {
+                const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+                ptx::mma_f16_ss(d, a_hi, bk, id128, first);     // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
+                ptx::mma_f16_ss(d, a_lo, bk, id64, 1u);         // a_lo * w_hi         -> columns [0,64)
+              } else {
+                ptx::mma_f16_ss(d, a_hi, bk, id64, first);
+              }
+            }
+          }
+          ptx::tc_commit(sm.bar_wfree + 8 * slot);
+          ++tapx;
+        }
+        ptx::tc_commit(sm.bar_acc + 8 * s);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== worker threads =====
+    Who me;
+    me.slot = tid / P; me.wt = tid % P; me.warp = me.wt >> 5; me.lane = tid & 31;
+    me.img_l = me.wt / T::IS;
+    {
+      const int r = me.wt % T::IS, hh = r / T::Wp, ww = r % T::Wp;
+      me.inimg = me.img_l < T::G && hh < T::H && ww < T::W;
+      me.pix = hh * T::W + ww;
+      me.cls = (hh == 0 ? 0 : (hh == T::H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == T::W - 1 ? 2 : 1));
+      if (!me.inimg) me.cls = 4;
+      const int ia = (me.warp * 32) / T::IS, ib = (me.warp * 32 + 31) / T::IS;
+      me.straddle = ia != ib;
+      me.isB = me.img_l != ia;
+    }
+    const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
+    float* Ycur = w.Y[cur]; float* Ynew = w.Y[cur ^ 1];
+    float* Fcur = w.F[cur]; float* Fnew = w.F[cur ^ 1];
+    const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
+    const float sa0 = w.scal[0], sa1 = w.scal[1], inv0 = w.scal[4], inv1 = w.scal[5];
+    uint32_t njob = 0;
+    const int u0 = blockIdx.x * NSLOT + me.slot;
+
+#pragma unroll 1
+    for (int st = u0; st < NST; st += stride) {
+      const int img = st * T::G + me.img_l;
+      const bool valid = me.inimg && img < a.g.N;
+      const size_t goff = valid ? (size_t)img * kC * HW + me.pix : 0;
+      float x[64];
+
+#pragma unroll 1
+      for (int ev = 0; ev < nevals; ++ev) {
+        // ---- stage input (rk_common.py:49-51)
+        if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            float v = 0.f;
+            if (valid) {
+              v = a.y_in[goff + (size_t)c * HW];
+              if (a.mode == MODE_F0) {
+                Ycur[goff + (size_t)c * HW] = v;
+                if (a.out0 != nullptr) a.out0[goff + (size_t)c * HW] = v;
+              }
+            }
+            x[c] = v;
+          }
+        } else {
+          // sources in reference order k1, k2, ... with the zero coefficient beta_62 dropped
+          float* ynew = (a.mode == MODE_STEP && ev == 5) ? Ynew : nullptr;
+          const float* const cf = sm.coef + ev * 8;
+          if (a.mode == MODE_PROBE) {                               // y0 + h0*f0 (misc.py:133)
+            const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
+            const float hc[6] = {h, 0.f, 0.f, 0.f, 0.f, 0.f};
+            stage_in<HW, 1>(x, Ycur, src, hc, nullptr, goff, valid);
+          } else if (ev == 0) {
+            const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
+            const float hc[6] = {cf[0], 0.f, 0.f, 0.f, 0.f, 0.f};
+            stage_in<HW, 1>(x, Ycur, src, hc, ynew, goff, valid);
+          } else if (ev == 1) {
+            const float* src[6] = {Fcur, w.K[0], Fcur, Fcur, Fcur, Fcur};
+            const float hc[6] = {cf[0], cf[1], 0.f, 0.f, 0.f, 0.f};
+            stage_in<HW, 2>(x, Ycur, src, hc, ynew, goff, valid);
+          } else if (ev == 2) {
+            const float* src[6] = {Fcur, w.K[0], w.K[1], Fcur, Fcur, Fcur};
+            const float hc[6] = {cf[0], cf[1], cf[2], 0.f, 0.f, 0.f};
+            stage_in<HW, 3>(x, Ycur, src, hc, ynew, goff, valid);
+          } else if (ev == 3) {
+            const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], Fcur, Fcur};
+            const float hc[6] = {cf[0], cf[1], cf[2], cf[3], 0.f, 0.f};
+            stage_in<HW, 4>(x, Ycur, src, hc, ynew, goff, valid);
+          } else if (ev == 4) {
+            const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], w.K[3], Fcur};
+            const float hc[6] = {cf[0], cf[1], cf[2], cf[3], cf[4], 0.f};
+            stage_in<HW, 5>(x, Ycur, src, hc, ynew, goff, valid);
+          } else {
+            const float* src[6] = {Fcur, w.K[1], w.K[2], w.K[3], w.K[4], Fcur};
+            const float hc[6] = {cf[0], cf[2], cf[3], cf[4], cf[5], 0.f};
+            stage_in<HW, 5>(x, Ycur, src, hc, ynew, goff, valid);
+          }
+        }
+
+        // ---- the dynamics (model.py:339-348)
+        const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
+        const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
+        gn_stats<T>(sm, me, x, valid, a.eps);
+        gn_apply_to_A<T>(sm, me, x, 0, sa0, valid, split);
+        conv_exchange<T>(sm, me, x, tmem, njob, timeout, 0, inv0, t, split);
+        if (!valid) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) x[c] = 0.f;
+        }
+        gn_stats<T>(sm, me, x, valid, a.eps);
+        gn_apply_to_A<T>(sm, me, x, 1, sa1, valid, split);
+        conv_exchange<T>(sm, me, x, tmem, njob, timeout, 1, inv1, t, split);
+        if (!valid) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) x[c] = 0.f;
+        }
+        gn_stats<T>(sm, me, x, valid, a.eps);
+        {
+          const float2* stt = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
+          const float4* gp = sm.gnp + 2 * 32;
+#pragma unroll
+          for (int g = 0; g < 32; ++g) {
+            const float2 s = stt[g];
+            const float4 p = gp[g];
+            const float a0 = s.y * p.x, a1 = s.y * p.y;
+            const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+            x[2 * g] = fmaf(x[2 * g], a0, b0) * a.tsign;
+            x[2 * g + 1] = fmaf(x[2 * g + 1], a1, b1) * a.tsign;
+          }
+        }
+        // ---- k_{ev+2} -> global
+        float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : Fnew) : (a.mode == MODE_F0 ? Fcur : (a.mode == MODE_EVAL ? a.k_out : nullptr));
+        if (kdst != nullptr && valid) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) kdst[goff + (size_t)c * HW] = x[c];
+        }
+      }
+
+      // ---- per-super-tile epilogues: norms that feed the controller (x holds the last k)
+      if (valid) {
+        if (a.mode == MODE_F0) {               // misc.py:121-126
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float y = a.y_in[goff + (size_t)c * HW];
+            const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+            const float uu = A::div(y, scale), vv = A::div(x[c], scale);
+            acc0 += (double)A::mul(uu, uu);
+            acc1 += (double)A::mul(vv, vv);
+          }
+        } else if (a.mode == MODE_PROBE) {     // misc.py:136
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float y = Ycur[goff + (size_t)c * HW];
+            const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+            const float uu = A::div(A::sub(x[c], Fcur[goff + (size_t)c * HW]), scale);
+            acc0 += (double)A::mul(uu, uu);
+          }
+        } else if (a.mode == MODE_STEP) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
+          const float* ce = sm.coef + 7 * 8;
+          const float* cm = sm.coef + 6 * 8;
+          float part = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const size_t o = goff + (size_t)c * HW;
+            const float y0 = Ycur[o], y1 = Ynew[o];
+            const float kk[7] = {Fcur[o], 0.f, w.K[1][o], w.K[2][o], w.K[3][o], w.K[4][o], x[c]};
+            float e = 0.f, md = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              if (j == 1) continue;
+              e = A::add(e, A::mul(ce[j], kk[j]));
+              md = A::add(md, A::mul(cm[j], kk[j]));
+            }
+            bad |= !isfinite(y0);
+            const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
+            const float qv = A::div(e, tol);
+            part += A::mul(qv, qv);
+            w.YMID[o] = A::add(y0, md);
+          }
+          acc0 += (double)part;
+        }
+      }
+    }
+  }
+
+  if (a.mode != MODE_EVAL) {
+    if (bad) atomicOr(w.nonfinite, 1);
+    const double r0 = block_sum(acc0, sm.scratch);
+    const double r1 = block_sum(acc1, sm.scratch);
+    if (tid == 0) {
+      w.partials[blockIdx.x] = r0;
+      w.partials[kPartialBlocksF + blockIdx.x] = r1;
+    }
+  }
+  if (timeout) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (!worker) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---- launch ----------------------------------------------------------------------------------------
+template <int H_, int W_, int NSLOT>
+static int launch_step_shape(const FusedArgs& a, cudaStream_t st) {
+  using T = Tile<H_, W_>;
+  constexpr size_t smem = step_smem_bytes(T::A_PART, NSLOT, T::NWARP, T::G);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NODE_CUDA_OK(cudaFuncSetAttribute(k_step<H_, W_, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int NST = (a.g.N + T::G - 1) / T::G;
+  int grid = (NST + NSLOT - 1) / NSLOT;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  k_step<H_, W_, NSLOT><<<grid, NSLOT * T::P + 32, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int H_, int W_>
+static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
+  using T = Tile<H_, W_>;
+  constexpr bool two = step_smem_bytes(T::A_PART, 2, T::NWARP, T::G) <= 227 * 1024 && 2 * T::MT * 128 <= 512;
+  if constexpr (two) {
+    const int NST = (a.g.N + T::G - 1) / T::G;
+    if (NST > kMaxGrid) return launch_step_shape<H_, W_, 2>(a, st);
+  }
+  return launch_step_shape<H_, W_, 1>(a, st);
+}
+
+}  // namespace node
+
+// One translation unit per feature-map shape (they compile in parallel): step_shape_HxW.cu
+#define NODE_STEP_SHAPE_TU(H, W) \
+  namespace node { int launch_step_##H##x##W(const FusedArgs& a, cudaStream_t st) { return launch_step_slots<H, W>(a, st); } }

@@ -1,0 +1,2 @@
+#include "step_engine.cuh"
+NODE_STEP_SHAPE_TU(8, 8)

@@ -25,7 +25,7 @@ from . import distributed as dist_state
 
 _KNOWN_METHODS = ('explicit_adams', 'fixed_adams', 'adams', 'tsit5', 'dopri5', 'euler', 'midpoint', 'rk4')
 _DOPRI5_OPTIONS = ('first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps')
-CONV_MODES = {'tf32x3': 0, 'tf32': 1, 'simt': 2}
+CONV_MODES = {'f16x3': 0, 'f16': 1, 'simt': 2, 'tf32x3': 3, 'tf32': 4}
 
 last_stats = {}          # filled after every solve: nfe, n_accept, n_reject, trace, route, launches
 # bench.py sets this to a list: the fused route then records a (start, end) CUDA-event pair around
@@ -37,7 +37,7 @@ _step_guess = {}
 
 
 def _conv_mode():
-    name = os.environ.get('NODE_B200_CONV', 'tf32x3')
+    name = os.environ.get('NODE_B200_CONV', 'f16x3')
     if name not in CONV_MODES:
         raise ValueError('NODE_B200_CONV must be one of %s' % sorted(CONV_MODES))
     return CONV_MODES[name]

@@ -18,7 +18,7 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('name', CASES)
 def test_fused_dynamics_kernel(native_lib, golden, monkeypatch, name, mode):
     from node_b200 import solver
@@ -45,7 +45,7 @@ def test_tf32_single_pass_mode_is_reported_separately(native_lib, golden, monkey
     assert 2e-5 < e < 5e-3, e        # 1xTF32 is outside the fp32 contract, by about this much
 
 
-@pytest.mark.parametrize('mode', ['simt', 'tf32x3'])
+@pytest.mark.parametrize('mode', ['simt', 'tf32x3', 'f16x3'])
 @pytest.mark.parametrize('name', CASES)
 def test_fused_solve_matches_reference(native_lib, golden, monkeypatch, name, mode):
     from node_b200 import odeint, solver
