@@ -46,21 +46,22 @@ struct Tile {
 };
 
 __host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
-  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
+  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 32 * 4 +
          (size_t)NSLOT * G * 32 * 8 + 3 * 32 * 16 + 2 * 64 * 4 + 2 * 9 * 64 * 4 + 64 * 4 + 32 * 8 + 16 * 8 + 64;
 }
 
 struct StepSmem {
   uint32_t wring;        // shared address of the weight ring
   uint32_t abase;        // shared address of slot 0's A image (hi part)
-  float* part;           // [NSLOT][NWARP][2][32] warp partials of the GroupNorm reductions
+  float* part;           // [NSLOT][NWARP][2][16] warp partials of the GroupNorm reductions
   float2* stat;          // [NSLOT][G][32] (mean, rstd)
   float4* gnp;           // [3][32] (gamma0, gamma1, beta0, beta1) per group
   float* bias;           // [2][64]
   float* tmapc;          // [2][9][64]
   float* coef;           // [8][8] h * coefficient table
   double* scratch;       // 32 doubles
-  uint32_t bar_wfull, bar_wfree, bar_aready, bar_acc;
+  uint32_t bar_wfull, bar_wfree, bar_turn, bar_acc;
+  volatile uint32_t* ring;   // [0] weight tiles requested, [1] taps consumed (owned by whoever holds the turn)
   uint32_t* tmem_slot;
 };
 
@@ -68,22 +69,14 @@ __device__ __forceinline__ void slot_sync(int slot, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(nthreads) : "memory");
 }
 
-// Sum 32 per-lane values across the warp; lane L returns the total of u[L] (31 shuffles).
-__device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
-  float a[16], b[8], c[4], d[2];
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float send = up ? u[i] : u[i + 16], keep = up ? u[i + 16] : u[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
+// Sum 16 per-lane values across the warp; lanes L and L^16 return the total of u[L & 15] (16 shuffles).
+__device__ __forceinline__ float xreduce16(const float (&u)[16], int lane) {
+  float b[8], c[4], d[2];
   {
     const bool up = lane & 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      const float send = up ? u[i] : u[i + 8], keep = up ? u[i + 8] : u[i];
       b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
   }
@@ -105,7 +98,8 @@ __device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
   }
   const bool up = lane & 1;
   const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  const float r = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  return r + __shfl_xor_sync(0xffffffffu, r, 16);
 }
 
 // Per-thread constants of a worker.
@@ -117,65 +111,75 @@ struct Who {
   int pix;                       // h*W + w
 };
 
-// One GroupNorm reduction round: u[g] summed over every pixel of the image -> result[img][g] through `fin`.
-template <class T, class Fin>
-__device__ __forceinline__ void gn_reduce(const StepSmem& sm, const Who& me, float (&u)[32], Fin fin) {
-  float* part = sm.part + (me.slot * T::NWARP + me.warp) * 64;
-  if (!me.straddle) {
-    part[me.lane] = xreduce32(u, me.lane);
-  } else {
-    float v[32];
+// All per-pixel work runs on HALF of the channels at a time (32 channels = 16 GroupNorm groups): GroupNorm
+// cells never couple the halves, and 32 live values per thread leave room for two worker slots per SM.
+
+// One GroupNorm reduction round over 16 groups: val(j) summed over every pixel of the image ->
+// fin(&stat[img][16*hb + j], total). A warp that straddles two images reduces twice.
+template <class T, class Val, class Fin>
+__device__ __forceinline__ void gn_reduce(const StepSmem& sm, const Who& me, int hb, Val val, Fin fin) {
+  float* part = sm.part + (me.slot * T::NWARP + me.warp) * 32;
+  {
+    float u[16];
 #pragma unroll
-    for (int g = 0; g < 32; ++g) v[g] = me.isB ? 0.f : u[g];
-    part[me.lane] = xreduce32(v, me.lane);
+    for (int j = 0; j < 16; ++j) u[j] = val(j);
+    if (!me.straddle) {
+      const float r = xreduce16(u, me.lane);
+      if (me.lane < 16) part[me.lane] = r;
+    } else {
+      float v[16];
 #pragma unroll
-    for (int g = 0; g < 32; ++g) v[g] = me.isB ? u[g] : 0.f;
-    part[32 + me.lane] = xreduce32(v, me.lane);
+      for (int j = 0; j < 16; ++j) v[j] = me.isB ? 0.f : u[j];
+      const float ra = xreduce16(v, me.lane);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = me.isB ? u[j] : 0.f;
+      const float rb = xreduce16(v, me.lane);
+      if (me.lane < 16) { part[me.lane] = ra; part[16 + me.lane] = rb; }
+    }
   }
   slot_sync(me.slot, T::P);
-  if (me.wt < T::G * 32) {
-    const int img = me.wt >> 5, g = me.wt & 31;
-    const float* pp = sm.part + me.slot * T::NWARP * 64;
+  if (me.wt < T::G * 16) {
+    const int img = me.wt >> 4, g = me.wt & 15;
+    const float* pp = sm.part + me.slot * T::NWARP * 32;
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < T::NWARP; ++w) {
       const int ia = (w * 32) / T::IS, ib = (w * 32 + 31) / T::IS;
-      if (ia == img) tot += pp[w * 64 + g];
-      if (ib != ia && ib == img) tot += pp[w * 64 + 32 + g];
+      if (ia == img) tot += pp[w * 32 + g];
+      if (ib != ia && ib == img) tot += pp[w * 32 + 16 + g];
     }
-    fin(sm.stat + (me.slot * T::G + img) * 32 + g, tot);
+    fin(sm.stat + (me.slot * T::G + img) * 32 + 16 * hb + g, tot);
   }
   slot_sync(me.slot, T::P);
 }
 
-// GroupNorm statistics of x (64 channels of this thread's pixel) over the whole image: two passes
-// (mean, then squared deviations) like the reference's native_group_norm; leaves (mean, rstd) in sm.stat.
+// GroupNorm statistics of x (channels [32*hb, 32*hb+32) of this thread's pixel) over the whole image: two
+// passes (mean, then squared deviations) like the reference's native_group_norm; leaves (mean, rstd) in sm.stat.
 template <class T>
-__device__ __forceinline__ void gn_stats(const StepSmem& sm, const Who& me, const float (&x)[64], bool valid, float eps) {
+__device__ __forceinline__ void gn_stats(const StepSmem& sm, const Who& me, int hb, const float (&x)[32], bool valid, float eps) {
   constexpr float inv_n = 1.0f / (float)(kCpg * T::HW);
-  float u[32];
-#pragma unroll
-  for (int g = 0; g < 32; ++g) u[g] = x[2 * g] + x[2 * g + 1];          // x is zero on padding
-  gn_reduce<T>(sm, me, u, [&](float2* dst, float tot) { dst->x = tot * inv_n; });
-  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
-#pragma unroll
-  for (int g = 0; g < 32; ++g) {
-    const float m = st[g].x;
-    const float d0 = x[2 * g] - m, d1 = x[2 * g + 1] - m;
-    u[g] = valid ? fmaf(d0, d0, d1 * d1) : 0.f;
-  }
-  gn_reduce<T>(sm, me, u, [&](float2* dst, float tot) { dst->y = 1.0f / sqrtf(tot * inv_n + eps); });
+  gn_reduce<T>(sm, me, hb, [&](int j) { return x[2 * j] + x[2 * j + 1]; },          // x is zero on padding
+               [&](float2* dst, float tot) { dst->x = tot * inv_n; });
+  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+  gn_reduce<T>(sm, me, hb,
+               [&](int j) {
+                 const float m = st[j].x;
+                 const float d0 = x[2 * j] - m, d1 = x[2 * j + 1] - m;
+                 return valid ? fmaf(d0, d0, d1 * d1) : 0.f;
+               },
+               [&](float2* dst, float tot) { dst->y = 1.0f / sqrtf(tot * inv_n + eps); });
 }
 
-// relu(GN(x)) * scale split into fp16 hi + lo and written as this position's row of the A image.
+// relu(GN(x)) * scale split into fp16 hi + lo and written into this position's row of the A image
+// (k-chunks [4*hb, 4*hb+4)).
 template <class T>
-__device__ __forceinline__ void gn_apply_to_A(const StepSmem& sm, const Who& me, const float (&x)[64], int n, float scale,
+__device__ __forceinline__ void gn_apply_to_A(const StepSmem& sm, const Who& me, int hb, const float (&x)[32], int n, float scale,
                                               bool valid, bool split) {
-  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
-  const float4* gp = sm.gnp + n * 32;
-  const uint32_t row = sm.abase + me.slot * 2 * T::A_PART + (T::HALO + me.wt) * 16;
+  const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+  const float4* gp = sm.gnp + n * 32 + 16 * hb;
+  const uint32_t row = sm.abase + me.slot * 2 * T::A_PART + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
 #pragma unroll
-  for (int kc = 0; kc < 8; ++kc) {
+  for (int kc = 0; kc < 4; ++kc) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -200,79 +204,145 @@ __device__ __forceinline__ void gn_apply_to_A(const StepSmem& sm, const Who& me,
   }
 }
 
-// Hand the A image to the issuer, wait for the accumulators, x <- acc/scale + bias + t*Tmap.
-template <class T>
-__device__ __forceinline__ void conv_exchange(const StepSmem& sm, const Who& me, float (&x)[64], uint32_t tmem, uint32_t& njob,
-                                              bool& timeout, int cv, float inv_scale, float t, bool split) {
-  ptx::fence_proxy_async();
-  ptx::tc_fence_before();
-  __syncwarp();
-  if (me.lane == 0) ptx::mbar_arrive(sm.bar_aready + 8 * me.slot);
+constexpr uint32_t kIdF16N128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);   // kind::f16, fp16 x fp16 -> fp32, M128
+constexpr uint32_t kIdF16N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// Global conv-job schedule of a CTA: jobs alternate between the slots while both have super-tiles left.
+struct Jobs {
+  uint32_t jobs_full, jobs;     // jobs in rounds where every slot works / all jobs
+  __device__ __forceinline__ int slot_of(uint32_t j, int nslot) const { return j < jobs_full ? (int)(j % nslot) : 0; }
+  __device__ __forceinline__ uint32_t conv_of(uint32_t j, int nslot) const { return j < jobs_full ? (j / nslot) & 1u : (j - jobs_full) & 1u; }
+};
+
+// Issue one conv job (9 taps) of slot `s`: keep the TMA weight ring fed, issue the tcgen05.mma stream, commit.
+// Runs on ONE thread (the slot's leader); the ring counters live in shared memory and travel with the turn.
+template <class T, int NSLOT>
+__device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, uint32_t tmem,
+                                               int s, uint32_t job, uint32_t nth, bool split, bool& timeout) {
+  if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;   // my slot's nth turn
+  uint32_t issued = sm.ring[0], tapx = sm.ring[1];
+  const uint32_t total = jb.jobs * 9;
+  ptx::tc_fence_after();
+  const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    while (issued < total && issued <= tapx + (kNW - kWGap)) {
+      const uint32_t slot = issued % kNW;
+      if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
+      const uint32_t cv = jb.conv_of(issued / 9, NSLOT), tp = issued % 9;
+      ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
+      ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                    sm.bar_wfull + 8 * slot);
+      ++issued;
+    }
+    const uint32_t slot = tapx % kNW;
+    if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
+    ptx::tc_fence_after();
+    const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
+    const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+#pragma unroll
+    for (int mt = 0; mt < T::MT; ++mt) {
+      const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
+      const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
+        const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
+        const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
+        if (split) {
+          const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+          ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);   // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
+          ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);       // a_lo * w_hi         -> columns [0,64)
+        } else {
+          ptx::mma_f16_ss(d, a_hi, bk, kIdF16N64, first);
+        }
+      }
+    }
+    ptx::tc_commit(sm.bar_wfree + 8 * slot);
+    ++tapx;
+  }
+  ptx::tc_commit(sm.bar_acc + 8 * s);
+  sm.ring[0] = issued; sm.ring[1] = tapx;
+  if (job + 1 < jb.jobs) ptx::mbar_arrive(sm.bar_turn + 8 * jb.slot_of(job + 1, NSLOT));   // release: ring counters travel with it
+}
+
+// Publish the A image and run the conv job on the tensor core; returns when the accumulators are complete.
+template <class T, int NSLOT>
+__device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, const Jobs& jb, const uint16_t* __restrict__ w16,
+                                         uint32_t tmem, uint32_t& njob, uint32_t nfull, bool& timeout, bool split) {
+  const uint32_t job = njob < nfull ? njob * NSLOT + me.slot : jb.jobs_full + (njob - nfull);   // global index of my slot's njob-th job
+  ptx::fence_proxy_async();          // my rows of the A image -> visible to the tensor core
+  ptx::tc_fence_before();            // my tcgen05.ld of the previous accumulators are done
+  slot_sync(me.slot, T::P);
+  if (me.warp == 0) {
+    if (me.lane == 0) issue_conv_job<T, NSLOT>(sm, jb, w16, tmem, me.slot, job, njob, split, timeout);
+    __syncwarp();
+  }
   if (!timeout && !ptx::mbar_wait(sm.bar_acc + 8 * me.slot, njob & 1)) timeout = true;
   ++njob;
   ptx::tc_fence_after();
-  const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128);
-  const float* bs = sm.bias + cv * 64;
-  const float* tm = sm.tmapc + (cv * 9 + me.cls) * 64;
-#pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t v0[16], v1[16];
-    ptx::tmem_ld16(taddr + c0, v0);
-    if (split) ptx::tmem_ld16(taddr + 64 + c0, v1);
-    ptx::tc_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float acc = __uint_as_float(v0[j]);
-      if (split) acc += __uint_as_float(v1[j]);
-      x[c0 + j] = fmaf(acc, inv_scale, fmaf(t, tm[c0 + j], bs[c0 + j]));
-    }
-  }
-  ptx::tc_fence_before();
 }
 
-// x = y + sum_j (h*c_j) k_j over NK sources (rk_common.py:49-51), reference rounding and order.
+// x <- acc/scale + bias + t*Tmap for output channels [32*hb, 32*hb+32) of this thread's position.
+template <class T>
+__device__ __forceinline__ void conv_read(const StepSmem& sm, const Who& me, int hb, float (&x)[32], uint32_t tmem, int cv,
+                                          float inv_scale, float t, bool split, bool valid) {
+  const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128 + 32 * hb);
+  const float* bs = sm.bias + cv * 64 + 32 * hb;
+  const float* tm = sm.tmapc + (cv * 9 + me.cls) * 64 + 32 * hb;
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    uint32_t v0[8], v1[8];
+    ptx::tmem_ld8(taddr + c0, v0);
+    if (split) ptx::tmem_ld8(taddr + 64 + c0, v1);
+    ptx::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float acc = __uint_as_float(v0[j]);
+      if (split) acc += __uint_as_float(v1[j]);
+      x[c0 + j] = valid ? fmaf(acc, inv_scale, fmaf(t, tm[c0 + j], bs[c0 + j])) : 0.f;
+    }
+  }
+}
+
+// x = y + sum_j (h*c_j) k_j over NK sources (rk_common.py:49-51), reference rounding and order, for 32 channels
+// starting at `p0 = goff + 32*hb*HW`.
 template <int HW, int NK>
-__device__ __forceinline__ void stage_in(float (&x)[64], const float* __restrict__ y, const float* const (&src)[6],
-                                         const float (&hc)[6], float* __restrict__ ynew, size_t goff, bool valid) {
+__device__ __forceinline__ void stage_in(float (&x)[32], const float* __restrict__ y, const float* const (&src)[6],
+                                         const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid) {
   using A = Arith<float>;
+  // padding threads read image 0's data (p0 = their pixel offset only) and discard it: no divergent loads
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 4) {
+  for (int c0 = 0; c0 < 32; c0 += 4) {
     float yv[4], kv[NK][4];
-    if (valid) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        yv[i] = y[goff + (size_t)(c0 + i) * HW];
+    for (int i = 0; i < 4; ++i) {
+      yv[i] = ptx::ldg_ordered(y + p0 + (size_t)(c0 + i) * HW);
 #pragma unroll
-        for (int j = 0; j < NK; ++j) kv[j][i] = src[j][goff + (size_t)(c0 + i) * HW];
-      }
+      for (int j = 0; j < NK; ++j) kv[j][i] = ptx::ldg_ordered(src[j] + p0 + (size_t)(c0 + i) * HW);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float r = 0.f;
-      if (valid) {
-        float s = 0.f;
+      float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[j][i]));
-        r = A::add(yv[i], s);
-        if (ynew != nullptr) ynew[goff + (size_t)(c0 + i) * HW] = r;
-      }
-      x[c0 + i] = r;
+      for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[j][i]));
+      const float r = A::add(yv[i], s);
+      if (ynew != nullptr && valid) ynew[p0 + (size_t)(c0 + i) * HW] = r;
+      x[c0 + i] = valid ? r : 0.f;
     }
+    __syncwarp();   // scheduling fence: keeps the loads of later channels from being hoisted above this batch (register budget)
   }
 }
 
-__host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-
 template <int H_, int W_, int NSLOT>
-__global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const FusedArgs a) {
+__global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const FusedArgs a) {
   using T = Tile<H_, W_>;
   using A = Arith<float>;
-  constexpr int HW = T::HW, P = T::P, NWORK = NSLOT * P;
+  constexpr int HW = T::HW, P = T::P;
   extern __shared__ uint8_t smem_raw[];
   const FusedWs& w = a.w;
   node_ctl_t* ctl = w.ctl;
   const int tid = threadIdx.x;
-  const bool worker = tid < NWORK;
 
   if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform
 
@@ -285,7 +355,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
     size_t o = 0;
     sm.wring = al; o += (size_t)kNW * kW16TileBytes;
     sm.abase = al + (uint32_t)o; o += (size_t)NSLOT * 2 * T::A_PART;
-    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 64 * 4;
+    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 32 * 4;
     sm.stat = reinterpret_cast<float2*>(base + o); o += (size_t)NSLOT * T::G * 32 * 8;
     sm.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
     sm.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
@@ -294,8 +364,9 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
     sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
     sm.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
-    sm.bar_aready = al + (uint32_t)o; o += 8 * 2;
+    sm.bar_turn = al + (uint32_t)o; o += 8 * 2;
     sm.bar_acc = al + (uint32_t)o; o += 8 * 2;
+    sm.ring = reinterpret_cast<volatile uint32_t*>(base + o); o += 16;
     sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
     // zero the A images once: padding rows / columns are never written again
     uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);
@@ -317,10 +388,12 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
   }
   if (tid == 0) {
     for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_aready + 8 * i, T::NWARP); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_turn + 8 * i, 1); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
+    sm.ring[0] = 0; sm.ring[1] = 0;
     ptx::fence_mbar_init();
+    ptx::mbar_arrive(sm.bar_turn);          // the first conv job belongs to slot 0
   }
-  if (!worker) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+  if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
@@ -335,71 +408,22 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
   bool timeout = false;
   double acc0 = 0.0, acc1 = 0.0;
   bool bad = false;
-
-  if (!worker) {
-    // ===== issuer warp: TMA weight ring + every tcgen05.mma of this CTA =====
-    if (tid == NWORK) {
-      int nst[2] = {0, 0};
-      for (int s = 0; s < NSLOT; ++s) {
-        const int u = blockIdx.x * NSLOT + s;
-        nst[s] = u < NST ? (NST - u + stride - 1) / stride : 0;
-      }
-      const uint32_t jobs_full = (uint32_t)nst[NSLOT - 1] * nevals * 2 * NSLOT;   // rounds in which every slot works
-      const uint32_t jobs = (uint32_t)(nst[0] + (NSLOT > 1 ? nst[1] : 0)) * nevals * 2;
-      const uint32_t total = jobs * 9;
-      uint32_t issued = 0, tapx = 0, njob[2] = {0, 0};
-      const uint32_t id128 = idesc_f16(128), id64 = idesc_f16(64);
-#pragma unroll 1
-      for (uint32_t job = 0; job < jobs; ++job) {
-        const int s = job < jobs_full ? (int)(job % NSLOT) : 0;
-        if (!timeout && !ptx::mbar_wait(sm.bar_aready + 8 * s, njob[s] & 1)) timeout = true;
-        ++njob[s];
-        ptx::tc_fence_after();
-        const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          while (issued < total && issued <= tapx + (kNW - kWGap)) {
-            const uint32_t slot = issued % kNW;
-            if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
-            const uint32_t j = issued / 9, tp = issued % 9;
-            const uint32_t cv = j < jobs_full ? (j / NSLOT) & 1 : (j - jobs_full) & 1;
-            ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
-            ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w.w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
-                          sm.bar_wfull + 8 * slot);
-            ++issued;
-          }
-          const uint32_t slot = tapx % kNW;
-          if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
-          ptx::tc_fence_after();
-          const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
-          const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+  Jobs jb;
+  uint32_t nfull;                 // conv jobs of a slot inside the rounds where every slot works
+  {
+    int nst[2] = {0, 0};
 #pragma unroll
-          for (int mt = 0; mt < T::MT; ++mt) {
-            const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
-            const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-              const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
-              const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
-              if (split) {
-                const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
-                ptx::mma_f16_ss(d, a_hi, bk, id128, first);     // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
-                ptx::mma_f16_ss(d, a_lo, bk, id64, 1u);         // a_lo * w_hi         -> columns [0,64)
-              } else {
-                ptx::mma_f16_ss(d, a_hi, bk, id64, first);
-              }
-            }
-          }
-          ptx::tc_commit(sm.bar_wfree + 8 * slot);
-          ++tapx;
-        }
-        ptx::tc_commit(sm.bar_acc + 8 * s);
-      }
+    for (int s = 0; s < NSLOT; ++s) {
+      const int u = blockIdx.x * NSLOT + s;
+      nst[s] = u < NST ? (NST - u + stride - 1) / stride : 0;
     }
-    __syncwarp();
-  } else {
-    // ===== worker threads =====
+    nfull = (uint32_t)nst[NSLOT - 1] * nevals * 2;
+    jb.jobs_full = nfull * NSLOT;
+    jb.jobs = (uint32_t)(nst[0] + (NSLOT > 1 ? nst[1] : 0)) * nevals * 2;
+  }
+
+  {
+    // ===== every thread is a worker: one position of its slot's strip =====
     Who me;
     me.slot = tid / P; me.wt = tid % P; me.warp = me.wt >> 5; me.lane = tid & 31;
     me.img_l = me.wt / T::IS;
@@ -414,10 +438,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
       me.isB = me.img_l != ia;
     }
     const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
-    float* Ycur = w.Y[cur]; float* Ynew = w.Y[cur ^ 1];
-    float* Fcur = w.F[cur]; float* Fnew = w.F[cur ^ 1];
     const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
-    const float sa0 = w.scal[0], sa1 = w.scal[1], inv0 = w.scal[4], inv1 = w.scal[5];
     uint32_t njob = 0;
     const int u0 = blockIdx.x * NSLOT + me.slot;
 
@@ -425,141 +446,153 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
     for (int st = u0; st < NST; st += stride) {
       const int img = st * T::G + me.img_l;
       const bool valid = me.inimg && img < a.g.N;
-      const size_t goff = valid ? (size_t)img * kC * HW + me.pix : 0;
-      float x[64];
+      const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+      float x[32];
 
 #pragma unroll 1
       for (int ev = 0; ev < nevals; ++ev) {
-        // ---- stage input (rk_common.py:49-51)
-        if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            float v = 0.f;
-            if (valid) {
-              v = a.y_in[goff + (size_t)c * HW];
-              if (a.mode == MODE_F0) {
-                Ycur[goff + (size_t)c * HW] = v;
-                if (a.out0 != nullptr) a.out0[goff + (size_t)c * HW] = v;
-              }
-            }
-            x[c] = v;
-          }
-        } else {
-          // sources in reference order k1, k2, ... with the zero coefficient beta_62 dropped
-          float* ynew = (a.mode == MODE_STEP && ev == 5) ? Ynew : nullptr;
-          const float* const cf = sm.coef + ev * 8;
-          if (a.mode == MODE_PROBE) {                               // y0 + h0*f0 (misc.py:133)
-            const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
-            const float hc[6] = {h, 0.f, 0.f, 0.f, 0.f, 0.f};
-            stage_in<HW, 1>(x, Ycur, src, hc, nullptr, goff, valid);
-          } else if (ev == 0) {
-            const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
-            const float hc[6] = {cf[0], 0.f, 0.f, 0.f, 0.f, 0.f};
-            stage_in<HW, 1>(x, Ycur, src, hc, ynew, goff, valid);
-          } else if (ev == 1) {
-            const float* src[6] = {Fcur, w.K[0], Fcur, Fcur, Fcur, Fcur};
-            const float hc[6] = {cf[0], cf[1], 0.f, 0.f, 0.f, 0.f};
-            stage_in<HW, 2>(x, Ycur, src, hc, ynew, goff, valid);
-          } else if (ev == 2) {
-            const float* src[6] = {Fcur, w.K[0], w.K[1], Fcur, Fcur, Fcur};
-            const float hc[6] = {cf[0], cf[1], cf[2], 0.f, 0.f, 0.f};
-            stage_in<HW, 3>(x, Ycur, src, hc, ynew, goff, valid);
-          } else if (ev == 3) {
-            const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], Fcur, Fcur};
-            const float hc[6] = {cf[0], cf[1], cf[2], cf[3], 0.f, 0.f};
-            stage_in<HW, 4>(x, Ycur, src, hc, ynew, goff, valid);
-          } else if (ev == 4) {
-            const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], w.K[3], Fcur};
-            const float hc[6] = {cf[0], cf[1], cf[2], cf[3], cf[4], 0.f};
-            stage_in<HW, 5>(x, Ycur, src, hc, ynew, goff, valid);
-          } else {
-            const float* src[6] = {Fcur, w.K[1], w.K[2], w.K[3], w.K[4], Fcur};
-            const float hc[6] = {cf[0], cf[2], cf[3], cf[4], cf[5], 0.f};
-            stage_in<HW, 5>(x, Ycur, src, hc, ynew, goff, valid);
-          }
-        }
-
-        // ---- the dynamics (model.py:339-348)
         const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
         const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
-        gn_stats<T>(sm, me, x, valid, a.eps);
-        gn_apply_to_A<T>(sm, me, x, 0, sa0, valid, split);
-        conv_exchange<T>(sm, me, x, tmem, njob, timeout, 0, inv0, t, split);
-        if (!valid) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) x[c] = 0.f;
-        }
-        gn_stats<T>(sm, me, x, valid, a.eps);
-        gn_apply_to_A<T>(sm, me, x, 1, sa1, valid, split);
-        conv_exchange<T>(sm, me, x, tmem, njob, timeout, 1, inv1, t, split);
-        if (!valid) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) x[c] = 0.f;
-        }
-        gn_stats<T>(sm, me, x, valid, a.eps);
-        {
-          const float2* stt = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32;
-          const float4* gp = sm.gnp + 2 * 32;
-#pragma unroll
-          for (int g = 0; g < 32; ++g) {
-            const float2 s = stt[g];
-            const float4 p = gp[g];
-            const float a0 = s.y * p.x, a1 = s.y * p.y;
-            const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
-            x[2 * g] = fmaf(x[2 * g], a0, b0) * a.tsign;
-            x[2 * g + 1] = fmaf(x[2 * g + 1], a1, b1) * a.tsign;
-          }
-        }
-        // ---- k_{ev+2} -> global
-        float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : Fnew) : (a.mode == MODE_F0 ? Fcur : (a.mode == MODE_EVAL ? a.k_out : nullptr));
-        if (kdst != nullptr && valid) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) kdst[goff + (size_t)c * HW] = x[c];
-        }
-      }
 
-      // ---- per-super-tile epilogues: norms that feed the controller (x holds the last k)
-      if (valid) {
-        if (a.mode == MODE_F0) {               // misc.py:121-126
+        // ---- stage input (rk_common.py:49-51) -> GN1 -> ReLU -> A image of conv1
+#pragma unroll 1
+        for (int hb = 0; hb < 2; ++hb) {
+          const size_t p0 = goff + (size_t)(32 * hb) * HW;
+          float* const Ycur = w.Y[cur];
+          const float* const Fcur = w.F[cur];
+          if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float y = a.y_in[goff + (size_t)c * HW];
-            const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-            const float uu = A::div(y, scale), vv = A::div(x[c], scale);
-            acc0 += (double)A::mul(uu, uu);
-            acc1 += (double)A::mul(vv, vv);
-          }
-        } else if (a.mode == MODE_PROBE) {     // misc.py:136
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float y = Ycur[goff + (size_t)c * HW];
-            const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-            const float uu = A::div(A::sub(x[c], Fcur[goff + (size_t)c * HW]), scale);
-            acc0 += (double)A::mul(uu, uu);
-          }
-        } else if (a.mode == MODE_STEP) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
-          const float* ce = sm.coef + 7 * 8;
-          const float* cm = sm.coef + 6 * 8;
-          float part = 0.f;
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const size_t o = goff + (size_t)c * HW;
-            const float y0 = Ycur[o], y1 = Ynew[o];
-            const float kk[7] = {Fcur[o], 0.f, w.K[1][o], w.K[2][o], w.K[3][o], w.K[4][o], x[c]};
-            float e = 0.f, md = 0.f;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-              if (j == 1) continue;
-              e = A::add(e, A::mul(ce[j], kk[j]));
-              md = A::add(md, A::mul(cm[j], kk[j]));
+            for (int c = 0; c < 32; ++c) {
+              float v = 0.f;
+              if (valid) {
+                v = a.y_in[p0 + (size_t)c * HW];
+                if (a.mode == MODE_F0) {
+                  Ycur[p0 + (size_t)c * HW] = v;
+                  if (a.out0 != nullptr) a.out0[p0 + (size_t)c * HW] = v;
+                }
+              }
+              x[c] = v;
             }
-            bad |= !isfinite(y0);
-            const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
-            const float qv = A::div(e, tol);
-            part += A::mul(qv, qv);
-            w.YMID[o] = A::add(y0, md);
+          } else {
+            // sources in reference order k1, k2, ... with the zero coefficient beta_62 dropped
+            float* ynew = (a.mode == MODE_STEP && ev == 5) ? w.Y[cur ^ 1] : nullptr;
+            const float* const cf = sm.coef + ev * 8;
+            if (a.mode == MODE_PROBE) {                               // y0 + h0*f0 (misc.py:133)
+              const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
+              const float hc[6] = {h, 0.f, 0.f, 0.f, 0.f, 0.f};
+              stage_in<HW, 1>(x, Ycur, src, hc, nullptr, p0, valid);
+            } else if (ev == 0) {
+              const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
+              const float hc[6] = {cf[0], 0.f, 0.f, 0.f, 0.f, 0.f};
+              stage_in<HW, 1>(x, Ycur, src, hc, ynew, p0, valid);
+            } else if (ev == 1) {
+              const float* src[6] = {Fcur, w.K[0], Fcur, Fcur, Fcur, Fcur};
+              const float hc[6] = {cf[0], cf[1], 0.f, 0.f, 0.f, 0.f};
+              stage_in<HW, 2>(x, Ycur, src, hc, ynew, p0, valid);
+            } else if (ev == 2) {
+              const float* src[6] = {Fcur, w.K[0], w.K[1], Fcur, Fcur, Fcur};
+              const float hc[6] = {cf[0], cf[1], cf[2], 0.f, 0.f, 0.f};
+              stage_in<HW, 3>(x, Ycur, src, hc, ynew, p0, valid);
+            } else if (ev == 3) {
+              const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], Fcur, Fcur};
+              const float hc[6] = {cf[0], cf[1], cf[2], cf[3], 0.f, 0.f};
+              stage_in<HW, 4>(x, Ycur, src, hc, ynew, p0, valid);
+            } else if (ev == 4) {
+              const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], w.K[3], Fcur};
+              const float hc[6] = {cf[0], cf[1], cf[2], cf[3], cf[4], 0.f};
+              stage_in<HW, 5>(x, Ycur, src, hc, ynew, p0, valid);
+            } else {
+              const float* src[6] = {Fcur, w.K[1], w.K[2], w.K[3], w.K[4], Fcur};
+              const float hc[6] = {cf[0], cf[2], cf[3], cf[4], cf[5], 0.f};
+              stage_in<HW, 5>(x, Ycur, src, hc, ynew, p0, valid);
+            }
           }
-          acc0 += (double)part;
+          gn_stats<T>(sm, me, hb, x, valid, a.eps);
+          gn_apply_to_A<T>(sm, me, hb, x, 0, w.scal[0], valid, split);
+        }
+        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+
+        // ---- conv1 epilogue -> GN2 -> ReLU -> A image of conv2 (model.py:343-346)
+#pragma unroll 1
+        for (int hb = 0; hb < 2; ++hb) {
+          conv_read<T>(sm, me, hb, x, tmem, 0, w.scal[4], t, split, valid);
+          gn_stats<T>(sm, me, hb, x, valid, a.eps);
+          gn_apply_to_A<T>(sm, me, hb, x, 1, w.scal[1], valid, split);
+        }
+        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+
+        // ---- conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller
+#pragma unroll 1
+        for (int hb = 0; hb < 2; ++hb) {
+          conv_read<T>(sm, me, hb, x, tmem, 1, w.scal[5], t, split, valid);
+          gn_stats<T>(sm, me, hb, x, valid, a.eps);
+          {
+            const float2* stt = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+            const float4* gp = sm.gnp + 2 * 32 + 16 * hb;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              const float2 s = stt[g];
+              const float4 p = gp[g];
+              const float a0 = s.y * p.x, a1 = s.y * p.y;
+              const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+              x[2 * g] = fmaf(x[2 * g], a0, b0) * a.tsign;
+              x[2 * g + 1] = fmaf(x[2 * g + 1], a1, b1) * a.tsign;
+            }
+          }
+          if (!valid) continue;
+          const size_t p0 = goff + (size_t)(32 * hb) * HW;
+          float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : w.F[cur ^ 1]) : (a.mode == MODE_F0 ? w.F[cur] : (a.mode == MODE_EVAL ? a.k_out : nullptr));
+          if (kdst != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) kdst[p0 + (size_t)c * HW] = x[c];
+          }
+          if (a.mode == MODE_F0) {               // misc.py:121-126
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float y = a.y_in[p0 + (size_t)c * HW];
+              const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+              const float uu = A::div(y, scale), vv = A::div(x[c], scale);
+              acc0 += (double)A::mul(uu, uu);
+              acc1 += (double)A::mul(vv, vv);
+            }
+          } else if (a.mode == MODE_PROBE) {     // misc.py:136
+            const float* const Ycur = w.Y[cur];
+            const float* const Fcur = w.F[cur];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float y = Ycur[p0 + (size_t)c * HW];
+              const float scale = A::add(atol, A::mul(fabsf(y), rtol));
+              const float uu = A::div(A::sub(x[c], Fcur[p0 + (size_t)c * HW]), scale);
+              acc0 += (double)A::mul(uu, uu);
+            }
+          } else if (a.mode == MODE_STEP && ev == 5) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
+            const float* ce = sm.coef + 7 * 8;
+            const float* cm = sm.coef + 6 * 8;
+            const float* const Ycur = w.Y[cur];
+            const float* const Ynew = w.Y[cur ^ 1];
+            const float* const Fcur = w.F[cur];
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const size_t o = p0 + (size_t)c * HW;
+              const float y0 = ptx::ldg_ordered(Ycur + o), y1 = ptx::ldg_ordered(Ynew + o);
+              const float kk[7] = {ptx::ldg_ordered(Fcur + o), 0.f, ptx::ldg_ordered(w.K[1] + o), ptx::ldg_ordered(w.K[2] + o),
+                                   ptx::ldg_ordered(w.K[3] + o), ptx::ldg_ordered(w.K[4] + o), x[c]};
+              float e = 0.f, md = 0.f;
+#pragma unroll
+              for (int j = 0; j < 7; ++j) {
+                if (j == 1) continue;
+                e = A::add(e, A::mul(ce[j], kk[j]));
+                md = A::add(md, A::mul(cm[j], kk[j]));
+              }
+              bad |= !isfinite(y0);
+              const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
+              const float qv = A::div(e, tol);
+              part += A::mul(qv, qv);
+              w.YMID[o] = A::add(y0, md);
+            }
+            acc0 += (double)part;
+          }
         }
       }
     }
@@ -577,7 +610,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P + 32, 1) k_step(const 
   if (timeout) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
   ptx::tc_fence_before();
   __syncthreads();
-  if (!worker) ptx::tmem_dealloc(tmem, kTmemCols);
+  if (tid < 32) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
 // ---- launch ----------------------------------------------------------------------------------------
@@ -594,7 +627,7 @@ static int launch_step_shape(const FusedArgs& a, cudaStream_t st) {
   const int NST = (a.g.N + T::G - 1) / T::G;
   int grid = (NST + NSLOT - 1) / NSLOT;
   if (grid > kMaxGrid) grid = kMaxGrid;
-  k_step<H_, W_, NSLOT><<<grid, NSLOT * T::P + 32, smem, st>>>(a);
+  k_step<H_, W_, NSLOT><<<grid, NSLOT * T::P, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
