@@ -36,6 +36,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
+// Same, for waits that are expected to last thousands of cycles (a whole conv job): back off between polls so
+// the polling warps do not compete for issue / MIO slots with the warps that still have work.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
+    __nanosleep(64);
+    if (mbar_try_wait(bar, parity)) return true;
+  }
+  return false;
+}
+
 // 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -20,6 +20,7 @@
 //     tensor core runs the taps of one slot the other slot's threads do epilogue / GroupNorm work.
 #pragma once
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "fused_common.cuh"
 
 namespace node {
@@ -49,6 +50,13 @@ __host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int 
   return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 32 * 4 +
          (size_t)NSLOT * G * 32 * 8 + 3 * 32 * 16 + 2 * 64 * 4 + 2 * 9 * 64 * 4 + 64 * 4 + 32 * 8 + 16 * 8 + 64;
 }
+
+// Tuning aid: when enabled (node_b200_step_debug), CTA 0 records clock64() stamps of every conv job of each slot:
+// [slot][job][0..3] = A image published, turn acquired, MMAs issued, accumulators complete.
+#ifdef NODE_STEP_DEBUG
+static __device__ long long g_step_dbg[2 * 256 * 4];
+static __device__ long long g_step_dbg2[2 * 256 * 2];   // clocks the leader waited for weights to land / for ring slots to free
+#endif
 
 struct StepSmem {
   uint32_t wring;        // shared address of the weight ring
@@ -220,6 +228,9 @@ template <class T, int NSLOT>
 __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, uint32_t tmem,
                                                int s, uint32_t job, uint32_t nth, bool split, bool& timeout) {
   if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;   // my slot's nth turn
+#ifdef NODE_STEP_DEBUG
+  if (blockIdx.x == 0 && nth < 256) g_step_dbg[(s * 256 + nth) * 4 + 1] = clock64();
+#endif
   uint32_t issued = sm.ring[0], tapx = sm.ring[1];
   const uint32_t total = jb.jobs * 9;
   ptx::tc_fence_after();
@@ -228,7 +239,13 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
   for (int tap = 0; tap < 9; ++tap) {
     while (issued < total && issued <= tapx + (kNW - kWGap)) {
       const uint32_t slot = issued % kNW;
+#ifdef NODE_STEP_DEBUG
+      const long long q0 = clock64();
+#endif
       if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
+#ifdef NODE_STEP_DEBUG
+      if (blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 1] += clock64() - q0;
+#endif
       const uint32_t cv = jb.conv_of(issued / 9, NSLOT), tp = issued % 9;
       ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
       ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
@@ -236,9 +253,19 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
       ++issued;
     }
     const uint32_t slot = tapx % kNW;
+#ifdef NODE_STEP_DEBUG
+    const long long q1 = clock64();
+#endif
     if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
+#ifdef NODE_STEP_DEBUG
+    if (blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 0] += clock64() - q1;
+#endif
     ptx::tc_fence_after();
+#ifdef NODE_STEP_EXPERIMENT_ALIGNED
+    const int off = (tap / 3 - 1) * 8;      // timing experiment only (wrong results): 128-byte aligned row offsets
+#else
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
+#endif
     const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
 #pragma unroll
     for (int mt = 0; mt < T::MT; ++mt) {
@@ -274,11 +301,21 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
   ptx::fence_proxy_async();          // my rows of the A image -> visible to the tensor core
   ptx::tc_fence_before();            // my tcgen05.ld of the previous accumulators are done
   slot_sync(me.slot, T::P);
+#ifdef NODE_STEP_DEBUG
+  const bool rec = blockIdx.x == 0 && me.wt == 0 && njob < 256;
+  if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 0] = clock64();
+#endif
   if (me.warp == 0) {
     if (me.lane == 0) issue_conv_job<T, NSLOT>(sm, jb, w16, tmem, me.slot, job, njob, split, timeout);
     __syncwarp();
   }
-  if (!timeout && !ptx::mbar_wait(sm.bar_acc + 8 * me.slot, njob & 1)) timeout = true;
+#ifdef NODE_STEP_DEBUG
+  if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 2] = clock64();
+#endif
+  if (!timeout && !ptx::mbar_wait_relaxed(sm.bar_acc + 8 * me.slot, njob & 1)) timeout = true;
+#ifdef NODE_STEP_DEBUG
+  if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 3] = clock64();
+#endif
   ++njob;
   ptx::tc_fence_after();
 }
@@ -311,26 +348,34 @@ template <int HW, int NK>
 __device__ __forceinline__ void stage_in(float (&x)[32], const float* __restrict__ y, const float* const (&src)[6],
                                          const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid) {
   using A = Arith<float>;
-  // padding threads read image 0's data (p0 = their pixel offset only) and discard it: no divergent loads
-#pragma unroll
-  for (int c0 = 0; c0 < 32; c0 += 4) {
-    float yv[4], kv[NK][4];
+  // Padding threads read image 0's data (p0 = their pixel offset only) and discard it: no divergent loads.
+  // Software pipeline over batches of 4 channels: the loads of batch b+1 are in flight while batch b is
+  // combined; the warp-level fences stop the assembler from hoisting every load to the top (register budget).
+  float yv[2][4], kv[2][NK][4];
+  auto load = [&](int b, int c0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      yv[i] = ptx::ldg_ordered(y + p0 + (size_t)(c0 + i) * HW);
+      yv[b][i] = ptx::ldg_ordered(y + p0 + (size_t)(c0 + i) * HW);
 #pragma unroll
-      for (int j = 0; j < NK; ++j) kv[j][i] = ptx::ldg_ordered(src[j] + p0 + (size_t)(c0 + i) * HW);
+      for (int j = 0; j < NK; ++j) kv[b][j][i] = ptx::ldg_ordered(src[j] + p0 + (size_t)(c0 + i) * HW);
     }
+  };
+  load(0, 0);
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 4) {
+    const int b = (c0 >> 2) & 1;
+    if (c0 + 4 < 32) load(b ^ 1, c0 + 4);
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[j][i]));
-      const float r = A::add(yv[i], s);
+      for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[b][j][i]));
+      const float r = A::add(yv[b][i], s);
       if (ynew != nullptr && valid) ynew[p0 + (size_t)(c0 + i) * HW] = r;
       x[c0 + i] = valid ? r : 0.f;
     }
-    __syncwarp();   // scheduling fence: keeps the loads of later channels from being hoisted above this batch (register budget)
+    __syncwarp();
   }
 }
 
@@ -572,24 +617,43 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
             const float* const Ynew = w.Y[cur ^ 1];
             const float* const Fcur = w.F[cur];
             float part = 0.f;
+            // software pipeline over pairs of channels (same scheme as stage_in)
+            float ld[2][2][6];
+            auto load = [&](int b, int c) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const size_t o = p0 + (size_t)c * HW;
-              const float y0 = ptx::ldg_ordered(Ycur + o), y1 = ptx::ldg_ordered(Ynew + o);
-              const float kk[7] = {ptx::ldg_ordered(Fcur + o), 0.f, ptx::ldg_ordered(w.K[1] + o), ptx::ldg_ordered(w.K[2] + o),
-                                   ptx::ldg_ordered(w.K[3] + o), ptx::ldg_ordered(w.K[4] + o), x[c]};
-              float e = 0.f, md = 0.f;
-#pragma unroll
-              for (int j = 0; j < 7; ++j) {
-                if (j == 1) continue;
-                e = A::add(e, A::mul(ce[j], kk[j]));
-                md = A::add(md, A::mul(cm[j], kk[j]));
+              for (int i = 0; i < 2; ++i) {
+                const size_t o = p0 + (size_t)(c + i) * HW;
+                ld[b][i][0] = ptx::ldg_ordered(Ycur + o); ld[b][i][1] = ptx::ldg_ordered(Ynew + o);
+                ld[b][i][2] = ptx::ldg_ordered(Fcur + o); ld[b][i][3] = ptx::ldg_ordered(w.K[1] + o);
+                ld[b][i][4] = ptx::ldg_ordered(w.K[2] + o); ld[b][i][5] = ptx::ldg_ordered(w.K[3] + o);
               }
-              bad |= !isfinite(y0);
-              const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
-              const float qv = A::div(e, tol);
-              part += A::mul(qv, qv);
-              w.YMID[o] = A::add(y0, md);
+            };
+            load(0, 0);
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const int b = (c >> 1) & 1;
+              const float k6a = ptx::ldg_ordered(w.K[4] + p0 + (size_t)c * HW), k6b = ptx::ldg_ordered(w.K[4] + p0 + (size_t)(c + 1) * HW);
+              if (c + 2 < 32) load(b ^ 1, c + 2);
+              __syncwarp(__activemask());   // padding lanes are not here
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const size_t o = p0 + (size_t)(c + i) * HW;
+                const float y0 = ld[b][i][0], y1 = ld[b][i][1];
+                const float kk[7] = {ld[b][i][2], 0.f, ld[b][i][3], ld[b][i][4], ld[b][i][5], i == 0 ? k6a : k6b, x[c + i]};
+                float e = 0.f, md = 0.f;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                  if (j == 1) continue;
+                  e = A::add(e, A::mul(ce[j], kk[j]));
+                  md = A::add(md, A::mul(cm[j], kk[j]));
+                }
+                bad |= !isfinite(y0);
+                const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
+                const float qv = A::div(e, tol);
+                part += A::mul(qv, qv);
+                w.YMID[o] = A::add(y0, md);
+              }
+              __syncwarp(__activemask());   // padding lanes are not here
             }
             acc0 += (double)part;
           }
@@ -637,7 +701,8 @@ static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
   constexpr bool two = step_smem_bytes(T::A_PART, 2, T::NWARP, T::G) <= 227 * 1024 && 2 * T::MT * 128 <= 512;
   if constexpr (two) {
     const int NST = (a.g.N + T::G - 1) / T::G;
-    if (NST > kMaxGrid) return launch_step_shape<H_, W_, 2>(a, st);
+    static const char* force = getenv("NODE_B200_SLOTS");          // "1": always one slot (tuning aid)
+    if (NST > kMaxGrid && !(force != nullptr && force[0] == '1')) return launch_step_shape<H_, W_, 2>(a, st);
   }
   return launch_step_shape<H_, W_, 1>(a, st);
 }
@@ -647,3 +712,13 @@ static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
 // One translation unit per feature-map shape (they compile in parallel): step_shape_HxW.cu
 #define NODE_STEP_SHAPE_TU(H, W) \
   namespace node { int launch_step_##H##x##W(const FusedArgs& a, cudaStream_t st) { return launch_step_slots<H, W>(a, st); } }
+#if defined(NODE_STEP_DEBUG) && defined(NODE_STEP_DEBUG_EXPORT)
+extern "C" int node_b200_step_debug_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, node::g_step_dbg, sizeof(long long) * (n < 2048 ? n : 2048));
+}
+extern "C" int node_b200_step_debug_read2(long long* host, int n, int clear) {
+  int rc = (int)cudaMemcpyFromSymbol(host, node::g_step_dbg2, sizeof(long long) * (n < 1024 ? n : 1024));
+  if (clear) { static long long z[1024]; rc |= (int)cudaMemcpyToSymbol(node::g_step_dbg2, z, sizeof(z)); }
+  return rc;
+}
+#endif
