@@ -173,6 +173,36 @@ int node_b200_fused_phase(void* workspace, int phase, const float* y0, const dou
 double* node_b200_fused_sums(void* workspace);       /* device pointer, 2*NODE_MAX_SEG doubles */
 node_ctl_t* node_b200_fused_ctl(void* workspace);    /* device pointer to the controller block */
 
+/* ---- adjoint: native vector-Jacobian product of the recognised ODEfunc (adjoint.py:32-55) ---- */
+
+/* Bytes of scratch the VJP needs for a [N,C,H,W] shard (convolution inputs and output gradients
+ * for the weight-gradient GEMM, per-CTA partials). Host function; < 0 when the shape is not served. */
+int64_t node_b200_vjp_workspace_bytes(int N, int C, int H, int W);
+
+/* One evaluation of the adjoint's augmented dynamics (adjoint.py:32-55) for the recognised ODEfunc,
+ * replacing `func(t, y)` + `torch.autograd.grad(f, (t, y) + params, -adj_y)`:
+ *   f_out      = s * ODEfunc(s*t, y)                      [N,C,H,W]
+ *   vjp_y      = s * d<f, -adj_y>/dy                      [N,C,H,W]
+ *   vjp_t      = s * d<f, -adj_y>/dt                      1 float
+ *   vjp_params = s * d<f, -adj_y>/dparams                 75,392 floats in func.parameters() order
+ *                (norm1.w, norm1.b, conv1.W[C,C+1,3,3], conv1.b, norm2.*, conv2.*, norm3.*; misc.py:5-7)
+ * s = tsign (+1, or -1 for the reversed-time wrapper of misc.py:184-187); t_dev is a DEVICE scalar (the
+ * solver's stage time lives in the controller block). `workspace` is the fused workspace whose parameters
+ * were prepared with node_b200_fused_prepare. Enqueues three kernels: fused VJP (tcgen05 forward + data
+ * gradients), weight-gradient GEMM (tcgen05), deterministic fold. */
+int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const float* y, const float* adj_y,
+                          const float* t_dev, float tsign, float* f_out, float* vjp_y, float* vjp_t,
+                          float* vjp_params, int N, int C, int H, int W, void* stream);
+
+/* The weight-gradient GEMM alone: per-CTA partials of dW[co, ci, tap] = sum GC[n,co,h,w] * IN[n,ci,h+dy,w+dx]
+ * for both convolutions (r = convolution inputs, gc = gradients at the convolution outputs, [N,C,H,W]). */
+int node_b200_wgrad(void* vjp_workspace, const float* r1, const float* gc1, const float* r2, const float* gc2,
+                    int N, int C, int H, int W, void* stream);
+
+/* Test aid: device pointers inside the VJP workspace (0..3 = R1, R2, GC1, GC2; 4 = weight-gradient partials
+ * [splits][2][9][64][80]). */
+void* node_b200_vjp_buffer(void* vjp_workspace, int which, int N, int C, int H, int W);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,10 +95,40 @@ static bool make_geo(int N, int C, int H, int W, Geo* g) {
   return true;
 }
 
+// ---- adjoint kernels (K7): launch arguments shared by vjp_engine.cuh, wgrad_engine.cuh and odefunc_vjp.cu
+constexpr int kWgCols = 80;                      // weight-gradient accumulator columns per tap: 64 ci + ones + 15 unused
+constexpr int kWgSplits = 37;                    // 37 splits x 2 tap groups x 2 convolutions = 148 CTAs
+
+struct VjpArgs {
+  FusedWs w; Geo g;
+  const float* y; const float* adj;
+  float* f_out; float* vy_out;
+  float* R[2]; float* GC[2];     // [N,64,H,W] fp32, operands of the weight-gradient GEMM
+  float* chan_part;              // [grid][6][64]: dgamma1, dbeta1, dgamma2, dbeta2, dgamma3, dbeta3
+  double* t_part;                // [grid]: sum GC*Tmap over both convolutions
+  const float* t_dev;            // device scalar: the time the solver evaluates at
+  float tsign, eps;
+};
+
+struct WgradArgs {
+  Geo g;
+  const float* R[2]; const float* GC[2];         // [N,64,H,W] fp32 (written by k_vjp)
+  float* part;                                   // [splits][2 conv][9 tap][64 co][kWgCols]
+  int nsplit;
+};
+
+// images per super-tile of the position-strip tiling (Tile<H,W>::G in step_engine.cuh)
+__host__ __device__ constexpr int strip_images(int H, int W) {
+  const int Wp = W + 1, IS = (H + 1) * Wp, SPAN = (H - 1) * Wp + W;
+  const int MT = SPAN <= 256 ? 2 : (SPAN + 127) / 128;
+  return (MT * 128 - SPAN) / IS + 1;
+}
+
 // f16 engine (odefunc_step.cu)
 bool step_engine_supports(int H, int W);
 int launch_step_engine(const FusedArgs& a, cudaStream_t st);
 int launch_prepare16(const FusedWs& w, int H, int W, const float* c1w, const float* c2w, const float* g1w, const float* g1b,
                      const float* g2w, const float* g2b, cudaStream_t st);
+int launch_prepare_dgrad(const FusedWs& w, const float* c1w, const float* c2w, cudaStream_t st);   // odefunc_vjp.cu
 
 }  // namespace node

@@ -714,7 +714,8 @@ extern "C" int node_b200_fused_prepare(void* workspace, int C, int H, int W, con
   (void)eps;
   k_prepare<<<148, 256, 0, (cudaStream_t)stream>>>(w, H, W, c1w, c1b, c2w, c2b, g1w, g1b, g2w, g2b, g3w, g3b);
   NODE_CUDA_OK(cudaGetLastError());
-  return launch_prepare16(w, H, W, c1w, c2w, g1w, g1b, g2w, g2b, (cudaStream_t)stream);
+  NODE_CUDA_OK((cudaError_t)launch_prepare16(w, H, W, c1w, c2w, g1w, g1b, g2w, g2b, (cudaStream_t)stream));
+  return launch_prepare_dgrad(w, c1w, c2w, (cudaStream_t)stream);     // adjoint: flipped / transposed bf16 tiles
 }
 
 extern "C" int node_b200_odefunc_forward(void* workspace, const float* y, float t, float tsign, float* k, int N, int C,

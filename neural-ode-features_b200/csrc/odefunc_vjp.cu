@@ -1,0 +1,177 @@
+// K7 - native vector-Jacobian product of the ODE-Net dynamics for the adjoint's augmented system
+// (reference adjoint.py:32-55): parameter preparation of the data-gradient weight tiles, shape dispatch of the
+// fused VJP kernel (vjp_engine.cuh) and the weight-gradient GEMM (wgrad_engine.cuh), the deterministic fold of
+// their per-CTA partials into the flat parameter gradient, and the C entry points.
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include "fused_common.cuh"
+
+namespace node {
+
+constexpr int kNParam = 2 * (kC * (kC + 1) * 9 + kC) + 6 * kC;   // 75,392 (misc.py:5-7 order)
+
+struct VjpWs {
+  float* R[2]; float* GC[2];
+  float* chan_part; double* t_part; float* wpart;
+};
+
+static int64_t vjp_ws_layout(void* base, int N, int C, int H, int W, VjpWs* out) {
+  const int64_t E = (int64_t)N * C * H * W;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t r = o; o = align_up(o + bytes, 1024); return r; };
+  int64_t o_t[4];
+  for (int i = 0; i < 4; ++i) o_t[i] = take(E * 4);
+  const int64_t o_chan = take((int64_t)kMaxGrid * 384 * 4);
+  const int64_t o_tp = take((int64_t)kMaxGrid * 8);
+  const int64_t o_wp = take((int64_t)kWgSplits * 2 * 9 * 64 * kWgCols * 4);
+  if (out != nullptr) {
+    char* b = (char*)base;
+    out->R[0] = (float*)(b + o_t[0]); out->R[1] = (float*)(b + o_t[1]);
+    out->GC[0] = (float*)(b + o_t[2]); out->GC[1] = (float*)(b + o_t[3]);
+    out->chan_part = (float*)(b + o_chan); out->t_part = (double*)(b + o_tp); out->wpart = (float*)(b + o_wp);
+  }
+  return o;
+}
+
+// Data-gradient weight tiles (sets 2, 3 of w16): dL/dr[q, ci] = sum_tap' sum_co GC[q + off(tap'), co] * W[co, ci+1, 8 - tap'],
+// i.e. the forward implicit GEMM with "cout" = ci, "cin" = co and flipped taps. bf16 hi (rows 0..63) / lo (rows 64..127),
+// 64 K-values per 128-byte row, SWIZZLE_128B image - same geometry as the forward tiles.
+__global__ void k_prepare_dgrad_tiles(FusedWs w, const float* c1w, const float* c2w) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const float* cw[2] = {c1w, c2w};
+  for (int i = tid; i < 2 * 9 * 128 * 64; i += nth) {
+    int r = i;
+    const int co = r % 64; r /= 64;          // K index
+    const int row = r % 128; r /= 128;
+    const int tap = r % 9; r /= 9;
+    const int cv = r;
+    const int ci = row & 63;
+    const float v = cw[cv][((int64_t)co * (kC + 1) + ci + 1) * 9 + (8 - tap)];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 val = row < 64 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int chunk = (co >> 3) ^ (row & 7);
+    const int64_t dst = ((int64_t)((2 + cv) * 9 + tap) * 128 + row) * 64 + chunk * 8 + (co & 7);
+    w.w16[dst] = *reinterpret_cast<const uint16_t*>(&val);
+  }
+}
+
+int launch_prepare_dgrad(const FusedWs& w, const float* c1w, const float* c2w, cudaStream_t st) {
+  k_prepare_dgrad_tiles<<<148, 256, 0, st>>>(w, c1w, c2w);
+  return (int)cudaGetLastError();
+}
+
+// Fold the per-CTA partials in a fixed order into (vjp_t, flat vjp_params) in func.parameters() order:
+// norm1.w, norm1.b, conv1.W [64,65,3,3], conv1.b, norm2.w, norm2.b, conv2.W, conv2.b, norm3.w, norm3.b.
+__global__ void k_vjp_finalize(const float* __restrict__ wpart, int nsplit, const float* __restrict__ chan_part, int ngrid,
+                               const double* __restrict__ t_part, const float* __restrict__ t_dev, float tsign,
+                               float* __restrict__ out_t, float* __restrict__ out_p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float t_eff = tsign * t_dev[0];
+  constexpr int kWsz = kC * (kC + 1) * 9, kBlock = 2 * kC + kWsz + kC;   // one (norm, conv) block: 37,632
+  if (i == kNParam) {
+    double s = 0.0;
+    for (int b = 0; b < ngrid; ++b) s += t_part[b];
+    out_t[0] = (float)s * tsign;
+    return;
+  }
+  if (i > kNParam) return;
+  const int blk = i / kBlock, r = i % kBlock;       // blk 0, 1: (norm, conv) pairs; blk 2: norm3 only
+  float v = 0.f;
+  if (r < 2 * kC) {                                  // GroupNorm affine gradients
+    const int q = blk * 2 + r / kC, c = r % kC;
+    for (int b = 0; b < ngrid; ++b) v += chan_part[(size_t)b * 384 + q * 64 + c];
+  } else if (r < 2 * kC + kWsz) {                    // conv weight [co][ci1][tap]
+    const int j = r - 2 * kC;
+    const int co = j / ((kC + 1) * 9), rem = j % ((kC + 1) * 9), ci1 = rem / 9, tap = rem % 9;
+    const int col = ci1 == 0 ? 64 : ci1 - 1;
+    for (int s = 0; s < nsplit; ++s) v += wpart[(((size_t)(s * 2 + blk) * 9 + tap) * 64 + co) * kWgCols + col];
+    if (ci1 == 0) v *= t_eff;                        // the time plane is t*ones (model.py:321)
+  } else {                                           // conv bias: the ones column at the centre tap
+    const int co = r - 2 * kC - kWsz;
+    for (int s = 0; s < nsplit; ++s) v += wpart[(((size_t)(s * 2 + blk) * 9 + 4) * 64 + co) * kWgCols + 64];
+  }
+  out_p[i] = v * tsign;
+}
+
+// per-shape translation units (vjp_shape_HxW.cu)
+int launch_vjp_8x8(const VjpArgs& a, cudaStream_t st);
+int launch_vjp_7x7(const VjpArgs& a, cudaStream_t st);
+int launch_vjp_6x6(const VjpArgs& a, cudaStream_t st);
+int launch_vjp_14x14(const VjpArgs& a, cudaStream_t st);
+int launch_vjp_16x16(const VjpArgs& a, cudaStream_t st);
+int launch_wgrad_8x8(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad_7x7(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad_6x6(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad_14x14(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad_16x16(const WgradArgs& a, cudaStream_t st);
+
+}  // namespace node
+
+using namespace node;
+
+extern "C" int64_t node_b200_vjp_workspace_bytes(int N, int C, int H, int W) {
+  Geo g;
+  if (!make_geo(N, C, H, W, &g) || !step_engine_supports(H, W)) return -1;
+  return vjp_ws_layout(nullptr, N, C, H, W, nullptr);
+}
+
+// Device pointers of the VJP workspace's buffers (0..3: R1, R2, GC1, GC2; 4: weight-gradient partials) - test aid.
+extern "C" void* node_b200_vjp_buffer(void* vjp_workspace, int which, int N, int C, int H, int W) {
+  VjpWs v;
+  vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
+  switch (which) {
+    case 0: return v.R[0];
+    case 1: return v.R[1];
+    case 2: return v.GC[0];
+    case 3: return v.GC[1];
+    case 4: return v.wpart;
+    default: return nullptr;
+  }
+}
+
+extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float* gc1, const float* r2, const float* gc2,
+                               int N, int C, int H, int W, void* stream) {
+  WgradArgs a{};
+  if (!make_geo(N, C, H, W, &a.g) || !step_engine_supports(H, W)) return (int)cudaErrorInvalidValue;
+  VjpWs v;
+  vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
+  a.R[0] = r1; a.R[1] = r2; a.GC[0] = gc1; a.GC[1] = gc2; a.part = v.wpart;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == 8 && W == 8) return launch_wgrad_8x8(a, st);
+  if (H == 7 && W == 7) return launch_wgrad_7x7(a, st);
+  if (H == 6 && W == 6) return launch_wgrad_6x6(a, st);
+  if (H == 14 && W == 14) return launch_wgrad_14x14(a, st);
+  if (H == 16 && W == 16) return launch_wgrad_16x16(a, st);
+  return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const float* y, const float* adj_y,
+                                     const float* t_dev, float tsign, float* f_out, float* vjp_y, float* vjp_t,
+                                     float* vjp_params, int N, int C, int H, int W, void* stream) {
+  VjpArgs a{};
+  if (!make_geo(N, C, H, W, &a.g) || !step_engine_supports(H, W)) return (int)cudaErrorInvalidValue;
+  ws_layout(workspace, N, C, H, W, &a.w);
+  VjpWs v;
+  vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
+  a.y = y; a.adj = adj_y; a.f_out = f_out; a.vy_out = vjp_y;
+  a.R[0] = v.R[0]; a.R[1] = v.R[1]; a.GC[0] = v.GC[0]; a.GC[1] = v.GC[1];
+  a.chan_part = v.chan_part; a.t_part = v.t_part; a.t_dev = t_dev; a.tsign = tsign < 0 ? -1.f : 1.f; a.eps = 1e-5f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (H == 8 && W == 8) rc = launch_vjp_8x8(a, st);
+  else if (H == 7 && W == 7) rc = launch_vjp_7x7(a, st);
+  else if (H == 6 && W == 6) rc = launch_vjp_6x6(a, st);
+  else if (H == 14 && W == 14) rc = launch_vjp_14x14(a, st);
+  else rc = launch_vjp_16x16(a, st);
+  if (rc != 0) return rc;
+  rc = node_b200_wgrad(vjp_workspace, v.R[0], v.GC[0], v.R[1], v.GC[1], N, C, H, W, stream);
+  if (rc != 0) return rc;
+  // grid sizes the two kernels used (same rules as their launchers)
+  const int per = strip_images(H, W);
+  const int NST = (N + per - 1) / per;
+  const int nst_vjp = NST < kMaxGrid ? NST : kMaxGrid;
+  const int nsplit = NST < kWgSplits ? NST : kWgSplits;
+  k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
+                                                              vjp_t, vjp_params);
+  return (int)cudaGetLastError();
+}

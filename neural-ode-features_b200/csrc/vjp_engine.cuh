@@ -1,0 +1,528 @@
+// K7a - fused vector-Jacobian product of the ODE-Net dynamics (reference adjoint.py:32-55 applied to
+// model.py:339-348): one launch evaluates, for every image,
+//     f      = s * ODEfunc(s*t, y)
+//     vjp_y  = s * d<f, -a>/dy        (a = adj_y; the cotangent -a is adjoint.py:43)
+// and leaves everything the parameter / time gradients need:
+//     R1 = relu(GN1(y)), R2 = relu(GN2(c1))      the convolution inputs
+//     GC1, GC2 = dL/dc1, dL/dc2                   the gradients at the convolution outputs
+//     per-CTA partial sums of the six GroupNorm affine gradients and of vjp_t = sum GC*Tmap.
+// The weight gradient itself (a GEMM whose reduction dimension is the batch) is K7b, wgrad.cuh.
+//
+// Mapping: the step engine's (step_engine.cuh) thread-per-position tiling with ONE worker slot. The two
+// forward convolutions keep their fp32 accumulators (c1, c2) in TENSOR MEMORY until the backward pass has
+// consumed them, so nothing but y and a is read from HBM: 2*MT*64 columns hold c1 and c2, the two data-gradient
+// convolutions (the same implicit GEMM with flipped, transposed weight tiles) reuse c2's columns.
+// Forward operands are the fp16 hi/lo split of the step engine; gradient operands are split into bf16 hi/lo
+// (gradients have no a-priori bound, bf16 keeps fp32's exponent range): g*w ~ g_hi*w_hi + g_lo*w_hi + g_hi*w_lo,
+// 2^-16 relative, fp32 accumulation.
+#pragma once
+#include <cuda_bf16.h>
+#include "step_engine.cuh"
+
+namespace node {
+
+constexpr uint32_t kIdBF16N64 = kIdF16N64 | (1u << 7) | (1u << 10);   // kind::f16 with bf16 A and B
+
+// Sum 32 per-lane values across the warp; lane L returns the total of u[L] (31 shuffles).
+__device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
+  float a[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? u[i] : u[i + 16], keep = up ? u[i + 16] : u[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float b[8], c[4], d[2];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? b[i] : b[i + 4], keep = up ? b[i + 4] : b[i];
+      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? c[i] : c[i + 2], keep = up ? c[i + 2] : c[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+struct VjpSmem {
+  StepSmem s;            // wring, abase, part, stat (set 0), gnp, bias, tmapc, scratch, barriers of the step engine
+  float2* stat3;         // [3][G][32] (mean, rstd) of GN1, GN2, GN3
+  float* gsum;           // [G][32]: per image, S1 of 16 groups then S2 of 16 groups (current half)
+  float* part64;         // [NWARP][64]
+  float* chacc;          // [NWARP][12][32] per-lane channel accumulators: [(norm*2 + {gamma,beta})*2 + half]
+};
+
+// 32 values per thread summed over every pixel of the thread's image -> dst[img][32].
+template <class T>
+__device__ __forceinline__ void reduce32_img(const VjpSmem& sm, const Who& me, const float (&u)[32]) {
+  float* pw = sm.part64 + me.warp * 64;
+  if (!me.straddle) {
+    const float r = xreduce32(u, me.lane);
+    pw[me.lane] = r;
+  } else {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = me.isB ? 0.f : u[j];
+    const float ra = xreduce32(v, me.lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = me.isB ? u[j] : 0.f;
+    const float rb = xreduce32(v, me.lane);
+    pw[me.lane] = ra; pw[32 + me.lane] = rb;
+  }
+  slot_sync(0, T::P);
+  if (me.wt < T::G * 32) {
+    const int img = me.wt >> 5, q = me.wt & 31;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < T::NWARP; ++w) {
+      const int ia = (w * 32) / T::IS, ib = (w * 32 + 31) / T::IS;
+      if (ia == img) tot += sm.part64[w * 64 + q];
+      if (ib != ia && ib == img) tot += sm.part64[w * 64 + 32 + q];
+    }
+    sm.gsum[img * 32 + q] = tot;
+  }
+  slot_sync(0, T::P);
+}
+
+// Per-channel sums over the warp's positions, accumulated in the lane's private shared-memory cell.
+__device__ __forceinline__ void chan_accumulate(const VjpSmem& sm, const Who& me, int q, const float (&u)[32]) {
+  const float r = xreduce32(u, me.lane);
+  sm.chacc[(me.warp * 12 + q) * 32 + me.lane] += r;
+}
+
+// relu(GN(x)) for 32 channels: fp16 hi/lo image rows for the tensor core (scaled) + the plain value to HBM.
+template <class T>
+__device__ __forceinline__ void act_to_A(const VjpSmem& sm, const Who& me, int hb, const float (&x)[32], int n, float scale,
+                                         bool valid, float* __restrict__ r_out, size_t p0) {
+  const float2* st = sm.stat3 + (n * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+  const float4* gp = sm.s.gnp + n * 32 + 16 * hb;
+  const uint32_t row = sm.s.abase + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = kc * 4 + j;
+      const float2 s = st[g];
+      const float4 p = gp[g];
+      const float a0 = s.y * p.x, a1 = s.y * p.y;
+      const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+      const float v0 = fmaxf(fmaf(x[2 * g], a0, b0), 0.f), v1 = fmaxf(fmaf(x[2 * g + 1], a1, b1), 0.f);
+      if (valid) { r_out[p0 + (size_t)(2 * g) * T::HW] = v0; r_out[p0 + (size_t)(2 * g + 1) * T::HW] = v1; }
+      const float r0 = v0 * scale, r1 = v1 * scale;
+      const __half2 h = __floats2half2_rn(r0, r1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    if (valid) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + kc * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + kc * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+  }
+}
+
+// 32 gradient values -> bf16 hi/lo rows of the A image.
+template <class T>
+__device__ __forceinline__ void grad_to_A(const VjpSmem& sm, const Who& me, int hb, const float (&g)[32], bool valid) {
+  const uint32_t row = sm.s.abase + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = g[kc * 8 + 2 * j], v1 = g[kc * 8 + 2 * j + 1];
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    if (valid) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + kc * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + kc * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+  }
+}
+
+// Leader thread: one conv job = 9 taps of MT x 4 k-steps x 3 MMAs (hi*hi, lo*hi, hi*lo) into `dcol`.
+struct VjpRing { uint32_t issued, tapx, total; };
+__device__ __forceinline__ int vjp_set_of(uint32_t job) { const uint32_t k = job & 3u; return k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 3 : 2)); }
+
+template <class T>
+__device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, VjpRing& rg, const uint16_t* __restrict__ w16, uint32_t tmem,
+                                              uint32_t dcol, uint32_t idesc, bool& timeout) {
+  ptx::tc_fence_after();
+  const uint32_t abase = sm.s.abase + T::HALO * 16;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    while (rg.issued < rg.total && rg.issued <= rg.tapx + (kNW - kWGap)) {
+      const uint32_t slot = rg.issued % kNW;
+      if (rg.issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.s.bar_wfree + 8 * slot, ((rg.issued / kNW) - 1) & 1)) timeout = true;
+      const uint32_t set = (uint32_t)vjp_set_of(rg.issued / 9), tp = rg.issued % 9;
+      ptx::mbar_expect_tx(sm.s.bar_wfull + 8 * slot, kW16TileBytes);
+      ptx::bulk_g2s(sm.s.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(set * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                    sm.s.bar_wfull + 8 * slot);
+      ++rg.issued;
+    }
+    const uint32_t slot = rg.tapx % kNW;
+    if (!timeout && !ptx::mbar_wait(sm.s.bar_wfull + 8 * slot, (rg.tapx / kNW) & 1)) timeout = true;
+    ptx::tc_fence_after();
+    const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
+    const uint64_t b_hi0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes);
+    const uint64_t b_lo0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes + 64 * 128);
+#pragma unroll
+    for (int mt = 0; mt < T::MT; ++mt) {
+      const uint32_t d = tmem + dcol + (uint32_t)(mt * 64);
+      const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
+        const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+        const uint64_t kadv = (uint64_t)((ks * 32) >> 4);
+        ptx::mma_f16_ss(d, a_hi, b_hi0 + kadv, idesc, (tap == 0 && ks == 0) ? 0u : 1u);
+        ptx::mma_f16_ss(d, a_lo, b_hi0 + kadv, idesc, 1u);
+        ptx::mma_f16_ss(d, a_hi, b_lo0 + kadv, idesc, 1u);
+      }
+    }
+    ptx::tc_commit(sm.s.bar_wfree + 8 * slot);
+    ++rg.tapx;
+  }
+  ptx::tc_commit(sm.s.bar_acc);
+}
+
+template <class T>
+__device__ __forceinline__ void vjp_conv_run(const VjpSmem& sm, const Who& me, VjpRing& rg, const uint16_t* __restrict__ w16,
+                                             uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t& njob, bool& timeout) {
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  slot_sync(0, T::P);
+  if (me.warp == 0) {
+    if (me.lane == 0) vjp_issue_job<T>(sm, rg, w16, tmem, dcol, idesc, timeout);
+    __syncwarp();
+  }
+  if (!timeout && !ptx::mbar_wait_relaxed(sm.s.bar_acc, njob & 1)) timeout = true;
+  ++njob;
+  ptx::tc_fence_after();
+}
+
+// 32 accumulator columns of this thread's row -> x = acc*mul (+ bias + t*Tmap when cv >= 0).
+template <class T>
+__device__ __forceinline__ void vjp_tmem_read(const VjpSmem& sm, const Who& me, int hb, float (&x)[32], uint32_t tmem, uint32_t col,
+                                              int cv, float mul, float t, bool valid) {
+  const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + col + (uint32_t)((me.wt >> 7) * 64 + 32 * hb);
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t v[16];
+    ptx::tmem_ld16(taddr + c0, v);
+    ptx::tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float acc = __uint_as_float(v[j]) * mul;
+      if (cv >= 0) {
+        const float extra = fmaf(t, sm.s.tmapc[(cv * 9 + me.cls) * 64 + 32 * hb + c0 + j], sm.s.bias[cv * 64 + 32 * hb + c0 + j]);
+        x[c0 + j] = valid ? acc + extra : 0.f;
+      } else {
+        x[c0 + j] = valid ? acc : 0.f;
+      }
+    }
+  }
+}
+
+// Backward of one GroupNorm for 32 channels of this thread's position (oracle/odefunc_port.py:_gn_bwd):
+// in: x = the norm's input, g = gradient at its output (already masked by the ReLU that follows, if any);
+// out: g <- gradient at the norm's input. Accumulates dgamma / dbeta of norm n.
+template <class T>
+__device__ __forceinline__ void gn_backward(const VjpSmem& sm, const Who& me, int hb, int n, const float (&x)[32], float (&g)[32]) {
+  constexpr float inv_m = 1.0f / (float)(kCpg * T::HW);
+  const float2* st = sm.stat3 + (n * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+  const float4* gp = sm.s.gnp + n * 32 + 16 * hb;
+  float u[32];
+  // dgamma_c = sum g*xhat, dbeta_c = sum g (over every image and pixel)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 s = st[j];
+    u[2 * j] = g[2 * j] * ((x[2 * j] - s.x) * s.y);
+    u[2 * j + 1] = g[2 * j + 1] * ((x[2 * j + 1] - s.x) * s.y);
+  }
+  chan_accumulate(sm, me, (n * 2 + 0) * 2 + hb, u);
+  chan_accumulate(sm, me, (n * 2 + 1) * 2 + hb, g);
+  // S1 = sum_cell g*gamma, S2 = sum_cell g*gamma*xhat
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 s = st[j];
+    const float4 p = gp[j];
+    const float d0 = g[2 * j] * p.x, d1 = g[2 * j + 1] * p.y;
+    u[j] = d0 + d1;
+    u[16 + j] = d0 * ((x[2 * j] - s.x) * s.y) + d1 * ((x[2 * j + 1] - s.x) * s.y);
+  }
+  reduce32_img<T>(sm, me, u);
+  const float* gs = sm.gsum + min(me.img_l, T::G - 1) * 32;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 s = st[j];
+    const float4 p = gp[j];
+    const float m1 = gs[j] * inv_m, m2 = gs[16 + j] * inv_m;
+    const float xh0 = (x[2 * j] - s.x) * s.y, xh1 = (x[2 * j + 1] - s.x) * s.y;
+    g[2 * j] = s.y * (g[2 * j] * p.x - m1 - xh0 * m2);
+    g[2 * j + 1] = s.y * (g[2 * j + 1] * p.y - m1 - xh1 * m2);
+  }
+}
+
+template <int H_, int W_>
+__global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
+  using T = Tile<H_, W_>;
+  constexpr int HW = T::HW, P = T::P;
+  extern __shared__ uint8_t smem_raw[];
+  const FusedWs& w = a.w;
+  const int tid = threadIdx.x;
+
+  VjpSmem sm;
+  {
+    const uint32_t s0 = ptx::smem_u32(smem_raw);
+    const uint32_t al = (s0 + 1023u) & ~1023u;
+    uint8_t* base = smem_raw + (al - s0);
+    size_t o = 0;
+    sm.s.wring = al; o += (size_t)kNW * kW16TileBytes;
+    sm.s.abase = al + (uint32_t)o; o += (size_t)2 * T::A_PART;
+    sm.s.part = reinterpret_cast<float*>(base + o); o += (size_t)T::NWARP * 32 * 4;
+    sm.part64 = reinterpret_cast<float*>(base + o); o += (size_t)T::NWARP * 64 * 4;
+    sm.stat3 = reinterpret_cast<float2*>(base + o); o += (size_t)3 * T::G * 32 * 8;
+    sm.gsum = reinterpret_cast<float*>(base + o); o += (size_t)T::G * 32 * 4;
+    sm.chacc = reinterpret_cast<float*>(base + o); o += (size_t)T::NWARP * 12 * 32 * 4;
+    sm.s.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
+    sm.s.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
+    sm.s.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * 64 * 4;
+    sm.s.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
+    sm.s.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
+    sm.s.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
+    sm.s.bar_acc = al + (uint32_t)o; o += 8;
+    sm.s.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
+    sm.s.stat = sm.stat3;
+    uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);
+    for (int i = tid; i < 2 * T::A_PART / 16; i += blockDim.x) az[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < T::NWARP * 12 * 32; i += blockDim.x) sm.chacc[i] = 0.f;
+  }
+  for (int i = tid; i < 3 * 32; i += blockDim.x) {
+    const int n = i / 32, g = i % 32;
+    sm.s.gnp[i] = make_float4(w.gn[(2 * n) * kC + 2 * g], w.gn[(2 * n) * kC + 2 * g + 1], w.gn[(2 * n + 1) * kC + 2 * g],
+                              w.gn[(2 * n + 1) * kC + 2 * g + 1]);
+  }
+  for (int i = tid; i < 2 * 64; i += blockDim.x) sm.s.bias[i] = w.bias[i];
+  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.s.tmapc[i] = w.tmapc[i];
+  if (tid == 0) {
+    for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.s.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.s.bar_wfree + 8 * i, 1); }
+    ptx::mbar_init(sm.s.bar_acc, 1);
+    ptx::fence_mbar_init();
+  }
+  if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.s.tmem_slot), kTmemCols);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *sm.s.tmem_slot;
+  constexpr uint32_t kColC1 = 0, kColC2 = T::MT * 64;
+
+  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int nst = (int)blockIdx.x < NST ? (NST - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  VjpRing rg{0u, 0u, (uint32_t)nst * 4u * 9u};
+  bool timeout = false;
+  uint32_t njob = 0;
+  float tacc = 0.f;
+
+  Who me;
+  me.slot = 0; me.wt = tid; me.warp = tid >> 5; me.lane = tid & 31;
+  me.img_l = me.wt / T::IS;
+  {
+    const int r = me.wt % T::IS, hh = r / T::Wp, ww = r % T::Wp;
+    me.inimg = me.img_l < T::G && hh < T::H && ww < T::W;
+    me.pix = hh * T::W + ww;
+    me.cls = (hh == 0 ? 0 : (hh == T::H - 1 ? 2 : 1)) * 3 + (ww == 0 ? 0 : (ww == T::W - 1 ? 2 : 1));
+    if (!me.inimg) me.cls = 4;
+    const int ia = (me.warp * 32) / T::IS, ib = (me.warp * 32 + 31) / T::IS;
+    me.straddle = ia != ib;
+    me.isB = me.img_l != ia;
+  }
+  const float t = a.tsign * a.t_dev[0];      // reversed-time wrapper (misc.py:184-187)
+  StepSmem st1 = sm.s, st2 = sm.s, st3 = sm.s;
+  st1.stat = sm.stat3; st2.stat = sm.stat3 + T::G * 32; st3.stat = sm.stat3 + 2 * T::G * 32;
+
+#pragma unroll 1
+  for (int st = blockIdx.x; st < NST; st += gridDim.x) {
+    const int img = st * T::G + me.img_l;
+    const bool valid = me.inimg && img < a.g.N;
+    const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+    float x[32], g[32];
+
+    // ---- forward: y -> GN1 -> ReLU -> conv1 (model.py:341-343)
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float v = a.y[p0 + (size_t)c * HW]; x[c] = valid ? v : 0.f; }
+      gn_stats<T>(st1, me, hb, x, valid, a.eps);
+      act_to_A<T>(sm, me, hb, x, 0, w.scal[0], valid, a.R[0], p0);
+    }
+    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC1, kIdF16N64, njob, timeout);
+    // ---- c1 -> GN2 -> ReLU -> conv2 (model.py:344-346)
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      vjp_tmem_read<T>(sm, me, hb, x, tmem, kColC1, 0, w.scal[4], t, valid);
+      gn_stats<T>(st2, me, hb, x, valid, a.eps);
+      act_to_A<T>(sm, me, hb, x, 1, w.scal[1], valid, a.R[1], p0);
+    }
+    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);
+    // ---- c2 -> GN3 = f; backward of GN3 with cotangent -a (adjoint.py:43)
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      vjp_tmem_read<T>(sm, me, hb, x, tmem, kColC2, 1, w.scal[5], t, valid);
+      gn_stats<T>(st3, me, hb, x, valid, a.eps);
+      {
+        const float2* stt = st3.stat + min(me.img_l, T::G - 1) * 32 + 16 * hb;
+        const float4* gp = sm.s.gnp + 2 * 32 + 16 * hb;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 s = stt[j];
+          const float4 p = gp[j];
+          const float a0 = s.y * p.x, a1 = s.y * p.y;
+          const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+          if (valid) {
+            a.f_out[p0 + (size_t)(2 * j) * HW] = fmaf(x[2 * j], a0, b0) * a.tsign;
+            a.f_out[p0 + (size_t)(2 * j + 1) * HW] = fmaf(x[2 * j + 1], a1, b1) * a.tsign;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float v = a.adj[p0 + (size_t)c * HW]; g[c] = valid ? -v : 0.f; }
+      gn_backward<T>(sm, me, hb, 2, x, g);
+      const float* tm = sm.s.tmapc + (9 + me.cls) * 64 + 32 * hb;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (valid) { a.GC[1][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
+      }
+      grad_to_A<T>(sm, me, hb, g, valid);
+    }
+    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr2 over c2's columns
+    // ---- ReLU mask of GN2's output, backward of GN2
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, 1.f, 0.f, valid);
+      vjp_tmem_read<T>(sm, me, hb, x, tmem, kColC1, 0, w.scal[4], t, valid);
+      {
+        const float2* stt = st2.stat + min(me.img_l, T::G - 1) * 32 + 16 * hb;
+        const float4* gp = sm.s.gnp + 1 * 32 + 16 * hb;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 s = stt[j];
+          const float4 p = gp[j];
+          const float a0 = s.y * p.x, a1 = s.y * p.y;
+          const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+          if (!(fmaf(x[2 * j], a0, b0) > 0.f)) g[2 * j] = 0.f;
+          if (!(fmaf(x[2 * j + 1], a1, b1) > 0.f)) g[2 * j + 1] = 0.f;
+        }
+      }
+      gn_backward<T>(sm, me, hb, 1, x, g);
+      const float* tm = sm.s.tmapc + me.cls * 64 + 32 * hb;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (valid) { a.GC[0][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
+      }
+      grad_to_A<T>(sm, me, hb, g, valid);
+    }
+    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr1
+    // ---- ReLU mask of GN1's output, backward of GN1 -> vjp_y
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, 1.f, 0.f, valid);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { const float v = a.y[p0 + (size_t)c * HW]; x[c] = valid ? v : 0.f; }
+      {
+        const float2* stt = st1.stat + min(me.img_l, T::G - 1) * 32 + 16 * hb;
+        const float4* gp = sm.s.gnp + 16 * hb;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 s = stt[j];
+          const float4 p = gp[j];
+          const float a0 = s.y * p.x, a1 = s.y * p.y;
+          const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
+          if (!(fmaf(x[2 * j], a0, b0) > 0.f)) g[2 * j] = 0.f;
+          if (!(fmaf(x[2 * j + 1], a1, b1) > 0.f)) g[2 * j + 1] = 0.f;
+        }
+      }
+      gn_backward<T>(sm, me, hb, 0, x, g);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (valid) a.vy_out[p0 + (size_t)c * HW] = g[c] * a.tsign;
+      }
+    }
+  }
+
+  // ---- per-CTA partials: channel sums (fold the warps) and the time gradient
+  __syncthreads();
+  for (int i = tid; i < 12 * 32; i += blockDim.x) {
+    const int q = i >> 5, lane = i & 31;
+    float tot = 0.f;
+    for (int wp = 0; wp < T::NWARP; ++wp) tot += sm.chacc[(wp * 12 + q) * 32 + lane];
+    // q = (norm*2 + kind)*2 + half  ->  [norm*2 + kind][64]
+    a.chan_part[(size_t)blockIdx.x * 384 + (q >> 1) * 64 + (q & 1) * 32 + lane] = tot;
+  }
+  const double tsum = block_sum((double)tacc, sm.s.scratch);
+  if (tid == 0) a.t_part[blockIdx.x] = tsum;
+  if (timeout) atomicOr(&w.ctl->status, NODE_ST_WATCHDOG);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) ptx::tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int H_, int W_>
+constexpr size_t vjp_smem_bytes() {
+  using T = Tile<H_, W_>;
+  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)2 * T::A_PART + (size_t)T::NWARP * 32 * 4 + (size_t)T::NWARP * 64 * 4 +
+         (size_t)3 * T::G * 32 * 8 + (size_t)T::G * 32 * 4 + (size_t)T::NWARP * 12 * 32 * 4 + 3 * 32 * 16 + 2 * 64 * 4 +
+         2 * 9 * 64 * 4 + 32 * 8 + 16 * kNW + 8 + 64;
+}
+
+template <int H_, int W_>
+static int launch_vjp_shape(const VjpArgs& a, cudaStream_t st) {
+  using T = Tile<H_, W_>;
+  constexpr size_t smem = vjp_smem_bytes<H_, W_>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static_assert(2 * T::MT * 64 <= kTmemCols, "tensor memory budget");
+  static_assert(T::G == strip_images(H_, W_), "strip_images out of sync");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NODE_CUDA_OK(cudaFuncSetAttribute(k_vjp<H_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int grid = NST < kMaxGrid ? NST : kMaxGrid;
+  k_vjp<H_, W_><<<grid, T::P, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace node

@@ -30,7 +30,8 @@ EXPORTS = (
     'node_b200_rk_error_norm', 'node_b200_init_norms', 'node_b200_reduce_partials', 'node_b200_controller',
     'node_b200_interp_eval', 'node_b200_fused_workspace_bytes', 'node_b200_fused_prepare',
     'node_b200_odefunc_forward', 'node_b200_fused_solve', 'node_b200_fused_phase', 'node_b200_fused_sums',
-    'node_b200_fused_ctl',
+    'node_b200_fused_ctl', 'node_b200_vjp_workspace_bytes', 'node_b200_odefunc_vjp', 'node_b200_wgrad',
+    'node_b200_vjp_buffer',
 )
 
 _lib = None
@@ -59,6 +60,12 @@ def _declare(lib):
     lib.node_b200_fused_sums.restype = _vp
     lib.node_b200_fused_ctl.argtypes = [_vp]
     lib.node_b200_fused_ctl.restype = _vp
+    lib.node_b200_vjp_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.node_b200_vjp_workspace_bytes.restype = _i64
+    lib.node_b200_odefunc_vjp.argtypes = [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_wgrad.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_vjp_buffer.argtypes = [_vp, _i, _i, _i, _i, _i]
+    lib.node_b200_vjp_buffer.restype = _vp
 
 
 def lib():

@@ -204,6 +204,65 @@ def odefunc_forward(func, t, y, tsign=1.0, conv_mode=None):
     return k
 
 
+_vjp_ws_cache = {}
+N_PARAMS_64 = 2 * (64 * 65 * 9 + 64) + 6 * 64
+
+
+def _vjp_workspace(device, N, C, H, W):
+    key = (str(device), N, C, H, W)
+    buf = _vjp_ws_cache.get(key)
+    if buf is None:
+        nbytes = native.lib().node_b200_vjp_workspace_bytes(N, C, H, W)
+        if nbytes <= 0:
+            raise ValueError('shape [%d,%d,%d,%d] is not supported by the fused VJP kernels' % (N, C, H, W))
+        if len(_vjp_ws_cache) > 4:
+            _vjp_ws_cache.clear()
+        buf = _vjp_ws_cache[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+def odefunc_vjp(func, t, y, adj_y, tsign=1.0, out=None):
+    """One evaluation of the adjoint's augmented dynamics (adjoint.py:32-55) by the native kernels:
+    returns (f, vjp_y, vjp_t, vjp_params) with cotangent -adj_y, all multiplied by tsign and evaluated at
+    tsign*t. `t` is a python float or a 0-d float32 CUDA tensor; `out` optionally names the four destination tensors."""
+    params = recognise_odefunc(func)
+    if params is None or not _fusable_state(params, (y,)):
+        raise ValueError('func / y are not served by the fused ODEfunc kernels')
+    N, C, H, W = y.shape
+    ws = fused_workspace(y.device, N, C, H, W)
+    ws.prepare(params)
+    vws = _vjp_workspace(y.device, N, C, H, W)
+    if not torch.is_tensor(t):
+        t = torch.tensor(float(t), dtype=torch.float32, device=y.device)
+    assert t.dtype == torch.float32 and t.is_cuda
+    if out is None:
+        out = (torch.empty_like(y), torch.empty_like(y), torch.empty((), dtype=y.dtype, device=y.device),
+               torch.empty(N_PARAMS_64, dtype=y.dtype, device=y.device))
+    f, vy, vt, vp = out
+    for o in (y, adj_y, f, vy, vp):
+        assert o.is_contiguous()
+    err = native.lib().node_b200_odefunc_vjp(native.ptr(ws.buf), native.ptr(vws), native.ptr(y), native.ptr(adj_y),
+                                            native.ptr(t), float(tsign), native.ptr(f), native.ptr(vy), native.ptr(vt),
+                                            native.ptr(vp), N, C, H, W, native.stream_ptr())
+    native.check(err, 'odefunc_vjp')
+    return out
+
+
+class _FusedAugmented(object):
+    """The adjoint's augmented dynamics (adjoint.py:32-55) served by the native VJP kernels: the generic route
+    calls eval_into() with views of its own stage buffers, so nothing is copied and no autograd graph exists."""
+
+    def __init__(self, func):
+        self.func = func
+        self.target = _unwrap(func)
+
+    def eval_into(self, t_dev, src, dst, tsign):
+        y, adj_y = src[0], src[1]
+        odefunc_vjp(self.func, t_dev, y, adj_y, tsign=tsign, out=(dst[0], dst[1], dst[2], dst[3]))
+        if hasattr(self.target, 'nfe'):
+            self.target.nfe += 1                  # model.py:340 counts every evaluation
+
+
 def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     y = y0.detach().contiguous()
     N, C, H, W = y.shape
@@ -283,8 +342,9 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
 class _GenericSolve(object):
     NBUF = 11  # Y0 Y1 F0 F1 K2..K6 YMID YI
 
-    def __init__(self, func, y0, t_host, rtol, atol, opts):
+    def __init__(self, func, y0, t_host, rtol, atol, opts, tsign=1):
         self.func = func
+        self.tsign = tsign
         ref = y0[0]
         if ref.dtype not in (torch.float32, torch.float64):
             raise TypeError('node_b200 serves float32 and float64 states, got {}'.format(ref.dtype))
@@ -337,6 +397,9 @@ class _GenericSolve(object):
         return [row[o:o + n].view(s) for o, n, s in zip(self.offs, self.lens, self.shapes)]
 
     def _eval(self, t0d, src, dst):
+        if hasattr(self.func, 'eval_into'):
+            self.func.eval_into(t0d, self._views(src), self._views(dst), self.tsign)
+            return
         vals = self.func(t0d, tuple(self._views(src)))
         for b, v in zip(self._views(dst), vals):
             b.copy_(v)
@@ -447,12 +510,12 @@ def _solve(func, y0, t, rtol, atol, options):
         plain = not options and not _is_iterable(rtol) and not _is_iterable(atol)
         if params is not None and plain and _fusable_state(params, y0) and len(t_host) <= 1024:
             return (_solve_fused(func, params, y0[0], t_host, tsign, rtol, atol),)
-        if tsign < 0:
+        if tsign < 0 and not hasattr(func, 'eval_into'):
             base = func
             call = lambda tt, yy: tuple(-v for v in base(-tt, yy))
         else:
             call = func
-        return _GenericSolve(call, y0, t_host, rtol, atol, options).run()
+        return _GenericSolve(call, y0, t_host, rtol, atol, options, tsign=tsign).run()
 
 
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
@@ -525,6 +588,11 @@ class _AdjointFn(torch.autograd.Function):
             return tuple(v.detach() for v in fe) + vy + (vt.reshape(()), vp)
 
         T = ans[0].shape[0]
+        native_vjp = (n == 1 and os.environ.get('NODE_B200_NATIVE_VJP', '1') != '0' and recognise_odefunc(func) is not None
+                      and _fusable_state(recognise_odefunc(func), (ans[0][0],))
+                      and native.lib().node_b200_vjp_workspace_bytes(*[int(v) for v in ans[0].shape[1:]]) > 0)
+        if native_vjp:
+            augmented = _FusedAugmented(func)
         with torch.no_grad():
             adj_y = tuple(g[-1] for g in grad_output)
             adj_p = torch.zeros_like(flat_params)
@@ -533,7 +601,11 @@ class _AdjointFn(torch.autograd.Function):
             for i in range(T - 1, 0, -1):
                 ans_i = tuple(a[i] for a in ans)
                 ti = torch.tensor(t_host[i], dtype=ans[0].dtype, device=ans[0].device)
-                func_i = func(ti, ans_i)
+                if native_vjp:
+                    func_i = (odefunc_forward(func, float(t_host[i]), ans_i[0].contiguous()),)
+                    _unwrap(func).nfe += 1
+                else:
+                    func_i = func(ti, ans_i)
                 d = sum(torch.dot(f.reshape(-1), g[i].reshape(-1)).view(1) for f, g in zip(func_i, grad_output))
                 adj_t = adj_t - d.reshape(())
                 tv.append(d)
@@ -548,6 +620,7 @@ class _AdjointFn(torch.autograd.Function):
                 adj_y = tuple(a + g[i - 1] for a, g in zip(adj_y, grad_output))
             tv.append(adj_t.reshape(1))
             time_vjps = torch.cat(tv[::-1]).to(t.dtype)
+        last_stats['adjoint_vjp'] = 'native' if native_vjp else 'autograd'
         return (None, time_vjps, None, None, None, None, adj_p) + tuple(adj_y)
 
 
