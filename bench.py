@@ -192,6 +192,43 @@ def rk_roofline(device, pk):
                 peak_source=pk['src'], note='E = 32Mi fp32 per tensor (9 tensors, 1.1 GiB) so every pass streams from HBM')
 
 
+def train_step_rate(dev, batch, steps, warmup):
+    """cfg3: CIFAR-10 ODENet training step - forward, cross-entropy, odeint_adjoint backward through the native VJP
+    kernels, SGD step (reproduce.sh:3-6 hyper-parameters). One rank; returns a dict for the JSON line."""
+    from node_b200 import solver
+    torch.manual_seed(0)
+    net = build_model(dev, adjoint=True).train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(99)
+    x = torch.rand(batch, 3, 32, 32, generator=g).to(dev)
+    y = torch.randint(0, 10, (batch,), generator=g).to(dev)
+    nfe = [0, 0]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        nfe[0] = net.nfe(reset=True)
+        loss.backward()
+        nfe[1] = net.nfe(reset=True)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    dt = a.elapsed_time(b) * 1e-3
+    return dict(images_per_s=batch * steps / dt, ms_per_step=1e3 * dt / steps, batch=batch, steps=steps, nfe_forward=nfe[0],
+                nfe_backward=nfe[1], adjoint_vjp=solver.last_stats.get('adjoint_vjp'), loss=float(loss),
+                note='forward + CE loss + odeint_adjoint backward (native VJP kernels, tol 1e-3) + SGD step; '
+                     'downsampler / classifier autograd in PyTorch fp32')
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -202,6 +239,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=1024)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--train-batch', type=int, default=1024, help='batch of the adjoint training-step measurement (0 = skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     if args.impl == 'reference':
@@ -319,6 +357,8 @@ def main():
                               n_accept=stats.get('n_accept'), n_reject=stats.get('n_reject')))
     if world == 1:
         line['roofline_rk'] = rk_roofline(dev, pk)
+        if args.train_batch > 0:
+            line['train_step'] = train_step_rate(dev, args.train_batch, max(2, args.steps // 2), 2)
         if not args.skip_cpu:
             threads = os.cpu_count() or 1
             rate, times = cpu_forward_rate(min(B, args.cpu_sample), args.cpu_seconds, threads)

@@ -35,44 +35,78 @@ template <> __device__ __forceinline__ void vstore<double>(double* p, const doub
 }
 
 // ---- K2: out = y0 + sum_j (h*c_j)*k_j ------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kThreads) k_stage_combine(const node_ctl_t* __restrict__ ctl, int row, T* __restrict__ out,
+// ROW is a template parameter: the coefficient row, its non-zero entries and therefore the set of source tensors
+// are compile-time, so every 128-bit load of an iteration (y0 + up to 6 k's, two vectors each) is issued before the
+// first use - the kernel is bound by HBM, not by load latency.
+template <typename T, int ROW>
+__global__ void __launch_bounds__(kThreads) k_stage_combine(const node_ctl_t* __restrict__ ctl, T* __restrict__ out,
                                                             const T* __restrict__ y0, KPtrs ks, int64_t n) {
   using A = Arith<T>;
   constexpr int V = Vec<T>::n;
+  constexpr int U = 2;                      // vectors per thread per iteration
   // row 7: probe step h0; row 6 (dense-output mid-point) runs AFTER the controller accepted the step, when
   // ctl->h* already hold the next attempt's size, so it takes the accepted step's h saved in it_h*.
-  const T h = row == 7 ? (sizeof(T) == 4 ? (T)ctl->h0_32 : (T)ctl->h0)
-            : row == 6 ? (sizeof(T) == 4 ? (T)ctl->it_h32 : (T)ctl->it_h64) : ctl_h<T>(ctl);
+  const T h = ROW == 7 ? (sizeof(T) == 4 ? (T)ctl->h0_32 : (T)ctl->h0)
+            : ROW == 6 ? (sizeof(T) == 4 ? (T)ctl->it_h32 : (T)ctl->it_h64) : ctl_h<T>(ctl);
   T hc[7];
-  int src[7];
-  int nk = 0;
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const double c = kCoef(row, j);
-    if (j < kRowLen(row) && c != 0.0) { hc[nk] = A::mul(h, (T)c); src[nk] = j; ++nk; }
-  }
+  for (int j = 0; j < 7; ++j) hc[j] = A::mul(h, (T)kCoef(ROW, j));
   const int64_t nvec = n / V;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    T acc[V], y[V], kv[V];
+  const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i0 = tid; i0 < nvec; i0 += nthr * U) {
+    T kv[U][7][V], y[U][V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = (T)0;
-    for (int j = 0; j < nk; ++j) {
-      vload<T>(reinterpret_cast<const T*>(ks.p[src[j]]) + i * V, kv);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * nthr;
+      if (i < nvec) {
+        vload<T>(y0 + i * V, y[u]);
 #pragma unroll
-      for (int e = 0; e < V; ++e) acc[e] = A::add(acc[e], A::mul(hc[j], kv[e]));
+        for (int j = 0; j < 7; ++j)
+          if (j < kRowLen(ROW) && kCoef(ROW, j) != 0.0) vload<T>(reinterpret_cast<const T*>(ks.p[j]) + i * V, kv[u][j]);
+      }
     }
-    vload<T>(y0 + i * V, y);
 #pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = A::add(y[e], acc[e]);
-    vstore<T>(out + i * V, acc);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * nthr;
+      if (i < nvec) {
+        T acc[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = (T)0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {        // reference order, zero coefficients skipped (adding +-0 changes nothing)
+          if (j < kRowLen(ROW) && kCoef(ROW, j) != 0.0) {
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[e] = A::add(acc[e], A::mul(hc[j], kv[u][j][e]));
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = A::add(y[u][e], acc[e]);
+        vstore<T>(out + i * V, acc);
+      }
+    }
   }
   // scalar tail
-  for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (int64_t i = nvec * V + tid; i < n; i += nthr) {
     T acc = (T)0;
-    for (int j = 0; j < nk; ++j) acc = A::add(acc, A::mul(hc[j], reinterpret_cast<const T*>(ks.p[src[j]])[i]));
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < kRowLen(ROW) && kCoef(ROW, j) != 0.0) acc = A::add(acc, A::mul(hc[j], reinterpret_cast<const T*>(ks.p[j])[i]));
     out[i] = A::add(y0[i], acc);
+  }
+}
+
+template <typename T>
+static void launch_stage_combine(int row, int grid, cudaStream_t st, const node_ctl_t* ctl, T* out, const T* y0, const KPtrs& kp, int64_t n) {
+  switch (row) {
+    case 0: k_stage_combine<T, 0><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 1: k_stage_combine<T, 1><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 2: k_stage_combine<T, 2><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 3: k_stage_combine<T, 3><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 4: k_stage_combine<T, 4><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 5: k_stage_combine<T, 5><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    case 6: k_stage_combine<T, 6><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
+    default: k_stage_combine<T, 7><<<grid, kThreads, 0, st>>>(ctl, out, y0, kp, n); break;
   }
 }
 
@@ -375,6 +409,14 @@ __global__ void k_ctl_init(node_ctl_t* c, int dtype, int n_seg, double safety, d
   c->max_num_steps = max_num_steps; c->n_out = n_out; c->tsign = tsign; c->next_out = 1;
 }
 
+// elementwise kernels without per-block partials: up to 8 resident blocks per SM
+static int grid_wide(int64_t n_items) {
+  int64_t b = (n_items + kThreads - 1) / kThreads;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
 static int grid_for(int64_t n_items) {
   int64_t b = (n_items + kThreads - 1) / kThreads;
   if (b < 1) b = 1;
@@ -430,9 +472,9 @@ extern "C" int node_b200_rk_stage_combine(const node_ctl_t* ctl, int dtype, int 
   for (int i = 0; i < 7; ++i) kp.p[i] = i < n_k ? ks[i] : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == NODE_F32) {
-    k_stage_combine<float><<<grid_for(numel / 4 + 1) , kThreads, 0, st>>>(ctl, which, (float*)out, (const float*)y0, kp, numel);
+    launch_stage_combine<float>(which, grid_wide(numel / 8 + 1), st, ctl, (float*)out, (const float*)y0, kp, numel);
   } else {
-    k_stage_combine<double><<<grid_for(numel / 2 + 1), kThreads, 0, st>>>(ctl, which, (double*)out, (const double*)y0, kp, numel);
+    launch_stage_combine<double>(which, grid_wide(numel / 4 + 1), st, ctl, (double*)out, (const double*)y0, kp, numel);
   }
   return (int)cudaGetLastError();
 }

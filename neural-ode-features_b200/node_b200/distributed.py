@@ -35,6 +35,11 @@ def group():
     return _group
 
 
+def rank():
+    import torch.distributed as dist
+    return dist.get_rank(_group)
+
+
 def all_reduce_sum(t):
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)

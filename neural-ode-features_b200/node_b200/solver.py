@@ -252,6 +252,11 @@ class _FusedAugmented(object):
     """The adjoint's augmented dynamics (adjoint.py:32-55) served by the native VJP kernels: the generic route
     calls eval_into() with views of its own stage buffers, so nothing is copied and no autograd graph exists."""
 
+    # Members 2.. of the augmented state (adj_t, adj_params) are SUMS over the batch: when the batch is sharded every
+    # rank holds a partial; the generic route all-reduces them after each evaluation so that all ranks integrate the
+    # identical global values, and counts their error norms once (SURVEY 8e "adjoint collective").
+    replicated_from = 2
+
     def __init__(self, func):
         self.func = func
         self.target = _unwrap(func)
@@ -342,9 +347,10 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
 class _GenericSolve(object):
     NBUF = 11  # Y0 Y1 F0 F1 K2..K6 YMID YI
 
-    def __init__(self, func, y0, t_host, rtol, atol, opts, tsign=1):
+    def __init__(self, func, y0, t_host, rtol, atol, opts, tsign=1, rep_from=None):
         self.func = func
         self.tsign = tsign
+        self.rep_from = len(y0) if rep_from is None else rep_from   # first member that is a batch sum (identical on all ranks)
         ref = y0[0]
         if ref.dtype not in (torch.float32, torch.float64):
             raise TypeError('node_b200 serves float32 and float64 states, got {}'.format(ref.dtype))
@@ -377,8 +383,9 @@ class _GenericSolve(object):
         nseg = len(y0)
         rt = list(rtol) if _is_iterable(rtol) else [rtol] * nseg
         at = list(atol) if _is_iterable(atol) else [atol] * nseg
-        numel = native.host_i64([dist_state.global_numel(n, self.device) if dist_state.group() is not None else n
-                                 for n in self.lens])
+        sharded = dist_state.group() is not None
+        numel = native.host_i64([dist_state.global_numel(n, self.device) if (sharded and i < self.rep_from) else n
+                                 for i, n in enumerate(self.lens)])
         err = native.lib().node_b200_ctl_init(
             native.ptr(self.ctl), self.code, nseg, native.host_f64(rt), native.host_f64(at),
             numel, _dflt(opts.get('safety', 0.9)), _dflt(opts.get('ifactor', 10.0)),
@@ -399,10 +406,12 @@ class _GenericSolve(object):
     def _eval(self, t0d, src, dst):
         if hasattr(self.func, 'eval_into'):
             self.func.eval_into(t0d, self._views(src), self._views(dst), self.tsign)
-            return
-        vals = self.func(t0d, tuple(self._views(src)))
-        for b, v in zip(self._views(dst), vals):
-            b.copy_(v)
+        else:
+            vals = self.func(t0d, tuple(self._views(src)))
+            for b, v in zip(self._views(dst), vals):
+                b.copy_(v)
+        if dist_state.group() is not None and self.rep_from < len(self.lens):
+            dist_state.all_reduce_sum(self.bufs[dst][self.offs[self.rep_from]:])   # partial batch sums -> global
 
     def _kptrs(self, idxs):
         arr = (native._vp * 7)()
@@ -415,6 +424,8 @@ class _GenericSolve(object):
         nrows = 2 * len(self.lens)
         native.check(lib.node_b200_reduce_partials(native.ptr(self.partials), nrows, native.ptr(self.sums), sp), 'reduce')
         if dist_state.group() is not None:
+            if self.rep_from < len(self.lens) and dist_state.rank() != 0:
+                self.sums[2 * self.rep_from:].zero_()        # replicated members: counted once (rank 0's copy)
             dist_state.all_reduce_sum(self.sums)
         native.check(lib.node_b200_controller(native.ptr(self.ctl), mode, native.ptr(self.sums),
                                               native.ptr(self.flag) if mode == 2 else native._vp(0),
@@ -515,7 +526,8 @@ def _solve(func, y0, t, rtol, atol, options):
             call = lambda tt, yy: tuple(-v for v in base(-tt, yy))
         else:
             call = func
-        return _GenericSolve(call, y0, t_host, rtol, atol, options, tsign=tsign).run()
+        return _GenericSolve(call, y0, t_host, rtol, atol, options, tsign=tsign,
+                             rep_from=getattr(func, 'replicated_from', None)).run()
 
 
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
@@ -593,6 +605,8 @@ class _AdjointFn(torch.autograd.Function):
                       and native.lib().node_b200_vjp_workspace_bytes(*[int(v) for v in ans[0].shape[1:]]) > 0)
         if native_vjp:
             augmented = _FusedAugmented(func)
+        else:
+            augmented.replicated_from = 2 * n       # adj_t, adj_params: sums over the (possibly sharded) batch
         with torch.no_grad():
             adj_y = tuple(g[-1] for g in grad_output)
             adj_p = torch.zeros_like(flat_params)
@@ -607,6 +621,8 @@ class _AdjointFn(torch.autograd.Function):
                 else:
                     func_i = func(ti, ans_i)
                 d = sum(torch.dot(f.reshape(-1), g[i].reshape(-1)).view(1) for f, g in zip(func_i, grad_output))
+                if dist_state.group() is not None:
+                    dist_state.all_reduce_sum(d)              # dL/dt is a sum over the whole (sharded) batch
                 adj_t = adj_t - d.reshape(())
                 tv.append(d)
                 if adj_p.numel() == 0:
