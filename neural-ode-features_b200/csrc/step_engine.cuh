@@ -223,15 +223,18 @@ struct Jobs {
 };
 
 // Issue one conv job (9 taps) of slot `s`: keep the TMA weight ring fed, issue the tcgen05.mma stream, commit.
-// Runs on ONE thread (the slot's leader); the ring counters live in shared memory and travel with the turn.
+// Runs on the slot's whole first WARP with warp-uniform arguments (descriptors then live in uniform registers);
+// the asynchronous instructions themselves are issued by one elected lane. The ring counters live in shared
+// memory and travel with the turn.
 template <class T, int NSLOT>
 __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, uint32_t tmem,
                                                int s, uint32_t job, uint32_t nth, bool split, bool& timeout) {
+  const bool lead = ptx::elect_one();
   if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;   // my slot's nth turn
 #ifdef NODE_STEP_DEBUG
-  if (blockIdx.x == 0 && nth < 256) g_step_dbg[(s * 256 + nth) * 4 + 1] = clock64();
+  if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg[(s * 256 + nth) * 4 + 1] = clock64();
 #endif
-  uint32_t issued = sm.ring[0], tapx = sm.ring[1];
+  uint32_t issued = __shfl_sync(0xffffffffu, sm.ring[0], 0), tapx = __shfl_sync(0xffffffffu, sm.ring[1], 0);
   const uint32_t total = jb.jobs * 9;
   ptx::tc_fence_after();
   const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
@@ -244,12 +247,14 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
 #endif
       if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
 #ifdef NODE_STEP_DEBUG
-      if (blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 1] += clock64() - q0;
+      if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 1] += clock64() - q0;
 #endif
       const uint32_t cv = jb.conv_of(issued / 9, NSLOT), tp = issued % 9;
-      ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
-      ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
-                    sm.bar_wfull + 8 * slot);
+      if (lead) {
+        ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
+        ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                      sm.bar_wfull + 8 * slot);
+      }
       ++issued;
     }
     const uint32_t slot = tapx % kNW;
@@ -258,39 +263,40 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
 #endif
     if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
 #ifdef NODE_STEP_DEBUG
-    if (blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 0] += clock64() - q1;
+    if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 0] += clock64() - q1;
 #endif
     ptx::tc_fence_after();
-#ifdef NODE_STEP_EXPERIMENT_ALIGNED
-    const int off = (tap / 3 - 1) * 8;      // timing experiment only (wrong results): 128-byte aligned row offsets
-#else
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
-#endif
     const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+    if (lead) {
 #pragma unroll
-    for (int mt = 0; mt < T::MT; ++mt) {
-      const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
-      const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
+      for (int mt = 0; mt < T::MT; ++mt) {
+        const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
+        const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-        const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
-        const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
-        if (split) {
-          const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
-          ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);   // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
-          ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);       // a_lo * w_hi         -> columns [0,64)
-        } else {
-          ptx::mma_f16_ss(d, a_hi, bk, kIdF16N64, first);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
+          const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
+          const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
+          if (split) {
+            const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+            ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);   // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
+            ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);       // a_lo * w_hi         -> columns [0,64)
+          } else {
+            ptx::mma_f16_ss(d, a_hi, bk, kIdF16N64, first);
+          }
         }
       }
+      ptx::tc_commit(sm.bar_wfree + 8 * slot);
     }
-    ptx::tc_commit(sm.bar_wfree + 8 * slot);
     ++tapx;
   }
-  ptx::tc_commit(sm.bar_acc + 8 * s);
-  sm.ring[0] = issued; sm.ring[1] = tapx;
-  if (job + 1 < jb.jobs) ptx::mbar_arrive(sm.bar_turn + 8 * jb.slot_of(job + 1, NSLOT));   // release: ring counters travel with it
+  if (lead) {
+    ptx::tc_commit(sm.bar_acc + 8 * s);
+    sm.ring[0] = issued; sm.ring[1] = tapx;
+    if (job + 1 < jb.jobs) ptx::mbar_arrive(sm.bar_turn + 8 * jb.slot_of(job + 1, NSLOT));   // release: ring counters travel with it
+  }
+  __syncwarp();
 }
 
 // Publish the A image and run the conv job on the tensor core; returns when the accumulators are complete.
@@ -305,10 +311,9 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
   const bool rec = blockIdx.x == 0 && me.wt == 0 && njob < 256;
   if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 0] = clock64();
 #endif
-  if (me.warp == 0) {
-    if (me.lane == 0) issue_conv_job<T, NSLOT>(sm, jb, w16, tmem, me.slot, job, njob, split, timeout);
-    __syncwarp();
-  }
+  if (__shfl_sync(0xffffffffu, me.warp, 0) == 0)     // shuffles: tell the compiler these values are warp-uniform
+    issue_conv_job<T, NSLOT>(sm, jb, w16, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, me.slot, 0),
+                             __shfl_sync(0xffffffffu, job, 0), __shfl_sync(0xffffffffu, njob, 0), split, timeout);
 #ifdef NODE_STEP_DEBUG
   if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 2] = clock64();
 #endif

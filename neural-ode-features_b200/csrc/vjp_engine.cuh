@@ -173,6 +173,8 @@ __device__ __forceinline__ int vjp_set_of(uint32_t job) { const uint32_t k = job
 template <class T>
 __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, VjpRing& rg, const uint16_t* __restrict__ w16, uint32_t tmem,
                                               uint32_t dcol, uint32_t idesc, bool& timeout) {
+  // whole first warp, warp-uniform arguments, asynchronous instructions by one elected lane (see step_engine.cuh)
+  const bool lead = ptx::elect_one();
   ptx::tc_fence_after();
   const uint32_t abase = sm.s.abase + T::HALO * 16;
 #pragma unroll 1
@@ -181,9 +183,11 @@ __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, VjpRing& rg, co
       const uint32_t slot = rg.issued % kNW;
       if (rg.issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.s.bar_wfree + 8 * slot, ((rg.issued / kNW) - 1) & 1)) timeout = true;
       const uint32_t set = (uint32_t)vjp_set_of(rg.issued / 9), tp = rg.issued % 9;
-      ptx::mbar_expect_tx(sm.s.bar_wfull + 8 * slot, kW16TileBytes);
-      ptx::bulk_g2s(sm.s.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(set * 9 + tp) * kW16TileBytes, kW16TileBytes,
-                    sm.s.bar_wfull + 8 * slot);
+      if (lead) {
+        ptx::mbar_expect_tx(sm.s.bar_wfull + 8 * slot, kW16TileBytes);
+        ptx::bulk_g2s(sm.s.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(set * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                      sm.s.bar_wfull + 8 * slot);
+      }
       ++rg.issued;
     }
     const uint32_t slot = rg.tapx % kNW;
@@ -192,24 +196,27 @@ __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, VjpRing& rg, co
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
     const uint64_t b_hi0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes);
     const uint64_t b_lo0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes + 64 * 128);
+    if (lead) {
 #pragma unroll
-    for (int mt = 0; mt < T::MT; ++mt) {
-      const uint32_t d = tmem + dcol + (uint32_t)(mt * 64);
-      const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
+      for (int mt = 0; mt < T::MT; ++mt) {
+        const uint32_t d = tmem + dcol + (uint32_t)(mt * 64);
+        const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-        const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
-        const uint64_t kadv = (uint64_t)((ks * 32) >> 4);
-        ptx::mma_f16_ss(d, a_hi, b_hi0 + kadv, idesc, (tap == 0 && ks == 0) ? 0u : 1u);
-        ptx::mma_f16_ss(d, a_lo, b_hi0 + kadv, idesc, 1u);
-        ptx::mma_f16_ss(d, a_hi, b_lo0 + kadv, idesc, 1u);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
+          const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+          const uint64_t kadv = (uint64_t)((ks * 32) >> 4);
+          ptx::mma_f16_ss(d, a_hi, b_hi0 + kadv, idesc, (tap == 0 && ks == 0) ? 0u : 1u);
+          ptx::mma_f16_ss(d, a_lo, b_hi0 + kadv, idesc, 1u);
+          ptx::mma_f16_ss(d, a_hi, b_lo0 + kadv, idesc, 1u);
+        }
       }
+      ptx::tc_commit(sm.s.bar_wfree + 8 * slot);
     }
-    ptx::tc_commit(sm.s.bar_wfree + 8 * slot);
     ++rg.tapx;
   }
-  ptx::tc_commit(sm.s.bar_acc);
+  if (lead) ptx::tc_commit(sm.s.bar_acc);
+  __syncwarp();
 }
 
 template <class T>
@@ -218,9 +225,13 @@ __device__ __forceinline__ void vjp_conv_run(const VjpSmem& sm, const Who& me, V
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   slot_sync(0, T::P);
-  if (me.warp == 0) {
-    if (me.lane == 0) vjp_issue_job<T>(sm, rg, w16, tmem, dcol, idesc, timeout);
-    __syncwarp();
+  if (__shfl_sync(0xffffffffu, me.warp, 0) == 0) {     // shuffles: tell the compiler these values are warp-uniform
+    VjpRing ru;
+    ru.issued = __shfl_sync(0xffffffffu, rg.issued, 0); ru.tapx = __shfl_sync(0xffffffffu, rg.tapx, 0);
+    ru.total = __shfl_sync(0xffffffffu, rg.total, 0);
+    vjp_issue_job<T>(sm, ru, w16, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, dcol, 0),
+                     __shfl_sync(0xffffffffu, idesc, 0), timeout);
+    rg = ru;
   }
   if (!timeout && !ptx::mbar_wait_relaxed(sm.s.bar_acc, njob & 1)) timeout = true;
   ++njob;

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
 
   // this thread's position in the strip
   const int wt = tid, img_l = wt / T::IS;
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
     }
     ptx::fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
+    if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {      // first warp, warp-uniform; one elected lane issues
+      const bool lead = ptx::elect_one();
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int tp = 0; tp < ntap; ++tp) {
@@ -128,11 +129,14 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
           const uint32_t brow = rimg + (uint32_t)(T::HALO + k0 + off) * 16;
           const uint64_t b_hi = ptx::make_desc_nosw(brow, r_lbo, r_sbo);
           const uint64_t b_lo = ptx::make_desc_nosw(brow + 10u * (uint32_t)WT::R_STRIDE, r_lbo, r_sbo);
-          ptx::mma_f16_ss(d, adesc, b_hi, wg_idesc(kWgCols), (it == 0 && k0 == 0) ? 0u : 1u);
-          ptx::mma_f16_ss(d, adesc, b_lo, wg_idesc(64), 1u);
+          if (lead) {
+            ptx::mma_f16_ss(d, adesc, b_hi, wg_idesc(kWgCols), (it == 0 && k0 == 0) ? 0u : 1u);
+            ptx::mma_f16_ss(d, adesc, b_lo, wg_idesc(64), 1u);
+          }
         }
       }
-      ptx::tc_commit(bar);
+      if (lead) ptx::tc_commit(bar);
+      __syncwarp();
     }
     if (!timeout && !ptx::mbar_wait_relaxed(bar, it & 1)) timeout = true;   // operands free again / accumulators current
     ptx::tc_fence_after();
