@@ -27,6 +27,8 @@ namespace node {
 
 constexpr int kNW = 4;                    // weight ring depth (taps)
 constexpr int kWGap = 2;                  // a ring slot is refilled once the tap two back has retired
+constexpr int kTbFloats = 2 * 16 * 9 * 4; // per slot: bias + t*Tmap for [conv][4-channel block][border class][4 channels]
+constexpr float kGnIllCond = 16.0f;       // one-pass GroupNorm moments are redone in two passes when mean^2 > 16 var
 
 template <int H_, int W_>
 struct Tile {
@@ -47,8 +49,9 @@ struct Tile {
 };
 
 __host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
-  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 32 * 4 +
-         (size_t)NSLOT * G * 32 * 8 + 3 * 32 * 16 + 2 * 64 * 4 + 2 * 9 * 64 * 4 + 64 * 4 + 32 * 8 + 16 * 8 + 64;
+  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
+         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 3 * 32 * 16 + (size_t)NSLOT * kTbFloats * 4 + 64 * 4 + 32 * 8 +
+         16 * 8 + 64;
 }
 
 // Tuning aid: when enabled (node_b200_step_debug), CTA 0 records clock64() stamps of every conv job of each slot:
@@ -61,8 +64,11 @@ static __device__ long long g_step_dbg2[2 * 256 * 2];   // clocks the leader wai
 struct StepSmem {
   uint32_t wring;        // shared address of the weight ring
   uint32_t abase;        // shared address of slot 0's A image (hi part)
-  float* part;           // [NSLOT][NWARP][2][16] warp partials of the GroupNorm reductions
+  float* part;           // [NSLOT][NWARP][2][32] warp partials of the GroupNorm reductions (k_vjp: [NWARP][2][16])
   float2* stat;          // [NSLOT][G][32] (mean, rstd)
+  float4* aff;           // [NSLOT][G][32] (a0, a1, b0, b1): GN(x) = a*x + b for the two channels of a group (k_step)
+  float4* tb;            // [NSLOT][2][16][9] bias + t*Tmap of the evaluation the slot is working on (k_step)
+  uint32_t* illcond;     // [NSLOT] set by a fold thread when a one-pass variance is ill-conditioned (k_step)
   float4* gnp;           // [3][32] (gamma0, gamma1, beta0, beta1) per group
   float* bias;           // [2][64]
   float* tmapc;          // [2][9][64]
@@ -108,6 +114,47 @@ __device__ __forceinline__ float xreduce16(const float (&u)[16], int lane) {
   const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
   const float r = keep + __shfl_xor_sync(0xffffffffu, send, 1);
   return r + __shfl_xor_sync(0xffffffffu, r, 16);
+}
+
+// Sum 32 per-lane values across the warp; lane L returns the total of u[L] (31 shuffles).
+__device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
+  float a[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? u[i] : u[i + 16], keep = up ? u[i + 16] : u[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float b[8], c[4], d[2];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? b[i] : b[i + 4], keep = up ? b[i + 4] : b[i];
+      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? c[i] : c[i + 2], keep = up ? c[i + 2] : c[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool up = lane & 1;
+  const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
 // Per-thread constants of a worker.
@@ -176,6 +223,133 @@ __device__ __forceinline__ void gn_stats(const StepSmem& sm, const Who& me, int 
                  return valid ? fmaf(d0, d0, d1 * d1) : 0.f;
                },
                [&](float2* dst, float tot) { dst->y = 1.0f / sqrtf(tot * inv_n + eps); });
+}
+
+// k_step's GroupNorm statistics: ONE reduction round. Every thread contributes, for each of its 16 groups, the sum and the
+// sum of squares of its two channels; the fold threads turn the totals into the affine form GN(x) = a*x + b of
+// GroupNorm `n` (sm.aff). var = E[x^2] - mean^2 loses digits when |mean| >> std, so a fold thread that sees
+// mean^2 > kGnIllCond * var raises the slot's flag and the whole slot repeats the statistics with the two-pass scheme
+// of the reference's native_group_norm (gn_reduce with squared deviations) - rare, slot-uniform, deterministic.
+template <class T>
+__device__ __forceinline__ void gn_affine(const StepSmem& sm, const Who& me, int hb, int n, const float (&x)[32], bool valid, float eps) {
+  constexpr float inv_n = 1.0f / (float)(kCpg * T::HW);
+  float* part = sm.part + (me.slot * T::NWARP + me.warp) * 64;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {              // q = 0: sums, q = 1: sums of squares (x is zero on padding)
+    float u[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      u[j] = q == 0 ? x[2 * j] + x[2 * j + 1] : fmaf(x[2 * j], x[2 * j], x[2 * j + 1] * x[2 * j + 1]);
+    if (!me.straddle) {
+      const float r = xreduce16(u, me.lane);
+      if (me.lane < 16) part[16 * q + me.lane] = r;
+    } else {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = me.isB ? 0.f : u[j];
+      const float ra = xreduce16(v, me.lane);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = me.isB ? u[j] : 0.f;
+      const float rb = xreduce16(v, me.lane);
+      if (me.lane < 16) { part[16 * q + me.lane] = ra; part[32 + 16 * q + me.lane] = rb; }
+    }
+  }
+  slot_sync(me.slot, T::P);
+  const bool folder = me.wt < T::G * 16;
+  const int fimg = me.wt >> 4, fg = me.wt & 15;
+  auto publish = [&](float mean, float var) {
+    const float rstd = 1.0f / sqrtf(var + eps);
+    const float4 p = sm.gnp[n * 32 + 16 * hb + fg];
+    const float a0 = rstd * p.x, a1 = rstd * p.y;
+    sm.aff[(me.slot * T::G + fimg) * 32 + 16 * hb + fg] = make_float4(a0, a1, p.z - a0 * mean, p.w - a1 * mean);
+  };
+  if (folder) {
+    const float* pp = sm.part + me.slot * T::NWARP * 64;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < T::NWARP; ++w) {
+      const int ia = (w * 32) / T::IS, ib = (w * 32 + 31) / T::IS;
+      if (ia == fimg) { s1 += pp[w * 64 + fg]; s2 += pp[w * 64 + 16 + fg]; }
+      if (ib != ia && ib == fimg) { s1 += pp[w * 64 + 32 + fg]; s2 += pp[w * 64 + 48 + fg]; }
+    }
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.f);
+    sm.stat[(me.slot * T::G + fimg) * 32 + 16 * hb + fg].x = mean;
+    if (mean * mean > kGnIllCond * var) sm.illcond[me.slot] = 1u;
+    publish(mean, var);
+  }
+  slot_sync(me.slot, T::P);
+  if (*reinterpret_cast<volatile uint32_t*>(sm.illcond + me.slot) != 0u) {           // slot-uniform: read after the barrier, cleared behind the next one
+    // the one-pass means are accurate (plain sums); every cell of the slot gets the two-pass variance
+    const float2* st = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+    float* p32 = sm.part + (me.slot * T::NWARP + me.warp) * 64;
+    {
+      float u[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float m = st[j].x;
+        const float d0 = x[2 * j] - m, d1 = x[2 * j + 1] - m;
+        u[j] = valid ? fmaf(d0, d0, d1 * d1) : 0.f;
+      }
+      if (!me.straddle) {
+        const float r = xreduce16(u, me.lane);
+        if (me.lane < 16) p32[me.lane] = r;
+      } else {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = me.isB ? 0.f : u[j];
+        const float ra = xreduce16(v, me.lane);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = me.isB ? u[j] : 0.f;
+        const float rb = xreduce16(v, me.lane);
+        if (me.lane < 16) { p32[me.lane] = ra; p32[32 + me.lane] = rb; }
+      }
+    }
+    slot_sync(me.slot, T::P);
+    if (me.wt == 0) sm.illcond[me.slot] = 0u;
+    if (folder) {
+      const float* pp = sm.part + me.slot * T::NWARP * 64;
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < T::NWARP; ++w) {
+        const int ia = (w * 32) / T::IS, ib = (w * 32 + 31) / T::IS;
+        if (ia == fimg) tot += pp[w * 64 + fg];
+        if (ib != ia && ib == fimg) tot += pp[w * 64 + 32 + fg];
+      }
+      publish(sm.stat[(me.slot * T::G + fimg) * 32 + 16 * hb + fg].x, tot * inv_n);
+    }
+    slot_sync(me.slot, T::P);
+  }
+}
+
+// relu(a*x + b) * scale (sm.aff of this thread's image) split into fp16 hi + lo and written into this position's row
+// of the A image (k-chunks [4*hb, 4*hb+4)).
+template <class T>
+__device__ __forceinline__ void affine_to_A(const StepSmem& sm, const Who& me, int hb, const float (&x)[32], float scale, bool valid,
+                                            bool split) {
+  const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+  const uint32_t row = sm.abase + me.slot * 2 * T::A_PART + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
+#pragma unroll
+  for (int kc = 0; kc < 4; ++kc) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = kc * 4 + j;
+      const float4 p = af[g];
+      const float r0 = fmaxf(fmaf(x[2 * g], p.x, p.z), 0.f) * scale;
+      const float r1 = fmaxf(fmaf(x[2 * g + 1], p.y, p.w), 0.f) * scale;
+      const __half2 h = __floats2half2_rn(r0, r1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    if (valid) {
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + kc * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      if (split)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + kc * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+  }
 }
 
 // relu(GN(x)) * scale split into fp16 hi + lo and written into this position's row of the A image
@@ -325,25 +499,37 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
   ptx::tc_fence_after();
 }
 
-// x <- acc/scale + bias + t*Tmap for output channels [32*hb, 32*hb+32) of this thread's position.
+// x <- acc/scale + (bias + t*Tmap) for output channels [32*hb, 32*hb+32) of this thread's position.
 template <class T>
 __device__ __forceinline__ void conv_read(const StepSmem& sm, const Who& me, int hb, float (&x)[32], uint32_t tmem, int cv,
-                                          float inv_scale, float t, bool split, bool valid) {
+                                          float inv_scale, bool split, bool valid) {
   const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128 + 32 * hb);
-  const float* bs = sm.bias + cv * 64 + 32 * hb;
-  const float* tm = sm.tmapc + (cv * 9 + me.cls) * 64 + 32 * hb;
+  const float4* tb = sm.tb + ((me.slot * 2 + cv) * 16 + 8 * hb) * 9 + me.cls;
 #pragma unroll
   for (int c0 = 0; c0 < 32; c0 += 8) {
     uint32_t v0[8], v1[8];
     ptx::tmem_ld8(taddr + c0, v0);
     if (split) ptx::tmem_ld8(taddr + 64 + c0, v1);
+    const float4 e0 = tb[(c0 >> 2) * 9], e1 = tb[((c0 >> 2) + 1) * 9];
+    const float ex[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     ptx::tc_wait_ld();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float acc = __uint_as_float(v0[j]);
       if (split) acc += __uint_as_float(v1[j]);
-      x[c0 + j] = valid ? fmaf(acc, inv_scale, fmaf(t, tm[c0 + j], bs[c0 + j])) : 0.f;
+      x[c0 + j] = valid ? fmaf(acc, inv_scale, ex[j]) : 0.f;
     }
+  }
+}
+
+// bias + t*Tmap of one evaluation, for both convolutions (the slot's threads; ordered by the GroupNorm barriers that
+// separate it from the conv epilogues on both sides).
+template <class T>
+__device__ __forceinline__ void make_tb(const StepSmem& sm, const Who& me, const FusedWs& w, float t) {
+  float* tb = reinterpret_cast<float*>(sm.tb) + me.slot * kTbFloats;
+  for (int i = me.wt; i < 2 * 9 * 64; i += T::P) {
+    const int c = i & 63, cls = (i >> 6) % 9, cv = i / (9 * 64);
+    tb[((cv * 16 + (c >> 2)) * 9 + cls) * 4 + (c & 3)] = fmaf(t, __ldg(w.tmapc + i), __ldg(w.bias + cv * 64 + c));
   }
 }
 
@@ -405,11 +591,12 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     size_t o = 0;
     sm.wring = al; o += (size_t)kNW * kW16TileBytes;
     sm.abase = al + (uint32_t)o; o += (size_t)NSLOT * 2 * T::A_PART;
-    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 32 * 4;
+    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 64 * 4;
     sm.stat = reinterpret_cast<float2*>(base + o); o += (size_t)NSLOT * T::G * 32 * 8;
+    sm.aff = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * T::G * 32 * 16;
     sm.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
-    sm.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
-    sm.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * 64 * 4;
+    sm.tb = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * kTbFloats * 4;
+    sm.bias = nullptr; sm.tmapc = nullptr;
     sm.coef = reinterpret_cast<float*>(base + o); o += 64 * 4;
     sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
@@ -417,7 +604,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     sm.bar_turn = al + (uint32_t)o; o += 8 * 2;
     sm.bar_acc = al + (uint32_t)o; o += 8 * 2;
     sm.ring = reinterpret_cast<volatile uint32_t*>(base + o); o += 16;
-    sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o);
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o); o += 8;
+    sm.illcond = reinterpret_cast<uint32_t*>(base + o);
     // zero the A images once: padding rows / columns are never written again
     uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);
     for (int i = tid; i < NSLOT * 2 * T::A_PART / 16; i += blockDim.x) az[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -427,8 +615,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     sm.gnp[i] = make_float4(w.gn[(2 * n) * kC + 2 * g], w.gn[(2 * n) * kC + 2 * g + 1], w.gn[(2 * n + 1) * kC + 2 * g],
                             w.gn[(2 * n + 1) * kC + 2 * g + 1]);
   }
-  for (int i = tid; i < 2 * 64; i += blockDim.x) sm.bias[i] = w.bias[i];
-  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.tmapc[i] = w.tmapc[i];
+  if (tid < 2) sm.illcond[tid] = 0u;
   const float h = a.mode == MODE_STEP ? ctl->h32 : (a.mode == MODE_PROBE ? ctl->h0_32 : 0.f);
   if (tid < 64) {   // rows 0..5 stage betas, 6 = C_MID, 7 = C_ERR (misc.py:22-25: (h*c)*k)
     const int r = tid >> 3, j = tid & 7;
@@ -503,6 +690,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
       for (int ev = 0; ev < nevals; ++ev) {
         const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
         const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
+        make_tb<T>(sm, me, w, t);
 
         // ---- stage input (rk_common.py:49-51) -> GN1 -> ReLU -> A image of conv1
 #pragma unroll 1
@@ -557,36 +745,32 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
               stage_in<HW, 5>(x, Ycur, src, hc, ynew, p0, valid);
             }
           }
-          gn_stats<T>(sm, me, hb, x, valid, a.eps);
-          gn_apply_to_A<T>(sm, me, hb, x, 0, w.scal[0], valid, split);
+          gn_affine<T>(sm, me, hb, 0, x, valid, a.eps);
+          affine_to_A<T>(sm, me, hb, x, w.scal[0], valid, split);
         }
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
 
         // ---- conv1 epilogue -> GN2 -> ReLU -> A image of conv2 (model.py:343-346)
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
-          conv_read<T>(sm, me, hb, x, tmem, 0, w.scal[4], t, split, valid);
-          gn_stats<T>(sm, me, hb, x, valid, a.eps);
-          gn_apply_to_A<T>(sm, me, hb, x, 1, w.scal[1], valid, split);
+          conv_read<T>(sm, me, hb, x, tmem, 0, w.scal[4], split, valid);
+          gn_affine<T>(sm, me, hb, 1, x, valid, a.eps);
+          affine_to_A<T>(sm, me, hb, x, w.scal[1], valid, split);
         }
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
 
         // ---- conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
-          conv_read<T>(sm, me, hb, x, tmem, 1, w.scal[5], t, split, valid);
-          gn_stats<T>(sm, me, hb, x, valid, a.eps);
+          conv_read<T>(sm, me, hb, x, tmem, 1, w.scal[5], split, valid);
+          gn_affine<T>(sm, me, hb, 2, x, valid, a.eps);
           {
-            const float2* stt = sm.stat + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
-            const float4* gp = sm.gnp + 2 * 32 + 16 * hb;
+            const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
 #pragma unroll
             for (int g = 0; g < 16; ++g) {
-              const float2 s = stt[g];
-              const float4 p = gp[g];
-              const float a0 = s.y * p.x, a1 = s.y * p.y;
-              const float b0 = p.z - a0 * s.x, b1 = p.w - a1 * s.x;
-              x[2 * g] = fmaf(x[2 * g], a0, b0) * a.tsign;
-              x[2 * g + 1] = fmaf(x[2 * g + 1], a1, b1) * a.tsign;
+              const float4 p = af[g];
+              x[2 * g] = fmaf(x[2 * g], p.x, p.z) * a.tsign;
+              x[2 * g + 1] = fmaf(x[2 * g + 1], p.y, p.w) * a.tsign;
             }
           }
           if (!valid) continue;

@@ -23,47 +23,6 @@ namespace node {
 
 constexpr uint32_t kIdBF16N64 = kIdF16N64 | (1u << 7) | (1u << 10);   // kind::f16 with bf16 A and B
 
-// Sum 32 per-lane values across the warp; lane L returns the total of u[L] (31 shuffles).
-__device__ __forceinline__ float xreduce32(const float (&u)[32], int lane) {
-  float a[16];
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float send = up ? u[i] : u[i + 16], keep = up ? u[i + 16] : u[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  float b[8], c[4], d[2];
-  {
-    const bool up = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = up ? a[i] : a[i + 8], keep = up ? a[i + 8] : a[i];
-      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool up = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = up ? b[i] : b[i + 4], keep = up ? b[i + 4] : b[i];
-      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool up = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = up ? c[i] : c[i + 2], keep = up ? c[i + 2] : c[i];
-      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-  }
-  const bool up = lane & 1;
-  const float send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-
 struct VjpSmem {
   StepSmem s;            // wring, abase, part, stat (set 0), gnp, bias, tmapc, scratch, barriers of the step engine
   float2* stat3;         // [3][G][32] (mean, rstd) of GN1, GN2, GN3

@@ -36,6 +36,27 @@ def test_fused_dynamics_kernel(native_lib, golden, monkeypatch, name, mode):
     assert rel(kr.cpu(), ref) < 2e-5
 
 
+@pytest.mark.parametrize('name', ['cifar_res_n8', 'mnist_conv_n9', 'cifar_oneshot_n3'])
+def test_fused_dynamics_ill_conditioned_groupnorm(native_lib, golden, name):
+    """States whose GroupNorm cells have |mean| >> std: the step engine's one-pass moments must fall back to the
+    two-pass variance of native_group_norm (model.py:268-271) instead of cancelling."""
+    from node_b200 import solver
+    g = golden(name)
+    func = load_odefunc(g, DEV)
+    p = odefunc_params(g)
+    h0 = torch.from_numpy(g['h0'])
+    gen = torch.Generator().manual_seed(3)
+    for offset, noise, tol in [(30.0, 1.0, 1e-4), (1000.0, 0.5, 2e-3), (5.0, 0.0, 5e-4)]:   # fp32 itself is ~2e-4 / 1e-4 from fp64 on the last two
+        y = offset * torch.sign(torch.randn(h0.shape[0], h0.shape[1], 1, 1, generator=gen)) + noise * h0
+        y[0] = h0[0]                                   # well- and ill-conditioned images share a super-tile
+        ref = odefunc_port.odefunc_forward(p, torch.tensor(0.37), y)
+        k = solver.odefunc_forward(func, 0.37, y.to(DEV))
+        torch.cuda.synchronize()
+        assert torch.isfinite(k).all()
+        assert rel(k.cpu(), ref) < tol, (offset, noise)
+        assert rel(k[0].cpu(), ref[0]) < 2e-5
+
+
 def test_tf32_single_pass_mode_is_reported_separately(native_lib, golden, monkeypatch):
     from node_b200 import solver
     monkeypatch.setenv('NODE_B200_CONV', 'tf32')
