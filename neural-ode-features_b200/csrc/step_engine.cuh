@@ -25,7 +25,10 @@
 
 namespace node {
 
-constexpr int kNW = 4;                    // weight ring depth (taps)
+#ifndef NODE_KNW
+#define NODE_KNW 4
+#endif
+constexpr int kNW = NODE_KNW;             // weight ring depth (taps)
 constexpr int kWGap = 2;                  // a ring slot is refilled once the tap two back has retired
 constexpr int kTbFloats = 2 * 16 * 9 * 4; // per slot: bias + t*Tmap for [conv][4-channel block][border class][4 channels]
 constexpr float kGnIllCond = 16.0f;       // one-pass GroupNorm moments are redone in two passes when mean^2 > 16 var
@@ -59,6 +62,10 @@ __host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int 
 #ifdef NODE_STEP_DEBUG
 static __device__ long long g_step_dbg[2 * 256 * 4];
 static __device__ long long g_step_dbg2[2 * 256 * 2];   // clocks the leader waited for weights to land / for ring slots to free
+static __device__ long long g_step_phase[2 * 16];       // per slot: clocks thread 32 of CTA 0 spent in each phase of the main loop
+#define NODE_STAMP(i) do { if (rec_ph) { const long long now_ = clock64(); g_step_phase[me.slot * 16 + (i)] += now_ - last_ph; last_ph = now_; } } while (0)
+#else
+#define NODE_STAMP(i) do { } while (0)
 #endif
 
 struct StepSmem {
@@ -396,52 +403,71 @@ struct Jobs {
   __device__ __forceinline__ uint32_t conv_of(uint32_t j, int nslot) const { return j < jobs_full ? (j / nslot) & 1u : (j - jobs_full) & 1u; }
 };
 
-// Issue one conv job (9 taps) of slot `s`: keep the TMA weight ring fed, issue the tcgen05.mma stream, commit.
-// Runs on the slot's whole first WARP with warp-uniform arguments (descriptors then live in uniform registers);
-// the asynchronous instructions themselves are issued by one elected lane. The ring counters live in shared
-// memory and travel with the turn.
+// The weight tiles of a CTA form one global sequence: tile i = tap i % 9 of conv job i / 9, living in ring slot
+// i % kNW. Two warps of the slot whose turn it is drive a conv job, decoupled from each other:
+//   * the LEADER (warp 0) only waits for tiles to land (bar_wfull), issues the tcgen05.mma stream of each tap and
+//     commits it to bar_wfree - it never waits for a tap to retire, so the tensor core's queue stays fed;
+//   * the PRODUCER (warp 1) refills the ring: tile i is requested as soon as tile i - kNW has retired. The producer
+//     of job j requests tiles 9j + kWAhead .. 9j + kWAhead + 8 (the first kWAhead tiles of the next job included),
+//     so nothing but the job index travels between the slots.
+// Both run with warp-uniform arguments (descriptors live in uniform registers); the asynchronous instructions
+// themselves are issued by one elected lane.
+#ifndef NODE_KWAHEAD
+#define NODE_KWAHEAD 3
+#endif
+constexpr uint32_t kWAhead = NODE_KWAHEAD;      // tiles requested before a job's first tap is issued
+
+template <int NSLOT>
+__device__ __forceinline__ void request_tile(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, uint32_t i) {
+  const uint32_t slot = i % kNW, cv = jb.conv_of(i / 9, NSLOT), tp = i % 9;
+  ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
+  ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                sm.bar_wfull + 8 * slot);
+}
+
 template <class T, int NSLOT>
-__device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, uint32_t tmem,
-                                               int s, uint32_t job, uint32_t nth, bool split, bool& timeout) {
+__device__ __forceinline__ void produce_conv_job(const StepSmem& sm, const Jobs& jb, const uint16_t* __restrict__ w16, int s, uint32_t job,
+                                                 uint32_t nth, bool& timeout) {
+  const bool lead = ptx::elect_one();
+  // the turn also tells that every tap of the previous job has been issued, hence (bar_wfull gating) that the
+  // barrier phases this job waits on cannot alias older ones
+  if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;
+  const uint32_t total = jb.jobs * 9;
+#pragma unroll 1
+  for (uint32_t i = job * 9 + kWAhead; i < job * 9 + kWAhead + 9 && i < total; ++i) {
+    const uint32_t slot = i % kNW;
+    if (i >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((i / kNW) - 1) & 1)) timeout = true;
+    if (lead) request_tile<NSLOT>(sm, jb, w16, i);
+  }
+  __syncwarp();
+}
+
+template <class T, int NSLOT>
+__device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, uint32_t tmem, int s, uint32_t job, uint32_t nth,
+                                               bool split, bool& timeout) {
   const bool lead = ptx::elect_one();
   if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;   // my slot's nth turn
 #ifdef NODE_STEP_DEBUG
   if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg[(s * 256 + nth) * 4 + 1] = clock64();
 #endif
-  uint32_t issued = __shfl_sync(0xffffffffu, sm.ring[0], 0), tapx = __shfl_sync(0xffffffffu, sm.ring[1], 0);
-  const uint32_t total = jb.jobs * 9;
   ptx::tc_fence_after();
   const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
-    while (issued < total && issued <= tapx + (kNW - kWGap)) {
-      const uint32_t slot = issued % kNW;
-#ifdef NODE_STEP_DEBUG
-      const long long q0 = clock64();
-#endif
-      if (issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((issued / kNW) - 1) & 1)) timeout = true;
-#ifdef NODE_STEP_DEBUG
-      if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 1] += clock64() - q0;
-#endif
-      const uint32_t cv = jb.conv_of(issued / 9, NSLOT), tp = issued % 9;
-      if (lead) {
-        ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
-        ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tp) * kW16TileBytes, kW16TileBytes,
-                      sm.bar_wfull + 8 * slot);
-      }
-      ++issued;
-    }
-    const uint32_t slot = tapx % kNW;
+    const uint32_t tile = job * 9 + tap, slot = tile % kNW;
 #ifdef NODE_STEP_DEBUG
     const long long q1 = clock64();
 #endif
-    if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tapx / kNW) & 1)) timeout = true;
+    if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tile / kNW) & 1)) timeout = true;
 #ifdef NODE_STEP_DEBUG
     if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg2[(s * 256 + nth) * 2 + 0] += clock64() - q1;
 #endif
     ptx::tc_fence_after();
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
     const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+#ifdef NODE_STEP_DEBUG
+    const long long q2 = clock64();
+#endif
     if (lead) {
 #pragma unroll
       for (int mt = 0; mt < T::MT; ++mt) {
@@ -463,12 +489,13 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
       }
       ptx::tc_commit(sm.bar_wfree + 8 * slot);
     }
-    ++tapx;
+#ifdef NODE_STEP_DEBUG
+    if (lead && blockIdx.x == 0) g_step_phase[s * 16 + 13] += clock64() - q2;
+#endif
   }
   if (lead) {
     ptx::tc_commit(sm.bar_acc + 8 * s);
-    sm.ring[0] = issued; sm.ring[1] = tapx;
-    if (job + 1 < jb.jobs) ptx::mbar_arrive(sm.bar_turn + 8 * jb.slot_of(job + 1, NSLOT));   // release: ring counters travel with it
+    if (job + 1 < jb.jobs) ptx::mbar_arrive(sm.bar_turn + 8 * jb.slot_of(job + 1, NSLOT));
   }
   __syncwarp();
 }
@@ -485,9 +512,13 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
   const bool rec = blockIdx.x == 0 && me.wt == 0 && njob < 256;
   if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 0] = clock64();
 #endif
-  if (__shfl_sync(0xffffffffu, me.warp, 0) == 0)     // shuffles: tell the compiler these values are warp-uniform
-    issue_conv_job<T, NSLOT>(sm, jb, w16, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, me.slot, 0),
+  const int wu = __shfl_sync(0xffffffffu, me.warp, 0);     // shuffles: tell the compiler these values are warp-uniform
+  if (wu == 0)
+    issue_conv_job<T, NSLOT>(sm, jb, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, me.slot, 0),
                              __shfl_sync(0xffffffffu, job, 0), __shfl_sync(0xffffffffu, njob, 0), split, timeout);
+  else if (wu == 1)
+    produce_conv_job<T, NSLOT>(sm, jb, w16, __shfl_sync(0xffffffffu, me.slot, 0), __shfl_sync(0xffffffffu, job, 0),
+                               __shfl_sync(0xffffffffu, njob, 0), timeout);
 #ifdef NODE_STEP_DEBUG
   if (rec) g_step_dbg[(me.slot * 256 + njob) * 4 + 2] = clock64();
 #endif
@@ -626,7 +657,6 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
   if (tid == 0) {
     for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_turn + 8 * i, 1); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
-    sm.ring[0] = 0; sm.ring[1] = 0;
     ptx::fence_mbar_init();
     ptx::mbar_arrive(sm.bar_turn);          // the first conv job belongs to slot 0
   }
@@ -658,6 +688,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     jb.jobs_full = nfull * NSLOT;
     jb.jobs = (uint32_t)(nst[0] + (NSLOT > 1 ? nst[1] : 0)) * nevals * 2;
   }
+  if (tid == 0)                     // the first tiles of the weight sequence; every later one is requested by a producer warp
+    for (uint32_t i = 0; i < kWAhead && i < jb.jobs * 9; ++i) request_tile<NSLOT>(sm, jb, w.w16, i);
 
   {
     // ===== every thread is a worker: one position of its slot's strip =====
@@ -678,6 +710,10 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
     uint32_t njob = 0;
     const int u0 = blockIdx.x * NSLOT + me.slot;
+#ifdef NODE_STEP_DEBUG
+    const bool rec_ph = blockIdx.x == 0 && me.wt == 32 && a.mode == MODE_STEP;
+    long long last_ph = clock64();
+#endif
 
 #pragma unroll 1
     for (int st = u0; st < NST; st += stride) {
@@ -691,6 +727,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
         const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
         const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
         make_tb<T>(sm, me, w, t);
+        NODE_STAMP(0);
 
         // ---- stage input (rk_common.py:49-51) -> GN1 -> ReLU -> A image of conv1
 #pragma unroll 1
@@ -700,16 +737,17 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
           const float* const Fcur = w.F[cur];
           if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float v = 0.f;
-              if (valid) {
-                v = a.y_in[p0 + (size_t)c * HW];
-                if (a.mode == MODE_F0) {
-                  Ycur[p0 + (size_t)c * HW] = v;
-                  if (a.out0 != nullptr) a.out0[p0 + (size_t)c * HW] = v;
-                }
+            for (int c = 0; c < 32; ++c) x[c] = ptx::ldg_ordered(a.y_in + p0 + (size_t)c * HW);   // all 32 loads in flight
+            if (a.mode == MODE_F0 && valid) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                Ycur[p0 + (size_t)c * HW] = x[c];
+                if (a.out0 != nullptr) a.out0[p0 + (size_t)c * HW] = x[c];
               }
-              x[c] = v;
+            }
+            if (!valid) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) x[c] = 0.f;
             }
           } else {
             // sources in reference order k1, k2, ... with the zero coefficient beta_62 dropped
@@ -745,25 +783,35 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
               stage_in<HW, 5>(x, Ycur, src, hc, ynew, p0, valid);
             }
           }
+          NODE_STAMP(1);
           gn_affine<T>(sm, me, hb, 0, x, valid, a.eps);
+          NODE_STAMP(2);
           affine_to_A<T>(sm, me, hb, x, w.scal[0], valid, split);
+          NODE_STAMP(3);
         }
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+        NODE_STAMP(4);
 
         // ---- conv1 epilogue -> GN2 -> ReLU -> A image of conv2 (model.py:343-346)
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
           conv_read<T>(sm, me, hb, x, tmem, 0, w.scal[4], split, valid);
+          NODE_STAMP(5);
           gn_affine<T>(sm, me, hb, 1, x, valid, a.eps);
+          NODE_STAMP(6);
           affine_to_A<T>(sm, me, hb, x, w.scal[1], valid, split);
+          NODE_STAMP(7);
         }
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+        NODE_STAMP(8);
 
         // ---- conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
           conv_read<T>(sm, me, hb, x, tmem, 1, w.scal[5], split, valid);
+          NODE_STAMP(9);
           gn_affine<T>(sm, me, hb, 2, x, valid, a.eps);
+          NODE_STAMP(10);
           {
             const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
 #pragma unroll
@@ -780,6 +828,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
 #pragma unroll
             for (int c = 0; c < 32; ++c) kdst[p0 + (size_t)c * HW] = x[c];
           }
+          NODE_STAMP(11);
           if (a.mode == MODE_F0) {               // misc.py:121-126
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
@@ -845,6 +894,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
               __syncwarp(__activemask());   // padding lanes are not here
             }
             acc0 += (double)part;
+            NODE_STAMP(12);
           }
         }
       }
@@ -904,6 +954,11 @@ static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
 #if defined(NODE_STEP_DEBUG) && defined(NODE_STEP_DEBUG_EXPORT)
 extern "C" int node_b200_step_debug_read(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, node::g_step_dbg, sizeof(long long) * (n < 2048 ? n : 2048));
+}
+extern "C" int node_b200_step_phase_read(long long* host, int clear) {
+  int rc = (int)cudaMemcpyFromSymbol(host, node::g_step_phase, sizeof(long long) * 32);
+  if (clear) { static long long z[32]; rc |= (int)cudaMemcpyToSymbol(node::g_step_phase, z, sizeof(z)); }
+  return rc;
 }
 extern "C" int node_b200_step_debug_read2(long long* host, int n, int clear) {
   int rc = (int)cudaMemcpyFromSymbol(host, node::g_step_dbg2, sizeof(long long) * (n < 1024 ? n : 1024));

@@ -20,6 +20,9 @@ with torch.no_grad():
         net.odeblock(h0)
     torch.cuda.synchronize()
     lib.node_b200_step_debug_read2(buf2, 1024, 1)
+    ph = (ctypes.c_longlong * 32)()
+    lib.node_b200_step_phase_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.node_b200_step_phase_read(ph, 1)
     solver._step_guess.clear()
     net.odeblock(h0)
     torch.cuda.synchronize()
@@ -41,3 +44,15 @@ for s in range(2):
         np.median(turn), np.median(issue), np.median(acc), np.median(d[:, 3] - d[:, 0]), np.median(d[1:, 0] - d[:-1, 3])))
     for j in range(min(n, 14)):
         print('  job %3d  pub %8d turn %8d issued %8d acc %8d' % (j, d[j, 0], d[j, 1], d[j, 2], d[j, 3]))
+
+lib.node_b200_step_phase_read(ph, 0)
+names = ['make_tb', 'stage_in', 'gn1', 'apply1', 'wait conv1', 'read c1', 'gn2', 'apply2', 'wait conv2', 'read c2', 'gn3', 'affine+k store',
+         'error norm']
+st = solver.last_stats
+nst = st['n_accept'] + st['n_reject']
+for s_ in range(2):
+    v = np.array(ph[s_ * 16:s_ * 16 + 13], dtype=np.float64)
+    print('   leader clocks inside the MMA issue blocks per step launch: %.0f' % (ph[s_ * 16 + 13] / nst))
+    print('slot', s_, 'thread 32 of CTA 0, clocks per step launch (%d launches), total %.0f' % (nst, v.sum() / nst))
+    for n_, x_ in zip(names, v):
+        print('   %-16s %9.0f  %5.1f%%' % (n_, x_ / nst, 100 * x_ / v.sum()))
