@@ -571,12 +571,14 @@ __device__ __forceinline__ void stage_in(float (&x)[32], const float* __restrict
                                          const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid) {
   using A = Arith<float>;
   // Padding threads read image 0's data (p0 = their pixel offset only) and discard it: no divergent loads.
-  // Software pipeline over batches of 4 channels: the loads of batch b+1 are in flight while batch b is
+  // Software pipeline over batches of B channels: the loads of batch b+1 are in flight while batch b is
   // combined; the warp-level fences stop the assembler from hoisting every load to the top (register budget).
-  float yv[2][4], kv[2][NK][4];
+  // B is sized so that about 48 values per thread are in flight whatever the number of sources.
+  constexpr int B = NK <= 2 ? 8 : 4;
+  float yv[2][B], kv[2][NK][B];
   auto load = [&](int b, int c0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < B; ++i) {
       yv[b][i] = ptx::ldg_ordered(y + p0 + (size_t)(c0 + i) * HW);
 #pragma unroll
       for (int j = 0; j < NK; ++j) kv[b][j][i] = ptx::ldg_ordered(src[j] + p0 + (size_t)(c0 + i) * HW);
@@ -584,12 +586,12 @@ __device__ __forceinline__ void stage_in(float (&x)[32], const float* __restrict
   };
   load(0, 0);
 #pragma unroll
-  for (int c0 = 0; c0 < 32; c0 += 4) {
-    const int b = (c0 >> 2) & 1;
-    if (c0 + 4 < 32) load(b ^ 1, c0 + 4);
+  for (int c0 = 0; c0 < 32; c0 += B) {
+    const int b = (c0 / B) & 1;
+    if (c0 + B < 32) load(b ^ 1, c0 + B);
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < B; ++i) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < NK; ++j) s = A::add(s, A::mul(hc[j], kv[b][j][i]));
