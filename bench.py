@@ -346,7 +346,7 @@ def main():
                 flops_per_launch=flops_per_launch, launch_ms=k_avg * 1e3, launches_timed=len(k_ms),
                 share_of_step=sum(k_ms) * 1e-3 / t_res,
                 peak_note='TF32 dense peak taken as 1/2 of %s sustained bf16 (%s); algorithmic FLOPs counted once although '
-                          '3xTF32 issues 3 MMAs' % (pk['bf16_sus'], pk['src']))
+                          'the fp16 operand split issues 3 products' % (pk['bf16_sus'], pk['src']))
     line = dict(metric='CIFAR-10 ODENet dopri5 forward throughput', value=value, unit='images/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * t_res / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=workload_config(args),

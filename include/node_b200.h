@@ -203,6 +203,14 @@ int node_b200_wgrad(void* vjp_workspace, const float* r1, const float* gc1, cons
  * [splits][2][9][64][80]). */
 void* node_b200_vjp_buffer(void* vjp_workspace, int which, int N, int C, int H, int W);
 
+/* Callers of the hot path: y = relu?(GroupNorm(x)) for a contiguous NCHW fp32 tensor [N, C, HW] with
+ * `groups` groups - replaces nn.GroupNorm (model.py:268-271) followed by nn.ReLU in the downsamplers
+ * (model.py:119-178) and the classifier head (model.py:231-250) by one pass (1 read + 1 write). Two-pass mean /
+ * biased variance like native_group_norm. Returns cudaErrorInvalidValue for cells larger than 4096 floats
+ * (the caller then keeps its own GroupNorm). x == y (in place) is allowed. */
+int node_b200_groupnorm_relu(const float* x, float* y, const float* gamma, const float* beta, int64_t N, int C,
+                             int groups, int HW, float eps, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,12 +8,15 @@ random initial weights (modules are created in the same order).
 
 The only compute that matters here is ODEBlock.forward -> odeint / odeint_adjoint, which is
 served by the B200 kernels behind `torchdiffeq` (this repo's drop-in package).  Downsamplers
-and the classifier run once per batch and stay plain PyTorch.
+and the classifier run once per batch: their convolutions / pooling / linear stay plain PyTorch
+(SURVEY 2, row 9); their GroupNorm -> ReLU pairs run as one CUDA pass when no gradient is needed
+(node_b200/caller_ops.py).
 """
 import torch
 import torch.nn as nn
 
 from .solver import odeint, odeint_adjoint
+from .caller_ops import group_norm_relu, run_sequential
 
 
 def _norm_factory(kind='group'):
@@ -127,10 +130,11 @@ class ResBlock(nn.Module):
         self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
 
     def forward(self, x):
-        out = self.relu(self.norm1(x))
+        out = group_norm_relu(self.norm1, x) if isinstance(self.norm1, nn.GroupNorm) else self.relu(self.norm1(x))
         shortcut = x if self.downsample is None else self.downsample(out)
-        out = self.conv2(self.relu(self.norm2(self.conv1(out))))
-        return out + shortcut
+        out = self.conv1(out)
+        out = group_norm_relu(self.norm2, out) if isinstance(self.norm2, nn.GroupNorm) else self.relu(self.norm2(out))
+        return self.conv2(out) + shortcut
 
 
 def _conv1x1(cin, cout, stride):
@@ -139,6 +143,8 @@ def _conv1x1(cin, cout, stride):
 
 class _Wrapped(nn.Module):
     def forward(self, *inputs):
+        if isinstance(self.module, nn.Sequential) and len(inputs) == 1:
+            return run_sequential(self.module, inputs[0])      # GroupNorm -> ReLU pairs in one pass (caller_ops)
         return self.module(*inputs)
 
 
@@ -203,12 +209,12 @@ class ODEDownsample2(nn.Module):
     def forward(self, x):
         x = self.odeblock(self.conv1(x))
         if x.dim() > 4:
-            x = torch.stack([self.norm(xi) for xi in x])
+            x = torch.stack([run_sequential(self.norm, xi) for xi in x])
             if self.apply_conv:
                 x = torch.stack([self.conv2(xi) for xi in x])
                 return x, x[-1]
             return x, self.conv2(x[-1])
-        return self.conv2(self.norm(x))
+        return self.conv2(run_sequential(self.norm, x))
 
 
 class FCClassifier(_Wrapped):

@@ -1,0 +1,55 @@
+"""GPU: the callers' GroupNorm -> ReLU pass (csrc/caller_ops.cu) against ATen's own group_norm + relu
+(the reference's model.py:268-271 / nn.ReLU), and the whole ODENet forward with and without it."""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('relu', [True, False])
+@pytest.mark.parametrize('shape,groups', [((64, 64, 30, 30), 32), ((33, 64, 15, 15), 32), ((16, 64, 8, 8), 32), ((8, 24, 13, 13), 24),
+                                          ((4, 64, 7, 7), 32), ((5, 64, 14, 14), 32), ((3, 256, 8, 8), 32), ((2, 64, 16, 16), 32)])
+def test_groupnorm_relu_matches_aten(native_lib, shape, groups, relu):
+    from node_b200 import caller_ops
+    torch.manual_seed(1)
+    norm = nn.GroupNorm(groups, shape[1]).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        x = (torch.randn(shape, device=DEV) * 2.0 + 0.7)
+        ref = norm(x)
+        ref = torch.relu(ref) if relu else ref
+        got = caller_ops.group_norm_relu(norm, x, relu=relu)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_groupnorm_relu_keeps_autograd_path(native_lib):
+    from node_b200 import caller_ops
+    norm = nn.GroupNorm(32, 64).to(DEV)
+    x = torch.randn(4, 64, 8, 8, device=DEV, requires_grad=True)
+    y = caller_ops.group_norm_relu(norm, x)          # gradients needed: the modules' own PyTorch ops
+    y.sum().backward()
+    assert x.grad is not None and norm.weight.grad is not None
+
+
+@pytest.mark.parametrize('downsample', ['residual', 'convolution', 'minimal'])
+def test_odenet_forward_same_with_fused_callers(native_lib, monkeypatch, downsample):
+    from node_b200 import models, caller_ops
+    torch.manual_seed(0)
+    net = models.ODENet(3, n_filters=64, downsample=downsample, tol=1e-3).eval().to(DEV)
+    x = torch.rand(16, 3, 32, 32, device=DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        net.nfe(reset=True)
+        fused = net(x)
+        nfe_f = net.nfe(reset=True)
+        monkeypatch.setattr(caller_ops, '_fusable', lambda norm, x: False)
+        plain = net(x)
+        nfe_p = net.nfe(reset=True)
+    assert nfe_f == nfe_p
+    assert float((fused - plain).abs().max()) <= 1e-4 * float(plain.abs().max())
+    assert torch.equal(fused.argmax(1), plain.argmax(1))
