@@ -143,7 +143,7 @@ def workload_config(args, sample_note=None):
     c = dict(workload='cfg2: CIFAR-10 ODENet(3, n_filters=64, downsample=residual, tol=1e-3).eval() forward, '
                       'synthetic 32x32 batches', per_gpu_batch=args.batch, global_batch=args.batch * args.gpus,
              solver='dopri5 rtol=atol=1e-3', conv_mode=os.environ.get('NODE_B200_CONV', 'f16x3'),
-             downsample_classifier='plain PyTorch fp32 (cudnn.allow_tf32=False)', parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
+             downsample_classifier='cuDNN fp32 convolutions (cudnn.allow_tf32=False) + one-pass CUDA GroupNorm->ReLU (csrc/caller_ops.cu)', parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
              l2='inputs larger than L2 (state %d MB per tensor, ~10 live tensors)' % (args.batch * 64 * 64 * 4 // 2 ** 20))
     if sample_note:
         c['sample'] = sample_note
