@@ -229,6 +229,29 @@ def train_step_rate(dev, batch, steps, warmup):
                      'downsampler / classifier autograd in PyTorch fp32')
 
 
+def small_batch_latency(net, dev, batch=128, reps=30):
+    """ODE block at the reference's default batch (train.py:207), where a solve is bound by its ~35 launches:
+    direct enqueue against CUDA-graph replay of the same launch sequence (north_star 3)."""
+    from node_b200 import solver
+    out = dict(batch=batch)
+    with torch.no_grad():
+        h0 = net.downsample(torch.rand(batch, 3, 32, 32, device=dev))
+        for mode in ('0', '1'):
+            os.environ['NODE_B200_GRAPH'] = mode
+            for _ in range(3):
+                net.odeblock(h0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                net.odeblock(h0)
+            torch.cuda.synchronize()
+            out['direct_ms' if mode == '0' else 'graph_ms'] = 1e3 * (time.perf_counter() - t0) / reps
+    os.environ.pop('NODE_B200_GRAPH', None)
+    out['launches_per_solve'] = solver.last_stats.get('launches')
+    out['note'] = 'wall clock per ODE-block forward incl. the one status read-back per solve'
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -357,6 +380,7 @@ def main():
                               n_accept=stats.get('n_accept'), n_reject=stats.get('n_reject')))
     if world == 1:
         line['roofline_rk'] = rk_roofline(dev, pk)
+        line['latency_b128'] = small_batch_latency(net, dev)
         if args.train_batch > 0:
             line['train_step'] = train_step_rate(dev, args.train_batch, max(2, args.steps // 2), 2)
         if not args.skip_cpu:

@@ -734,6 +734,12 @@ extern "C" node_ctl_t* node_b200_fused_ctl(void* workspace) {
   FusedWs w; ws_layout(workspace, 1, kC, 1, 4, &w); return w.ctl;
 }
 
+constexpr int kTimesByValue = 32;
+struct TimesArg { double t[kTimesByValue]; };
+__global__ void k_set_times(double* t_out, TimesArg ta, int T) {
+  if (threadIdx.x < T) t_out[threadIdx.x] = ta.t[threadIdx.x];
+}
+
 // phases: 0 = f0 (+INIT_A norms), 1 = INIT_A controller + probe (+INIT_B norms), 2 = INIT_B controller,
 //         3 = step kernel (+error norm), 4 = STEP controller + dense output.
 extern "C" int node_b200_fused_phase(void* workspace, int phase, const float* y0, const double* t_host, int T, double rtol,
@@ -751,7 +757,14 @@ extern "C" int node_b200_fused_phase(void* workspace, int phase, const float* y0
       const int64_t ne[1] = {global_numel};
       const double rt[1] = {rtol}, at[1] = {atol};
       NODE_CUDA_OK((cudaError_t)node_b200_ctl_init(a.w.ctl, NODE_F32, 1, rt, at, ne, (double)0.9f, 10.0, (double)0.2f, (double)0.2f, 2147483647, T, 1, stream));
-      NODE_CUDA_OK(cudaMemcpyAsync(a.w.t_out, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+      if (T <= kTimesByValue) {        // by value: the launch sequence stays capturable in a CUDA graph
+        TimesArg ta;
+        for (int i = 0; i < kTimesByValue; ++i) ta.t[i] = i < T ? t_host[i] : 0.0;
+        k_set_times<<<1, 32, 0, st>>>(a.w.t_out, ta, T);
+        NODE_CUDA_OK(cudaGetLastError());
+      } else {
+        NODE_CUDA_OK(cudaMemcpyAsync(a.w.t_out, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, st));
+      }
       NODE_CUDA_OK(cudaMemsetAsync(a.w.partials, 0, sizeof(double) * 2 * NODE_MAX_SEG * kPartialBlocksF, st));
       NODE_CUDA_OK(cudaMemsetAsync(a.w.nonfinite, 0, sizeof(int), st));
       a.mode = MODE_F0; a.y_in = y0; a.out0 = out; a.t_explicit = (float)t_host[0];

@@ -402,9 +402,14 @@ __global__ void __launch_bounds__(kThreads) k_interp(const node_ctl_t* __restric
   }
 }
 
+// Per-member tolerances and element counts travel as kernel arguments (by value): nothing is read from host memory
+// after the call returns, so the launch sequence of a solve can be captured in a CUDA graph and replayed.
+struct CtlSegs { double rtol[NODE_MAX_SEG], atol[NODE_MAX_SEG]; int64_t numel[NODE_MAX_SEG]; };
+
 __global__ void k_ctl_init(node_ctl_t* c, int dtype, int n_seg, double safety, double ifactor, double dfactor, double expo,
-                           int max_num_steps, int n_out, int tsign) {
+                           int max_num_steps, int n_out, int tsign, CtlSegs segs) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < NODE_MAX_SEG; ++i) { c->rtol[i] = segs.rtol[i]; c->atol[i] = segs.atol[i]; c->seg_numel[i] = segs.numel[i]; }
   c->dtype = dtype; c->n_seg = n_seg; c->safety = safety; c->ifactor = ifactor; c->dfactor = dfactor; c->expo = expo;
   c->max_num_steps = max_num_steps; c->n_out = n_out; c->tsign = tsign; c->next_out = 1;
 }
@@ -452,16 +457,11 @@ extern "C" int node_b200_ctl_init(node_ctl_t* ctl, int dtype, int n_seg, const d
   if (n_seg < 1 || n_seg > NODE_MAX_SEG) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   NODE_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(node_ctl_t), st));
-  // small host->device parameter copies: stage them through a pageable struct copy (async wrt device work
-  // already queued; the source is consumed before return for pageable memory)
-  double tmp[2 * NODE_MAX_SEG];
-  for (int i = 0; i < NODE_MAX_SEG; ++i) { tmp[i] = i < n_seg ? rtol[i] : 0.0; tmp[NODE_MAX_SEG + i] = i < n_seg ? atol[i] : 0.0; }
-  NODE_CUDA_OK(cudaMemcpyAsync(ctl->rtol, tmp, sizeof(double) * NODE_MAX_SEG, cudaMemcpyHostToDevice, st));
-  NODE_CUDA_OK(cudaMemcpyAsync(ctl->atol, tmp + NODE_MAX_SEG, sizeof(double) * NODE_MAX_SEG, cudaMemcpyHostToDevice, st));
-  int64_t ne[NODE_MAX_SEG];
-  for (int i = 0; i < NODE_MAX_SEG; ++i) ne[i] = i < n_seg ? seg_numel[i] : 0;
-  NODE_CUDA_OK(cudaMemcpyAsync(ctl->seg_numel, ne, sizeof(ne), cudaMemcpyHostToDevice, st));
-  k_ctl_init<<<1, 32, 0, st>>>(ctl, dtype, n_seg, safety, ifactor, dfactor, expo, max_num_steps, n_out, tsign);
+  CtlSegs segs;
+  for (int i = 0; i < NODE_MAX_SEG; ++i) {
+    segs.rtol[i] = i < n_seg ? rtol[i] : 0.0; segs.atol[i] = i < n_seg ? atol[i] : 0.0; segs.numel[i] = i < n_seg ? seg_numel[i] : 0;
+  }
+  k_ctl_init<<<1, 32, 0, st>>>(ctl, dtype, n_seg, safety, ifactor, dfactor, expo, max_num_steps, n_out, tsign, segs);
   return (int)cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ PROFILE_STEP_EVENTS = None
 _t_cache = {}
 _ws_cache = {}
 _step_guess = {}
+_warned_grad_bridge = False
 
 
 def _conv_mode():
@@ -285,17 +286,36 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     ws.param_key_fresh = False
     events = PROFILE_STEP_EVENTS
     if group is None and events is None:
-        guess = _step_guess.get(id(_unwrap(func)), 8)
+        guess = _step_guess.get(id(_unwrap(func)))
+        graph = None
+        if guess is not None and _graph_wanted(N, T):
+            # Launch-bound sizes: the whole enqueue sequence (f0, probe, `guess` attempted steps with their controllers
+            # and dense output) is captured ONCE per (shape, times, tolerances, step count) and replayed.
+            graph = _fused_graph(ws, y, th, t_host, common, E, conv_mode, int(tsign), guess)
         first = 1
-        while True:
-            err = lib.node_b200_fused_solve(native.ptr(ws.buf), native.ptr(y), *common, E, native.ptr(out), conv_mode,
+        if graph is not None:
+            graph.y.copy_(y)
+            graph.graph.replay()
+            src_y, dst_out = graph.y, graph.out
+            launches += 4 * guess
+            view = native.CtlView(ws.ctl)
+            first = 0 if view.i32('done') else -1
+        else:
+            src_y, dst_out = y, out
+            guess = 8 if guess is None else guess
+        while first != 0:
+            if first == -1:
+                first, guess = 0, 4
+            err = lib.node_b200_fused_solve(native.ptr(ws.buf), native.ptr(src_y), *common, E, native.ptr(dst_out), conv_mode,
                                             int(tsign), first, guess, native.stream_ptr())
             native.check(err, 'fused_solve')
             launches += 4 * guess
             view = native.CtlView(ws.ctl)
             if view.i32('done'):
                 break
-            first, guess = 0, 4
+            first = -1
+        if graph is not None:
+            out.copy_(graph.out)
     else:
         sharded = group is not None
         E_glob = dist_state.global_numel(E, y.device) if sharded else E
@@ -340,6 +360,47 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
                       status=view.i32('status'), trace=view.trace(), launches=launches)
     native.raise_for_status(view.i32('status'))
     return out
+
+
+# ---- CUDA-graph replay of the fused solve -------------------------------------------------------
+
+_graph_cache = {}
+_graph_failed = set()
+
+
+def _graph_wanted(N, T):
+    mode = os.environ.get('NODE_B200_GRAPH', 'auto')
+    if mode == '0' or T > 32:
+        return False
+    return mode == '1' or N <= 512          # auto: sizes at which a solve is bound by its ~35 launches
+
+
+class _FusedGraph(object):
+    def __init__(self, y, T):
+        self.y = torch.empty_like(y)
+        self.out = torch.empty((T,) + tuple(y.shape), dtype=y.dtype, device=y.device)
+        self.graph = torch.cuda.CUDAGraph()
+
+
+def _fused_graph(ws, y, th, t_host, common, E, conv_mode, tsign, guess):
+    key = (ws.buf.data_ptr(), tuple(float(v) for v in t_host), common[2], common[3], conv_mode, tsign, guess)
+    g = _graph_cache.get(key)
+    if g is not None or key in _graph_failed:
+        return g
+    if len(_graph_cache) >= 16:
+        _graph_cache.clear()
+    g = _FusedGraph(y, len(t_host))
+    try:
+        with torch.cuda.graph(g.graph):
+            err = native.lib().node_b200_fused_solve(native.ptr(ws.buf), native.ptr(g.y), *common, E, native.ptr(g.out),
+                                                    conv_mode, tsign, 1, guess, native.stream_ptr())
+        native.check(err, 'fused_solve (graph capture)')
+    except Exception as exc:                      # same kernels without the graph; say so once per configuration
+        _graph_failed.add(key)
+        warnings.warn('node_b200: CUDA-graph capture of the fused solve failed (%s); launching directly' % exc)
+        return None
+    _graph_cache[key] = g
+    return g
 
 
 # ---- generic route -------------------------------------------------------------------------------
@@ -548,9 +609,19 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
     if method != 'dopri5':
         raise NotImplementedError("node_b200 implements method='dopri5' only (got %r)" % method)
     if _needs_grad(func, y0, t):
-        raise NotImplementedError(
-            'node_b200.odeint does not record an autograd graph through the solver; call it under '
-            'torch.no_grad(), or use odeint_adjoint (ODENet(adjoint=True)) for gradients.')
+        # The reference unrolls autograd through every solver op (train.py without --adjoint, model.py:359). Here the
+        # solver runs in CUDA kernels that record no graph: gradients come from the adjoint ODE instead - the two
+        # agree to the solver tolerance (the reference's own gradient_tests.py:98-116 checks exactly that).
+        if not isinstance(func, nn.Module):
+            raise NotImplementedError(
+                'node_b200.odeint records no autograd graph through the solver and odeint_adjoint needs an nn.Module; '
+                'wrap the dynamics in an nn.Module or call under torch.no_grad().')
+        global _warned_grad_bridge
+        if not _warned_grad_bridge:
+            warnings.warn('node_b200.odeint: gradients requested through the non-adjoint entry point - served by the '
+                          'adjoint ODE (odeint_adjoint) at the same rtol/atol')
+            _warned_grad_bridge = True
+        return odeint_adjoint(func, y0[0] if tensor_input else y0, t, rtol=rtol, atol=atol, method=method, options=options or None)
     if tensor_input:
         user = func
         if isinstance(user, nn.Module):

@@ -175,3 +175,48 @@ def test_adjoint_gradients_match_reference(native_lib, golden):
     rp = torch.from_numpy(g['grad_params'])
     assert float((flat - rp).norm() / rp.norm()) < 2e-2
     assert rel(flat, rp) < 5e-2
+
+
+def test_training_without_adjoint_flag_gets_adjoint_gradients(native_lib):
+    """train.py's default (no --adjoint, model.py:359) asks odeint itself for gradients: served by the adjoint ODE."""
+    import warnings
+    from node_b200 import models
+    grads = {}
+    for adjoint in (False, True):
+        torch.manual_seed(0)
+        net = models.ODENet(3, n_filters=64, downsample='residual', tol=1e-3, adjoint=adjoint).train().to(DEV)
+        x = torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(5)).to(DEV)
+        y = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(6)).to(DEV)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss.backward()
+        grads[adjoint] = [p.grad.clone() for p in net.parameters()]
+        assert all(g is not None and torch.isfinite(g).all() for g in grads[adjoint])
+    for a, b in zip(grads[False], grads[True]):            # same kernels; cuDNN's backward is not bit-reproducible
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-9
+
+
+def test_cuda_graph_replay_of_the_solve(native_lib, golden, monkeypatch):
+    """north_star (3): the launch sequence of a solve is captured in a CUDA graph and replayed (launch-bound sizes)."""
+    from node_b200 import odeint, solver
+    g = golden('cifar_res_n8')
+    func = load_odefunc(g, DEV)
+    h0, t, tol = torch.from_numpy(g['h0']).to(DEV), torch.from_numpy(g['t']).to(DEV), float(g['tol'])
+    h1 = h0.flip(0).contiguous() * 0.9
+    outs = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('NODE_B200_GRAPH', mode)
+        solver._step_guess.clear(); solver._graph_cache.clear()
+        with torch.no_grad():
+            a = odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')      # first call: direct (learns the step count)
+            b = odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')      # second call: replayed when mode == '1'
+            st = dict(solver.last_stats)
+            c = odeint(func, h1, t, rtol=tol, atol=tol, method='dopri5')      # same graph, new input
+        assert (len(solver._graph_cache) > 0) == (mode == '1')
+        assert torch.equal(a, b) and st['nfe'] == int(g['nfe']) and st['status'] == 0
+        assert list(st['trace']['accepted']) == list(g['tr_acc'])
+        assert rel(b.cpu(), torch.from_numpy(g['out'])) < TOL_OUT
+        assert torch.equal(c[0], h1)
+        outs[mode] = (b.clone(), c.clone())
+    assert torch.equal(outs['0'][0], outs['1'][0]) and torch.equal(outs['0'][1], outs['1'][1])
