@@ -30,7 +30,7 @@ namespace node {
 #endif
 constexpr int kNW = NODE_KNW;             // weight ring depth (taps)
 constexpr int kWGap = 2;                  // a ring slot is refilled once the tap two back has retired
-constexpr int kTbFloats = 2 * 16 * 9 * 4; // per slot: bias + t*Tmap for [conv][4-channel block][border class][4 channels]
+constexpr int kTbFloats = 16 * 9 * 4;     // per slot: bias + t*Tmap of ONE convolution, [4-channel block][border class][4 channels]
 constexpr float kGnIllCond = 16.0f;       // one-pass GroupNorm moments are redone in two passes when mean^2 > 16 var
 
 template <int H_, int W_>
@@ -53,7 +53,7 @@ struct Tile {
 
 __host__ __device__ constexpr size_t step_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
   return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
-         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 3 * 32 * 16 + (size_t)NSLOT * kTbFloats * 4 + 64 * 4 + 32 * 8 +
+         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 3 * 32 * 16 + (size_t)NSLOT * kTbFloats * 4 + 2 * 9 * 64 * 4 + 2 * 64 * 4 + 64 * 4 + 32 * 8 +
          16 * 8 + 64;
 }
 
@@ -74,7 +74,7 @@ struct StepSmem {
   float* part;           // [NSLOT][NWARP][2][32] warp partials of the GroupNorm reductions (k_vjp: [NWARP][2][16])
   float2* stat;          // [NSLOT][G][32] (mean, rstd)
   float4* aff;           // [NSLOT][G][32] (a0, a1, b0, b1): GN(x) = a*x + b for the two channels of a group (k_step)
-  float4* tb;            // [NSLOT][2][16][9] bias + t*Tmap of the evaluation the slot is working on (k_step)
+  float4* tb;            // [NSLOT][16][9] bias + t*Tmap of the convolution whose epilogue the slot runs next (k_step)
   uint32_t* illcond;     // [NSLOT] set by a fold thread when a one-pass variance is ill-conditioned (k_step)
   float4* gnp;           // [3][32] (gamma0, gamma1, beta0, beta1) per group
   float* bias;           // [2][64]
@@ -535,7 +535,7 @@ template <class T>
 __device__ __forceinline__ void conv_read(const StepSmem& sm, const Who& me, int hb, float (&x)[32], uint32_t tmem, int cv,
                                           float inv_scale, bool split, bool valid) {
   const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128 + 32 * hb);
-  const float4* tb = sm.tb + ((me.slot * 2 + cv) * 16 + 8 * hb) * 9 + me.cls;
+  const float4* tb = sm.tb + (me.slot * 16 + 8 * hb) * 9 + me.cls;
 #pragma unroll
   for (int c0 = 0; c0 < 32; c0 += 8) {
     uint32_t v0[8], v1[8];
@@ -553,14 +553,14 @@ __device__ __forceinline__ void conv_read(const StepSmem& sm, const Who& me, int
   }
 }
 
-// bias + t*Tmap of one evaluation, for both convolutions (the slot's threads; ordered by the GroupNorm barriers that
-// separate it from the conv epilogues on both sides).
+// bias + t*Tmap of convolution `cv` at time t (the slot's threads). Written before the conv job whose epilogue reads it;
+// the GroupNorm barriers after the previous epilogue separate it from that epilogue's reads.
 template <class T>
-__device__ __forceinline__ void make_tb(const StepSmem& sm, const Who& me, const FusedWs& w, float t) {
+__device__ __forceinline__ void make_tb(const StepSmem& sm, const Who& me, int cv, float t) {
   float* tb = reinterpret_cast<float*>(sm.tb) + me.slot * kTbFloats;
-  for (int i = me.wt; i < 2 * 9 * 64; i += T::P) {
-    const int c = i & 63, cls = (i >> 6) % 9, cv = i / (9 * 64);
-    tb[((cv * 16 + (c >> 2)) * 9 + cls) * 4 + (c & 3)] = fmaf(t, __ldg(w.tmapc + i), __ldg(w.bias + cv * 64 + c));
+  for (int i = me.wt; i < 9 * 64; i += T::P) {
+    const int c = i & 63, cls = i >> 6;
+    tb[((c >> 2) * 9 + cls) * 4 + (c & 3)] = fmaf(t, sm.tmapc[cv * 9 * 64 + i], sm.bias[cv * 64 + c]);
   }
 }
 
@@ -629,7 +629,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
     sm.aff = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * T::G * 32 * 16;
     sm.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
     sm.tb = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * kTbFloats * 4;
-    sm.bias = nullptr; sm.tmapc = nullptr;
+    sm.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
+    sm.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * 64 * 4;
     sm.coef = reinterpret_cast<float*>(base + o); o += 64 * 4;
     sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
@@ -649,6 +650,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
                             w.gn[(2 * n + 1) * kC + 2 * g + 1]);
   }
   if (tid < 2) sm.illcond[tid] = 0u;
+  for (int i = tid; i < 2 * 64; i += blockDim.x) sm.bias[i] = w.bias[i];
+  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.tmapc[i] = w.tmapc[i];
   const float h = a.mode == MODE_STEP ? ctl->h32 : (a.mode == MODE_PROBE ? ctl->h0_32 : 0.f);
   if (tid < 64) {   // rows 0..5 stage betas, 6 = C_MID, 7 = C_ERR (misc.py:22-25: (h*c)*k)
     const int r = tid >> 3, j = tid & 7;
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
       for (int ev = 0; ev < nevals; ++ev) {
         const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
         const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
-        make_tb<T>(sm, me, w, t);
+        make_tb<T>(sm, me, 0, t);
         NODE_STAMP(0);
 
         // ---- stage input (rk_common.py:49-51) -> GN1 -> ReLU -> A image of conv1
@@ -804,6 +807,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
           affine_to_A<T>(sm, me, hb, x, w.scal[1], valid, split);
           NODE_STAMP(7);
         }
+        make_tb<T>(sm, me, 1, t);
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
         NODE_STAMP(8);
 
@@ -935,6 +939,9 @@ static int launch_step_shape(const FusedArgs& a, cudaStream_t st) {
   k_step<H_, W_, NSLOT><<<grid, NSLOT * T::P, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
+
+static_assert(step_smem_bytes(Tile<8, 8>::A_PART, 2, Tile<8, 8>::NWARP, Tile<8, 8>::G) <= 227 * 1024,
+              "the two-slot variant of the headline shape must fit in shared memory");
 
 template <int H_, int W_>
 static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
