@@ -211,6 +211,18 @@ void* node_b200_vjp_buffer(void* vjp_workspace, int which, int N, int C, int H, 
 int node_b200_groupnorm_relu(const float* x, float* y, const float* gamma, const float* beta, int64_t N, int C,
                              int groups, int HW, float eps, int relu, void* stream);
 
+/* Callers of the hot path: the tail of the reference's ResBlock (model.py:156-178),
+ *     out = conv2(relu(norm2(x))) + shortcut,  conv2 = Conv2d(64, 64, 3, 1, 1, bias=False), norm2 = GroupNorm(32, 64),
+ * as one tcgen05 kernel (fp32 contract by fp16 operand splitting, like the ODE-Net step engine). x, shortcut, out are
+ * contiguous NCHW fp32 [N,64,H,W]; supported maps: 15x15, 8x8 (CIFAR), 13x13, 7x7 (MNIST) - workspace_bytes returns 0
+ * otherwise and the caller keeps its own ops. prepare() packs the live conv weight [64,64,3,3] and the operand scales
+ * into the workspace (once per parameter version). */
+int64_t node_b200_resconv_workspace_bytes(int C, int H, int W);
+int node_b200_resconv_prepare(void* workspace, int C, int H, int W, const float* conv_w, const float* gn_w, const float* gn_b,
+                              void* stream);
+int node_b200_resconv_forward(void* workspace, const float* x, const float* shortcut, float* out, const float* gn_w,
+                              const float* gn_b, int N, int C, int H, int W, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,172 @@
+// the tail of the reference's ResBlock (model.py:156-178),
+//     out = conv2(relu(norm2(c))) + shortcut          conv2 = Conv2d(64, 64, 3, 1, 1, bias=False), norm2 = GroupNorm(32, 64)
+// as ONE kernel on the step engine's machinery (step_engine.cuh): position strips, one thread per position with its
+// channels in registers, GroupNorm statistics by warp transpose-reductions, the activation written once as the K-major
+// A image of an SS-mode tcgen05.mma implicit GEMM in which a tap is a descriptor row offset, fp32 contract by fp16
+// operand splitting, weight tiles streamed by a producer warp. ATen runs this as GroupNorm (2 kernels) + ReLU + cuDNN
+// fp32 SIMT convolution + add: 5 launches, 4 extra passes over the tensor.
+#pragma once
+#include "step_engine.cuh"
+
+namespace node {
+
+struct ResConvArgs {
+  const uint16_t* w16;       // [9 taps][128 rows][64 halves] weight tiles (hi rows 0..63, lo rows 64..127), SW128 image
+  const float* scal;         // [0] activation scale, [1] weight scale, [2] 1 / (sa * sw)
+  const float* gamma; const float* beta;
+  const float* x; const float* shortcut; float* out;
+  int N; float eps;
+};
+
+__host__ __device__ constexpr size_t resconv_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
+  return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
+         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 32 * 16 + 16 * 8 + 64;
+}
+
+template <int H_, int W_, int NSLOT>
+__global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const ResConvArgs a) {
+  using T = Tile<H_, W_>;
+  constexpr int HW = T::HW, P = T::P;
+  extern __shared__ uint8_t smem_raw[];
+  const int tid = threadIdx.x;
+  StepSmem sm;
+  {
+    const uint32_t s0 = ptx::smem_u32(smem_raw);
+    const uint32_t al = (s0 + 1023u) & ~1023u;
+    uint8_t* base = smem_raw + (al - s0);
+    size_t o = 0;
+    sm.wring = al; o += (size_t)kNW * kW16TileBytes;
+    sm.abase = al + (uint32_t)o; o += (size_t)NSLOT * 2 * T::A_PART;
+    sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 64 * 4;
+    sm.stat = reinterpret_cast<float2*>(base + o); o += (size_t)NSLOT * T::G * 32 * 8;
+    sm.aff = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * T::G * 32 * 16;
+    sm.gnp = reinterpret_cast<float4*>(base + o); o += 32 * 16;
+    sm.tb = nullptr; sm.bias = nullptr; sm.tmapc = nullptr; sm.coef = nullptr; sm.scratch = nullptr; sm.ring = nullptr;
+    sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
+    sm.bar_turn = al + (uint32_t)o; o += 8 * 2;
+    sm.bar_acc = al + (uint32_t)o; o += 8 * 2;
+    sm.tmem_slot = reinterpret_cast<uint32_t*>(base + o); o += 8;
+    sm.illcond = reinterpret_cast<uint32_t*>(base + o);
+    uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);   // padding rows / columns stay zero
+    for (int i = tid; i < NSLOT * 2 * T::A_PART / 16; i += blockDim.x) az[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int g = tid; g < 32; g += blockDim.x)
+    sm.gnp[g] = make_float4(a.gamma[2 * g], a.gamma[2 * g + 1], a.beta[2 * g], a.beta[2 * g + 1]);
+  if (tid < 2) sm.illcond[tid] = 0u;
+  if (tid == 0) {
+    for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_turn + 8 * i, 1); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive(sm.bar_turn);
+  }
+  if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *sm.tmem_slot;
+
+  const int NST = (a.N + T::G - 1) / T::G;
+  const int stride = gridDim.x * NSLOT;
+  bool timeout = false;
+  Jobs jb;
+  uint32_t nfull;
+  {
+    int nst[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int u = blockIdx.x * NSLOT + s;
+      nst[s] = u < NST ? (NST - u + stride - 1) / stride : 0;
+    }
+    nfull = (uint32_t)nst[NSLOT - 1];
+    jb.jobs_full = nfull * NSLOT;
+    jb.jobs = (uint32_t)(nst[0] + (NSLOT > 1 ? nst[1] : 0));
+    jb.single = 1;
+  }
+  if (tid == 0)
+    for (uint32_t i = 0; i < kWAhead && i < jb.jobs * 9; ++i) request_tile<NSLOT>(sm, jb, a.w16, i);
+
+  Who me;
+  me.slot = tid / P; me.wt = tid % P; me.warp = me.wt >> 5; me.lane = tid & 31;
+  me.img_l = me.wt / T::IS;
+  {
+    const int r = me.wt % T::IS, hh = r / T::Wp, ww = r % T::Wp;
+    me.inimg = me.img_l < T::G && hh < T::H && ww < T::W;
+    me.pix = hh * T::W + ww;
+    me.cls = 4;
+    const int ia = (me.warp * 32) / T::IS, ib = (me.warp * 32 + 31) / T::IS;
+    me.straddle = ia != ib;
+    me.isB = me.img_l != ia;
+  }
+  const float sa = a.scal[0], inv = a.scal[2];
+  uint32_t njob = 0;
+#pragma unroll 1
+  for (int st = blockIdx.x * NSLOT + me.slot; st < NST; st += stride) {
+    const int img = st * T::G + me.img_l;
+    const bool valid = me.inimg && img < a.N;
+    const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+    float x[32];
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = ptx::ldg_ordered(a.x + p0 + (size_t)c * HW);   // all 32 loads in flight
+      if (!valid) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x[c] = 0.f;
+      }
+      gn_affine<T>(sm, me, hb, 0, x, valid, a.eps);
+      affine_to_A<T>(sm, me, hb, x, sa, valid, true);
+    }
+    conv_run<T, NSLOT>(sm, me, jb, a.w16, tmem, njob, nfull, timeout, true);
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      conv_read<T, false>(sm, me, hb, x, tmem, 0, inv, true, valid);
+      if (!valid) continue;
+      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      float sc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sc[c] = ptx::ldg_ordered(a.shortcut + p0 + (size_t)c * HW);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a.out[p0 + (size_t)c * HW] = x[c] + sc[c];
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) ptx::tmem_dealloc(tmem, kTmemCols);
+  (void)timeout;
+}
+
+template <int H_, int W_, int NSLOT>
+static int launch_resconv_slots(const ResConvArgs& a, cudaStream_t st) {
+  using T = Tile<H_, W_>;
+  constexpr size_t smem = resconv_smem_bytes(T::A_PART, NSLOT, T::NWARP, T::G);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool attr_set = false;
+  if (!attr_set) {
+    NODE_CUDA_OK(cudaFuncSetAttribute(k_resconv<H_, W_, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int NST = (a.N + T::G - 1) / T::G;
+  int grid = (NST + NSLOT - 1) / NSLOT;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  k_resconv<H_, W_, NSLOT><<<grid, NSLOT * T::P, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+template <int H_, int W_>
+static int launch_resconv_shape(const ResConvArgs& a, cudaStream_t st) {
+  using T = Tile<H_, W_>;
+  constexpr bool two = resconv_smem_bytes(T::A_PART, 2, T::NWARP, T::G) <= 227 * 1024 && 2 * T::MT * 128 <= 512;
+  if constexpr (two) {
+    const int NST = (a.N + T::G - 1) / T::G;
+    if (NST > kMaxGrid) return launch_resconv_slots<H_, W_, 2>(a, st);
+  }
+  return launch_resconv_slots<H_, W_, 1>(a, st);
+}
+
+}  // namespace node
+
+#define NODE_RESCONV_SHAPE_TU(H, W) \
+  namespace node { int launch_resconv_##H##x##W(const ResConvArgs& a, cudaStream_t st) { return launch_resconv_shape<H, W>(a, st); } }

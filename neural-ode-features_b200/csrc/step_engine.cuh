@@ -399,8 +399,11 @@ constexpr uint32_t kIdF16N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 
 // Global conv-job schedule of a CTA: jobs alternate between the slots while both have super-tiles left.
 struct Jobs {
   uint32_t jobs_full, jobs;     // jobs in rounds where every slot works / all jobs
+  uint32_t single = 0;          // 1: every job is convolution 0 (k_resconv); 0: a slot alternates conv1, conv2 (k_step)
   __device__ __forceinline__ int slot_of(uint32_t j, int nslot) const { return j < jobs_full ? (int)(j % nslot) : 0; }
-  __device__ __forceinline__ uint32_t conv_of(uint32_t j, int nslot) const { return j < jobs_full ? (j / nslot) & 1u : (j - jobs_full) & 1u; }
+  __device__ __forceinline__ uint32_t conv_of(uint32_t j, int nslot) const {
+    return single ? 0u : (j < jobs_full ? (j / nslot) & 1u : (j - jobs_full) & 1u);
+  }
 };
 
 // The weight tiles of a CTA form one global sequence: tile i = tap i % 9 of conv job i / 9, living in ring slot
@@ -531,17 +534,17 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
 }
 
 // x <- acc/scale + (bias + t*Tmap) for output channels [32*hb, 32*hb+32) of this thread's position.
-template <class T>
+template <class T, bool TB = true>
 __device__ __forceinline__ void conv_read(const StepSmem& sm, const Who& me, int hb, float (&x)[32], uint32_t tmem, int cv,
                                           float inv_scale, bool split, bool valid) {
   const uint32_t taddr = tmem + ((uint32_t)((me.warp & 3) * 32) << 16) + (uint32_t)((me.slot * T::MT + (me.wt >> 7)) * 128 + 32 * hb);
-  const float4* tb = sm.tb + (me.slot * 16 + 8 * hb) * 9 + me.cls;
+  const float4* tb = TB ? sm.tb + (me.slot * 16 + 8 * hb) * 9 + me.cls : nullptr;
 #pragma unroll
   for (int c0 = 0; c0 < 32; c0 += 8) {
     uint32_t v0[8], v1[8];
     ptx::tmem_ld8(taddr + c0, v0);
     if (split) ptx::tmem_ld8(taddr + 64 + c0, v1);
-    const float4 e0 = tb[(c0 >> 2) * 9], e1 = tb[((c0 >> 2) + 1) * 9];
+    const float4 e0 = TB ? tb[(c0 >> 2) * 9] : make_float4(0.f, 0.f, 0.f, 0.f), e1 = TB ? tb[((c0 >> 2) + 1) * 9] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float ex[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     ptx::tc_wait_ld();
 #pragma unroll

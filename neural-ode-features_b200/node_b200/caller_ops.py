@@ -54,3 +54,48 @@ def run_sequential(seq, x):
             x = m(x)
         i += 1
     return x
+
+
+# ---- fused ResBlock tail: conv2(relu(norm2(x))) + shortcut (csrc/resconv_engine.cuh) ---------------------------------
+
+_resconv_ws = {}
+
+
+def _resconv_ok(norm, conv, x, shortcut):
+    if not (isinstance(norm, nn.GroupNorm) and isinstance(conv, nn.Conv2d)) or norm.weight is None:
+        return False
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and shortcut.shape == x.shape and shortcut.dtype == x.dtype):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or shortcut.requires_grad or conv.weight.requires_grad or norm.weight.requires_grad):
+        return False
+    if (conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups) != \
+            (64, 64, (3, 3), (1, 1), (1, 1), (1, 1), 1) or conv.bias is not None or conv.padding_mode != 'zeros':
+        return False
+    if norm.num_groups != 32 or norm.num_channels != 64 or x.shape[1] != 64:
+        return False
+    return native.lib().node_b200_resconv_workspace_bytes(64, int(x.shape[2]), int(x.shape[3])) > 0
+
+
+def res_conv(norm, conv, x, shortcut):
+    """conv(relu(norm(x))) + shortcut for the ResBlock tail; one tcgen05 kernel when the shape is served and no gradient
+    is needed, the modules' own ops otherwise."""
+    if not _resconv_ok(norm, conv, x, shortcut):
+        return conv(torch.relu(norm(x))) + shortcut
+    x, shortcut = x.contiguous(), shortcut.contiguous()
+    N, C, H, W = (int(v) for v in x.shape)
+    lib = native.lib()
+    key = (id(conv), id(norm), str(x.device), H, W)
+    ent = _resconv_ws.get(key)
+    ver = (conv.weight.data_ptr(), conv.weight._version, norm.weight.data_ptr(), norm.weight._version, norm.bias._version)
+    if ent is None or ent[1] != ver:
+        if len(_resconv_ws) > 32:
+            _resconv_ws.clear()
+        buf = ent[0] if ent is not None else torch.zeros(lib.node_b200_resconv_workspace_bytes(C, H, W), dtype=torch.uint8, device=x.device)
+        native.check(lib.node_b200_resconv_prepare(native.ptr(buf), C, H, W, native.ptr(conv.weight), native.ptr(norm.weight),
+                                                   native.ptr(norm.bias), native.stream_ptr()), 'resconv_prepare')
+        ent = _resconv_ws[key] = (buf, ver)
+    out = torch.empty_like(x)
+    native.check(lib.node_b200_resconv_forward(native.ptr(ent[0]), native.ptr(x), native.ptr(shortcut), native.ptr(out),
+                                               native.ptr(norm.weight), native.ptr(norm.bias), N, C, H, W, float(norm.eps),
+                                               native.stream_ptr()), 'resconv_forward')
+    return out

@@ -53,3 +53,27 @@ def test_odenet_forward_same_with_fused_callers(native_lib, monkeypatch, downsam
     assert nfe_f == nfe_p
     assert float((fused - plain).abs().max()) <= 1e-4 * float(plain.abs().max())
     assert torch.equal(fused.argmax(1), plain.argmax(1))
+
+
+@pytest.mark.parametrize('shape', [(37, 64, 15, 15), (16, 64, 8, 8), (9, 64, 13, 13), (11, 64, 7, 7), (450, 64, 15, 15), (1000, 64, 8, 8)])
+def test_resblock_tail_matches_aten(native_lib, shape):
+    """conv2(relu(norm2(x))) + shortcut (model.py:156-178) in one tcgen05 kernel vs cuDNN fp32 + ATen."""
+    from node_b200 import caller_ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(2)
+    norm = nn.GroupNorm(32, 64).to(DEV)
+    conv = nn.Conv2d(64, 64, 3, 1, 1, bias=False).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        x = torch.randn(shape, device=DEV) * 1.5 + 0.3
+        sc = torch.randn(shape, device=DEV)
+        ref = conv(torch.relu(norm(x))) + sc
+        assert caller_ops._resconv_ok(norm, conv, x, sc)
+        got = caller_ops.res_conv(norm, conv, x, sc)
+        torch.cuda.synchronize()
+        assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+        conv.weight.mul_(2.0)                       # in-place parameter update: the weight tiles are re-packed
+        ref2 = conv(torch.relu(norm(x))) + sc
+        got2 = caller_ops.res_conv(norm, conv, x, sc)
+        assert float((got2 - ref2).abs().max()) <= 2e-5 * float(ref2.abs().max())

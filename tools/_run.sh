@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "fused or vjp" > gpurun_out/t_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/t_pytest.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_pytest.log 2>&1; echo "pytest exit $?"; tail -12 gpurun_out/t_pytest.log
 timeout 600 python bench.py --skip-cpu --train-batch 0 > gpurun_out/t_bench.json 2> gpurun_out/t_bench.err; echo "bench exit $?"; tail -3 gpurun_out/t_bench.err
 python - <<'PY'
 import json
