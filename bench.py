@@ -143,10 +143,16 @@ def workload_config(args, sample_note=None):
     c = dict(workload='cfg2: CIFAR-10 ODENet(3, n_filters=64, downsample=residual, tol=1e-3).eval() forward, '
                       'synthetic 32x32 batches', per_gpu_batch=args.batch, global_batch=args.batch * args.gpus,
              solver='dopri5 rtol=atol=1e-3', conv_mode=os.environ.get('NODE_B200_CONV', 'f16x3'),
-             downsample_classifier='cuDNN fp32 convolutions (cudnn.allow_tf32=False) + one-pass CUDA GroupNorm->ReLU (csrc/caller_ops.cu)', parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
+             downsample_classifier='strided / first convolutions: cuDNN fp32 (cudnn.allow_tf32=False); GroupNorm->ReLU and the ResBlock tails '
+                                   '(GN->ReLU->conv3x3->add): own CUDA kernels (csrc/caller_ops.cu, resconv_engine.cuh)',
+             batch_note='per-GPU batch sized to whole rounds of the persistent step kernel: 148 SMs x 2 slots x 3 images x 5',
+             parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
              l2='inputs larger than L2 (state %d MB per tensor, ~10 live tensors)' % (args.batch * 64 * 64 * 4 // 2 ** 20))
-    if sample_note:
+    if sample_note:          # the reference arm: the oracle port on the host CPU, none of the kernels above
         c['sample'] = sample_note
+        c['conv_mode'] = 'ATen CPU fp32'
+        c['downsample_classifier'] = 'ATen CPU fp32'
+        c.pop('batch_note', None)
     return c
 
 
@@ -258,11 +264,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('NODE_B200_BENCH_BATCH', 4096)), help='per-GPU batch')
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('NODE_B200_BENCH_BATCH', 4440)),
+                    help='per-GPU batch; 4440 = 148 SMs x 2 worker slots x 3 images per super-tile x 5 rounds (no tail round)')
     ap.add_argument('--cpu-sample', type=int, default=1024)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
-    ap.add_argument('--train-batch', type=int, default=1024, help='batch of the adjoint training-step measurement (0 = skip)')
+    ap.add_argument('--train-batch', type=int, default=2048, help='batch of the adjoint training-step measurement (0 = skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     if args.impl == 'reference':
