@@ -223,6 +223,19 @@ int node_b200_resconv_prepare(void* workspace, int C, int H, int W, const float*
 int node_b200_resconv_forward(void* workspace, const float* x, const float* shortcut, float* out, const float* gn_w,
                               const float* gn_b, int N, int C, int H, int W, float eps, void* stream);
 
+/* Callers of the hot path: the head of the reference's strided ResBlock (model.py:156-178) on the already
+ * normalised activation a = relu(norm1(x)), contiguous NCHW fp32 [N,64,HI,WI]:
+ *     c_out  = conv1(a)       conv1      = Conv2d(64, 64, 3, stride 2, padding 1, bias=False)   [N,64,HO,WO]
+ *     sc_out = downsample(a)  downsample = Conv2d(64, 64, 1, stride 2, bias=False)              [N,64,HO,WO]
+ * in one tcgen05 kernel (parity planes: every stride-2 tap is a stride-1 tap of one plane). Supported inputs: 30x30,
+ * 15x15 (CIFAR), 26x26, 13x13 (MNIST); workspace_bytes returns 0 otherwise. prepare() takes the two live weights and the
+ * affine parameters of norm1 (they bound the activation for the fp16 operand split). */
+int64_t node_b200_convs2_workspace_bytes(int C, int HI, int WI);
+int node_b200_convs2_prepare(void* workspace, int C, int HI, int WI, const float* conv_w, const float* down_w,
+                             const float* gn_w, const float* gn_b, void* stream);
+int node_b200_convs2_forward(void* workspace, const float* act, float* c_out, float* sc_out, int N, int C, int HI, int WI,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

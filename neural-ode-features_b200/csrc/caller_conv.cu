@@ -1,6 +1,7 @@
 // C ABI of the fused ResBlock tail (resconv_engine.cuh): parameter preparation and shape dispatch.
 #include <cuda_fp16.h>
 #include "resconv_engine.cuh"
+#include "convs2_engine.cuh"
 
 namespace node {
 
@@ -57,9 +58,94 @@ __global__ void k_resconv_tiles(ResConvWs w, const float* cw) {
   }
 }
 
+// ---- strided ResBlock head (convs2_engine.cuh) ----------------------------------------------------------------------
+int launch_convs2_30x30(const ConvS2Args& a, cudaStream_t st);
+int launch_convs2_15x15(const ConvS2Args& a, cudaStream_t st);
+int launch_convs2_26x26(const ConvS2Args& a, cudaStream_t st);
+int launch_convs2_13x13(const ConvS2Args& a, cudaStream_t st);
+
+static int64_t convs2_layout(void* base, ResConvWs* out) {
+  const int64_t o_scal = (int64_t)kS2Tiles * kW16TileBytes;
+  if (out != nullptr) { out->w16 = (uint16_t*)base; out->scal = (float*)((char*)base + o_scal); }
+  return o_scal + 1024;
+}
+
+// scal[0] activation scale, [1] / [4] weight scales of conv1 / shortcut, [2] / [3] their inverse products
+__global__ void k_convs2_scales(ResConvWs w, int HWin, const float* cw, const float* dw, const float* gw, const float* gb) {
+  __shared__ float red[4][256];
+  const int tid = threadIdx.x;
+  float mw = 0.f, md = 0.f, mg = 0.f, mb = 0.f;
+  for (int i = tid; i < kC * kC * 9; i += 256) mw = fmaxf(mw, fabsf(cw[i]));
+  for (int i = tid; i < kC * kC; i += 256) md = fmaxf(md, fabsf(dw[i]));
+  for (int i = tid; i < kC; i += 256) { mg = fmaxf(mg, fabsf(gw[i])); mb = fmaxf(mb, fabsf(gb[i])); }
+  red[0][tid] = mw; red[1][tid] = md; red[2][tid] = mg; red[3][tid] = mb;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) for (int r = 0; r < 4; ++r) red[r][tid] = fmaxf(red[r][tid], red[r][tid + s]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float bound_a = red[2][0] * sqrtf((float)(kCpg * HWin)) + red[3][0];
+    int ea = bound_a > 0.f ? (int)floorf(log2f(32768.0f / bound_a)) : 0;
+    int ew = red[0][0] > 0.f ? (int)floorf(log2f(16384.0f / red[0][0])) : 0;
+    int ed = red[1][0] > 0.f ? (int)floorf(log2f(16384.0f / red[1][0])) : 0;
+    ea = max(-24, min(24, ea)); ew = max(-24, min(24, ew)); ed = max(-24, min(24, ed));
+    w.scal[0] = exp2f((float)ea); w.scal[1] = exp2f((float)ew); w.scal[4] = exp2f((float)ed);
+    w.scal[2] = exp2f((float)(-ea - ew)); w.scal[3] = exp2f((float)(-ea - ed));
+  }
+}
+
+// tiles in the kernel's issue order: 3x3 taps 0, 2, 6, 8, 1, 7, 3, 5, 4, then the 1x1 shortcut
+__global__ void k_convs2_tiles(ResConvWs w, const float* cw, const float* dw) {
+  const int order[kS2Tiles] = {0, 2, 6, 8, 1, 7, 3, 5, 4, -1};
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = tid; i < kS2Tiles * 128 * 64; i += nth) {
+    int r = i;
+    const int cin = r % 64; r /= 64;
+    const int row = r % 128; r /= 128;
+    const int t = r;
+    const int co = row & 63, tap = order[t];
+    const float v = tap >= 0 ? cw[((int64_t)co * kC + cin) * 9 + tap] * w.scal[1] : dw[(int64_t)co * kC + cin] * w.scal[4];
+    const __half hi = __float2half_rn(v);
+    const __half val = row < 64 ? hi : __float2half_rn(v - __half2float(hi));
+    const int chunk = (cin >> 3) ^ (row & 7);
+    w.w16[((int64_t)t * 128 + row) * 64 + chunk * 8 + (cin & 7)] = *reinterpret_cast<const uint16_t*>(&val);
+  }
+}
+
 }  // namespace node
 
 using namespace node;
+
+extern "C" int64_t node_b200_convs2_workspace_bytes(int C, int HI, int WI) {
+  if (C != kC) return 0;
+  const bool ok = (HI == 30 && WI == 30) || (HI == 15 && WI == 15) || (HI == 26 && WI == 26) || (HI == 13 && WI == 13);
+  return ok ? convs2_layout(nullptr, nullptr) : 0;
+}
+
+extern "C" int node_b200_convs2_prepare(void* workspace, int C, int HI, int WI, const float* conv_w, const float* down_w,
+                                        const float* gn_w, const float* gn_b, void* stream) {
+  if (node_b200_convs2_workspace_bytes(C, HI, WI) <= 0) return (int)cudaErrorInvalidValue;
+  ResConvWs w; convs2_layout(workspace, &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_convs2_scales<<<1, 256, 0, st>>>(w, HI * WI, conv_w, down_w, gn_w, gn_b);
+  NODE_CUDA_OK(cudaGetLastError());
+  k_convs2_tiles<<<148, 256, 0, st>>>(w, conv_w, down_w);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int node_b200_convs2_forward(void* workspace, const float* act, float* c_out, float* sc_out, int N, int C, int HI,
+                                        int WI, void* stream) {
+  if (N < 1 || node_b200_convs2_workspace_bytes(C, HI, WI) <= 0) return (int)cudaErrorInvalidValue;
+  ResConvWs w; convs2_layout(workspace, &w);
+  ConvS2Args a{};
+  a.w16 = w.w16; a.scal = w.scal; a.act = act; a.c_out = c_out; a.sc_out = sc_out; a.N = N;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (HI == 30) return launch_convs2_30x30(a, st);
+  if (HI == 15) return launch_convs2_15x15(a, st);
+  if (HI == 26) return launch_convs2_26x26(a, st);
+  return launch_convs2_13x13(a, st);
+}
 
 extern "C" int64_t node_b200_resconv_workspace_bytes(int C, int H, int W) {
   if (C != kC) return 0;

@@ -99,3 +99,50 @@ def res_conv(norm, conv, x, shortcut):
                                                native.ptr(norm.weight), native.ptr(norm.bias), N, C, H, W, float(norm.eps),
                                                native.stream_ptr()), 'resconv_forward')
     return out
+
+
+# ---- fused strided ResBlock head: conv1(a) [3x3 stride 2] and downsample(a) [1x1 stride 2] (csrc/convs2_engine.cuh) -------
+
+_convs2_ws = {}
+
+
+def _is_conv(m, k, stride, pad):
+    return (isinstance(m, nn.Conv2d) and (m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding, m.dilation, m.groups)
+            == (64, 64, (k, k), (stride, stride), (pad, pad), (1, 1), 1) and m.bias is None and m.padding_mode == 'zeros')
+
+
+def _convs2_ok(norm, conv, down, a):
+    if not (isinstance(norm, nn.GroupNorm) and norm.weight is not None and _is_conv(conv, 3, 2, 1) and _is_conv(down, 1, 2, 0)):
+        return False
+    if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 4 and a.shape[1] == 64 and norm.num_groups == 32):
+        return False
+    if torch.is_grad_enabled() and (a.requires_grad or conv.weight.requires_grad or down.weight.requires_grad):
+        return False
+    return native.lib().node_b200_convs2_workspace_bytes(64, int(a.shape[2]), int(a.shape[3])) > 0
+
+
+def res_head(norm, conv, down, a):
+    """(conv(a), down(a)) for a = relu(norm(x)) already computed: one tcgen05 kernel when the shape is served and no gradient
+    is needed, the modules' own ops otherwise. `norm` only supplies the bound of |a| for the fp16 operand split."""
+    if not _convs2_ok(norm, conv, down, a):
+        return conv(a), down(a)
+    a = a.contiguous()
+    N, C, HI, WI = (int(v) for v in a.shape)
+    HO, WO = (HI - 1) // 2 + 1, (WI - 1) // 2 + 1
+    lib = native.lib()
+    key = (id(conv), id(down), id(norm), str(a.device), HI, WI)
+    ent = _convs2_ws.get(key)
+    ver = (conv.weight.data_ptr(), conv.weight._version, down.weight.data_ptr(), down.weight._version, norm.weight._version,
+           norm.bias._version)
+    if ent is None or ent[1] != ver:
+        if len(_convs2_ws) > 32:
+            _convs2_ws.clear()
+        buf = ent[0] if ent is not None else torch.zeros(lib.node_b200_convs2_workspace_bytes(C, HI, WI), dtype=torch.uint8, device=a.device)
+        native.check(lib.node_b200_convs2_prepare(native.ptr(buf), C, HI, WI, native.ptr(conv.weight), native.ptr(down.weight),
+                                                  native.ptr(norm.weight), native.ptr(norm.bias), native.stream_ptr()), 'convs2_prepare')
+        ent = _convs2_ws[key] = (buf, ver)
+    c = torch.empty((N, C, HO, WO), dtype=a.dtype, device=a.device)
+    sc = torch.empty_like(c)
+    native.check(lib.node_b200_convs2_forward(native.ptr(ent[0]), native.ptr(a), native.ptr(c), native.ptr(sc), N, C, HI, WI,
+                                              native.stream_ptr()), 'convs2_forward')
+    return c, sc

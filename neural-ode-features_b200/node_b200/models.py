@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .solver import odeint, odeint_adjoint
-from .caller_ops import group_norm_relu, res_conv, run_sequential
+from .caller_ops import group_norm_relu, res_conv, res_head, run_sequential
 
 
 def _norm_factory(kind='group'):
@@ -131,8 +131,11 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         out = group_norm_relu(self.norm1, x) if isinstance(self.norm1, nn.GroupNorm) else self.relu(self.norm1(x))
-        shortcut = x if self.downsample is None else self.downsample(out)
-        out = self.conv1(out)
+        if self.downsample is not None and isinstance(self.norm1, nn.GroupNorm):
+            out, shortcut = res_head(self.norm1, self.conv1, self.downsample, out)   # one kernel when served (caller_ops)
+        else:
+            shortcut = x if self.downsample is None else self.downsample(out)
+            out = self.conv1(out)
         if isinstance(self.norm2, nn.GroupNorm):
             return res_conv(self.norm2, self.conv2, out, shortcut)        # one kernel when served (caller_ops)
         return self.conv2(self.relu(self.norm2(out))) + shortcut

@@ -32,7 +32,7 @@ EXPORTS = (
     'node_b200_odefunc_forward', 'node_b200_fused_solve', 'node_b200_fused_phase', 'node_b200_fused_sums',
     'node_b200_fused_ctl', 'node_b200_vjp_workspace_bytes', 'node_b200_odefunc_vjp', 'node_b200_wgrad',
     'node_b200_vjp_buffer', 'node_b200_groupnorm_relu', 'node_b200_resconv_workspace_bytes', 'node_b200_resconv_prepare',
-    'node_b200_resconv_forward',
+    'node_b200_resconv_forward', 'node_b200_convs2_workspace_bytes', 'node_b200_convs2_prepare', 'node_b200_convs2_forward',
 )
 
 _lib = None
@@ -72,6 +72,10 @@ def _declare(lib):
     lib.node_b200_resconv_workspace_bytes.restype = _i64
     lib.node_b200_resconv_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]
     lib.node_b200_resconv_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
+    lib.node_b200_convs2_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.node_b200_convs2_workspace_bytes.restype = _i64
+    lib.node_b200_convs2_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+    lib.node_b200_convs2_forward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
 
 
 def lib():

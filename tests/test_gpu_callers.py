@@ -77,3 +77,25 @@ def test_resblock_tail_matches_aten(native_lib, shape):
         ref2 = conv(torch.relu(norm(x))) + sc
         got2 = caller_ops.res_conv(norm, conv, x, sc)
         assert float((got2 - ref2).abs().max()) <= 2e-5 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize('shape', [(37, 64, 30, 30), (16, 64, 15, 15), (9, 64, 26, 26), (11, 64, 13, 13), (300, 64, 30, 30), (1000, 64, 15, 15)])
+def test_resblock_head_matches_aten(native_lib, shape):
+    """conv1 (3x3 stride 2) and the 1x1 stride-2 shortcut of a strided ResBlock (model.py:156-178) in one tcgen05 kernel."""
+    from node_b200 import caller_ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(3)
+    norm = nn.GroupNorm(32, 64).to(DEV)
+    conv = nn.Conv2d(64, 64, 3, 2, 1, bias=False).to(DEV)
+    down = nn.Conv2d(64, 64, 1, 2, bias=False).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        a = torch.relu(norm(torch.randn(shape, device=DEV) * 1.5 + 0.3))
+        ref_c, ref_s = conv(a), down(a)
+        assert caller_ops._convs2_ok(norm, conv, down, a)
+        c, s = caller_ops.res_head(norm, conv, down, a)
+        torch.cuda.synchronize()
+        assert c.shape == ref_c.shape and s.shape == ref_s.shape
+        assert float((c - ref_c).abs().max()) <= 2e-5 * float(ref_c.abs().max())
+        assert float((s - ref_s).abs().max()) <= 2e-5 * float(ref_s.abs().max())
