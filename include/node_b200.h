@@ -236,6 +236,13 @@ int node_b200_convs2_prepare(void* workspace, int C, int HI, int WI, const float
 int node_b200_convs2_forward(void* workspace, const float* act, float* c_out, float* sc_out, int N, int C, int HI, int WI,
                              void* stream);
 
+/* Callers of the hot path: the stem of the reference's downsamplers (model.py:119-178),
+ *     out = relu(GroupNorm(32, 64)(Conv2d(CIN, 64, 3, 1)(x)))          x [N,CIN,HIN,WIN] -> out [N,64,HIN-2,WIN-2]
+ * in one pass (one CTA per image, one thread per output pixel, fp32 FFMA, two-pass GroupNorm statistics). Served:
+ * (CIN,HIN,WIN) = (3,32,32) CIFAR and (1,28,28) MNIST; cudaErrorInvalidValue otherwise (the caller keeps its own ops). */
+int node_b200_stem_gn_relu(const float* x, const float* conv_w, const float* conv_b, const float* gn_w, const float* gn_b,
+                           float* out, int N, int CIN, int HIN, int WIN, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,3 +114,138 @@ extern "C" int node_b200_groupnorm_relu(const float* x, float* y, const float* g
   if (L <= 32 * kGnThreads) return launch_gn<32, 1>(x, y, gamma, beta, cells, groups, cpg, HW, eps, relu, st);
   return (int)cudaErrorInvalidValue;
 }
+
+// ---- stem: conv0 (Conv2d(CIN, 64, 3, 1), bias) -> GroupNorm(32, 64) -> ReLU in one pass ------------------------------------
+// The first layer of the reference's ResDownsample / ConvDownsample (model.py:119-178) followed by the first GroupNorm:
+// cuDNN + ATen run it as convolution, bias add, row moments, affine apply, ReLU = 5 passes over the [N,64,HO,WO] tensor;
+// here one CTA owns one image, one thread one output pixel: the 27 (9) inputs of the pixel stay in registers, the 64
+// output channels are produced 8 at a time (4 GroupNorm cells), their two-pass statistics are block reductions, and only
+// relu(GN(conv(x))) is written - 1 pass. Plain fp32 FFMA (K = 27: no tensor-core shape).
+namespace node {
+
+// Sum NV per-thread values over the CTA: warp shuffles, one partial per warp, warp 0 folds the partials, everyone reads
+// the totals (3 barriers; the fold costs NV loads per thread instead of NV x #warps).
+template <int NV>
+__device__ __forceinline__ void block_sum_n(float (&v)[NV], float* scratch, float* total, int nwarp) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                                   // previous totals / partials have been consumed
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[warp * NV + i] = v[i];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float r = lane < nwarp ? scratch[lane * NV + i] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      if (lane == 0) total[i] = r;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = total[i];
+}
+
+template <int CIN, int HIN, int WIN>
+__global__ void __launch_bounds__(((HIN - 2) * (WIN - 2) + 31) / 32 * 32, 1)
+k_stem_gn_relu(const float* __restrict__ x, const float* __restrict__ cw, const float* __restrict__ cb, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float* __restrict__ out, float eps) {
+  constexpr int HO = HIN - 2, WO = WIN - 2, NPIX = HO * WO, K = CIN * 9, NT = (NPIX + 31) / 32 * 32;
+  static_assert(NT / 32 <= 32, "one partial per warp, folded by one warp");
+  __shared__ float s_in[CIN * HIN * WIN];
+  __shared__ __align__(16) float s_w[64 * K];        // [pass of 8 channels][k][8 channels]
+  __shared__ float s_b[64], s_g[64], s_be[64];
+  __shared__ float scratch[(NT / 32) * 8], total[8];
+  const int tid = threadIdx.x, n = blockIdx.x;
+  for (int i = tid; i < CIN * HIN * WIN; i += NT) s_in[i] = x[(size_t)n * CIN * HIN * WIN + i];
+  for (int i = tid; i < 64 * K; i += NT) {
+    const int c = i / K, k = i % K;
+    s_w[((c >> 3) * K + k) * 8 + (c & 7)] = cw[i];
+  }
+  if (tid < 64) { s_b[tid] = cb[tid]; s_g[tid] = gamma[tid]; s_be[tid] = beta[tid]; }
+  __syncthreads();
+  const bool valid = tid < NPIX;
+  const int p = valid ? tid : 0, oy = p / WO, ox = p % WO;
+  float in[K];
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) in[(ci * 3 + dy) * 3 + dx] = s_in[(ci * HIN + oy + dy) * WIN + ox + dx];
+  constexpr float inv_n = 1.0f / (float)(2 * NPIX);
+#pragma unroll 1
+  for (int ps = 0; ps < 8; ++ps) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = s_b[8 * ps + j];
+    const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)ps * K * 8);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4 a = w4[2 * k], b = w4[2 * k + 1];
+      acc[0] = fmaf(in[k], a.x, acc[0]); acc[1] = fmaf(in[k], a.y, acc[1]); acc[2] = fmaf(in[k], a.z, acc[2]); acc[3] = fmaf(in[k], a.w, acc[3]);
+      acc[4] = fmaf(in[k], b.x, acc[4]); acc[5] = fmaf(in[k], b.y, acc[5]); acc[6] = fmaf(in[k], b.z, acc[6]); acc[7] = fmaf(in[k], b.w, acc[7]);
+    }
+    // one round: sums and sums of squares of the 4 GroupNorm cells; E[x^2] - mean^2 is redone in two passes when a cell
+    // is ill-conditioned (CTA-uniform decision: every thread sees the same totals)
+    float s[8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      s[g] = valid ? acc[2 * g] + acc[2 * g + 1] : 0.f;
+      s[4 + g] = valid ? fmaf(acc[2 * g], acc[2 * g], acc[2 * g + 1] * acc[2 * g + 1]) : 0.f;
+    }
+    block_sum_n<8>(s, scratch, total, NT / 32);
+    bool ill = false;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      s[g] *= inv_n;                                                  // mean
+      s[4 + g] = fmaxf(fmaf(-s[g], s[g], s[4 + g] * inv_n), 0.f);     // variance
+      ill |= s[g] * s[g] > 16.0f * s[4 + g];
+    }
+    if (ill) {
+      float q[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float d0 = acc[2 * g] - s[g], d1 = acc[2 * g + 1] - s[g];
+        q[g] = valid ? fmaf(d0, d0, d1 * d1) : 0.f;
+      }
+      block_sum_n<4>(q, scratch, total, NT / 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) s[4 + g] = q[g] * inv_n;
+    }
+    if (valid) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float rstd = 1.0f / sqrtf(s[4 + g] + eps);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = 8 * ps + 2 * g + h;
+          const float r = fmaf(acc[2 * g + h] - s[g], rstd * s_g[c], s_be[c]);
+          out[((size_t)n * 64 + c) * NPIX + p] = fmaxf(r, 0.f);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace node
+
+extern "C" int node_b200_stem_gn_relu(const float* x, const float* conv_w, const float* conv_b, const float* gn_w, const float* gn_b,
+                                      float* out, int N, int CIN, int HIN, int WIN, float eps, void* stream) {
+  using namespace node;
+  if (N < 1) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (CIN == 3 && HIN == 32 && WIN == 32) {
+    k_stem_gn_relu<3, 32, 32><<<N, (30 * 30 + 31) / 32 * 32, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
+  } else if (CIN == 1 && HIN == 28 && WIN == 28) {
+    k_stem_gn_relu<1, 28, 28><<<N, (26 * 26 + 31) / 32 * 32, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
+  } else {
+    return (int)cudaErrorInvalidValue;      // the caller keeps its own ops
+  }
+  return (int)cudaGetLastError();
+}

@@ -146,3 +146,30 @@ def res_head(norm, conv, down, a):
     native.check(lib.node_b200_convs2_forward(native.ptr(ent[0]), native.ptr(a), native.ptr(c), native.ptr(sc), N, C, HI, WI,
                                               native.stream_ptr()), 'convs2_forward')
     return c, sc
+
+
+# ---- fused stem: relu(norm(conv(x))) for the first Conv2d(CIN, 64, 3, 1) of a downsampler (csrc/caller_ops.cu) -------------
+
+def _stem_ok(conv, norm, x):
+    if not (isinstance(conv, nn.Conv2d) and isinstance(norm, nn.GroupNorm) and norm.weight is not None and conv.bias is not None):
+        return False
+    if (conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups) != (64, (3, 3), (1, 1), (0, 0), (1, 1), 1):
+        return False
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and norm.num_groups == 32 and norm.num_channels == 64):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad or norm.weight.requires_grad):
+        return False
+    return (int(x.shape[1]), int(x.shape[2]), int(x.shape[3])) in ((3, 32, 32), (1, 28, 28)) and conv.in_channels == x.shape[1]
+
+
+def stem_gn_relu(conv, norm, x):
+    """relu(norm(conv(x))): one CUDA pass when served and no gradient is needed, the modules' own ops otherwise."""
+    if not _stem_ok(conv, norm, x):
+        return group_norm_relu(norm, conv(x))
+    x = x.contiguous()
+    N, CIN, HIN, WIN = (int(v) for v in x.shape)
+    out = torch.empty((N, 64, HIN - 2, WIN - 2), dtype=x.dtype, device=x.device)
+    native.check(native.lib().node_b200_stem_gn_relu(native.ptr(x), native.ptr(conv.weight), native.ptr(conv.bias), native.ptr(norm.weight),
+                                                     native.ptr(norm.bias), native.ptr(out), N, CIN, HIN, WIN, float(norm.eps),
+                                                     native.stream_ptr()), 'stem_gn_relu')
+    return out

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .solver import odeint, odeint_adjoint
-from .caller_ops import group_norm_relu, res_conv, res_head, run_sequential
+from .caller_ops import group_norm_relu, res_conv, res_head, run_sequential, stem_gn_relu
 
 
 def _norm_factory(kind='group'):
@@ -131,6 +131,10 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         out = group_norm_relu(self.norm1, x) if isinstance(self.norm1, nn.GroupNorm) else self.relu(self.norm1(x))
+        return self.forward_act(out, x)
+
+    def forward_act(self, out, x=None):
+        """The block after its first normalisation: out = relu(norm1(x)) (x is only needed for an identity shortcut)."""
         if self.downsample is not None and isinstance(self.norm1, nn.GroupNorm):
             out, shortcut = res_head(self.norm1, self.conv1, self.downsample, out)   # one kernel when served (caller_ops)
         else:
@@ -185,6 +189,14 @@ class ResDownsample(_Wrapped):
             nn.Conv2d(in_ch, 64, 3, 1),
             ResBlock(64, 64, stride=2, downsample=_conv1x1(64, 64, 2), norm=norm),
             ResBlock(64, out_ch, stride=2, downsample=_conv1x1(64, out_ch, 2), norm=norm))
+
+    def forward(self, x):
+        conv0, rb1, rb2 = self.module[0], self.module[1], self.module[2]
+        if isinstance(rb1.norm1, nn.GroupNorm) and rb1.downsample is not None:
+            # conv0's raw output feeds nothing but rb1.norm1 (the shortcut branches off AFTER the normalisation,
+            # model.py:170-172): stem convolution, GroupNorm and ReLU in one pass (caller_ops.stem_gn_relu)
+            return rb2(rb1.forward_act(stem_gn_relu(conv0, rb1.norm1, x)))
+        return rb2(rb1(conv0(x)))
 
 
 class ODEDownsample(nn.Module):

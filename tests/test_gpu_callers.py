@@ -99,3 +99,22 @@ def test_resblock_head_matches_aten(native_lib, shape):
         assert c.shape == ref_c.shape and s.shape == ref_s.shape
         assert float((c - ref_c).abs().max()) <= 2e-5 * float(ref_c.abs().max())
         assert float((s - ref_s).abs().max()) <= 2e-5 * float(ref_s.abs().max())
+
+
+@pytest.mark.parametrize('shape', [(37, 3, 32, 32), (19, 1, 28, 28), (300, 3, 32, 32)])
+def test_stem_conv_groupnorm_relu_matches_aten(native_lib, shape):
+    from node_b200 import caller_ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(4)
+    conv = nn.Conv2d(shape[1], 64, 3, 1).to(DEV)
+    norm = nn.GroupNorm(32, 64).to(DEV)
+    with torch.no_grad():
+        norm.weight.uniform_(0.5, 1.5)
+        norm.bias.uniform_(-0.5, 0.5)
+        x = torch.rand(shape, device=DEV)
+        ref = torch.relu(norm(conv(x)))
+        assert caller_ops._stem_ok(conv, norm, x)
+        got = caller_ops.stem_gn_relu(conv, norm, x)
+        torch.cuda.synchronize()
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
