@@ -369,7 +369,7 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_fused_step_dram_bytes_per_launch')
+        traffic = json.load(open(tpath)).get('k_step_dram_bytes_per_launch')
     roof = dict(bound='tensor', kernel='k_step<8,8,2> (6 dopri5 stages = 12 implicit-GEMM convs per launch)',
                 achieved=flops_per_launch / k_avg / 1e12, peak=tf32_peak, unit='TFLOP/s',
                 frac=flops_per_launch / k_avg / 1e12 / tf32_peak, traffic=traffic,
