@@ -143,8 +143,8 @@ def workload_config(args, sample_note=None):
     c = dict(workload='cfg2: CIFAR-10 ODENet(3, n_filters=64, downsample=residual, tol=1e-3).eval() forward, '
                       'synthetic 32x32 batches', per_gpu_batch=args.batch, global_batch=args.batch * args.gpus,
              solver='dopri5 rtol=atol=1e-3', conv_mode=os.environ.get('NODE_B200_CONV', 'f16x3'),
-             downsample_classifier='strided / first convolutions: cuDNN fp32 (cudnn.allow_tf32=False); GroupNorm->ReLU and the ResBlock tails '
-                                   '(GN->ReLU->conv3x3->add): own CUDA kernels (csrc/caller_ops.cu, resconv_engine.cuh)',
+             downsample_classifier='own CUDA kernels for the stem (conv+GN+ReLU), the ResBlock heads (3x3 s2 + 1x1 s2, tcgen05) and '
+                                   'tails (GN->ReLU->conv3x3->add, tcgen05) and the remaining GroupNorm->ReLU pairs; pooling / linear: PyTorch',
              batch_note='per-GPU batch sized to whole rounds of the persistent step kernel: 148 SMs x 2 slots x 3 images x 5',
              parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
              l2='inputs larger than L2 (state %d MB per tensor, ~10 live tensors)' % (args.batch * 64 * 64 * 4 // 2 ** 20))
@@ -325,11 +325,36 @@ def main():
             net(x_dev)
         launches[0] += solver.last_stats.get('launches', 0)
 
+    # End to end: every step copies ITS input batch from pinned host memory and reads ITS logits back to the host. The
+    # input of step i+1 is prefetched on a copy stream while step i computes (the usual pinned-memory data-loader pattern:
+    # two device buffers, events in both directions); the result read-back is synchronous, once per step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_i = [0]
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the forward that last read this buffer is done
+            xbuf[slot].copy_(x_host, non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    for ev in consumed:
+        ev.record()
+    prefetch(0)
+
     def step_e2e():
+        cur = e2e_i[0] & 1
+        e2e_i[0] += 1
+        main = torch.cuda.current_stream()
+        main.wait_event(copied[cur])
+        prefetch(cur ^ 1)                                    # next step's input travels while this step computes
         with torch.no_grad():
-            xd = x_host.to(dev, non_blocking=True)
-            logits_host.copy_(net(xd), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            out = net(xbuf[cur])
+        consumed[cur].record(main)
+        logits_host.copy_(out, non_blocking=True)
+        main.synchronize()
 
     for _ in range(args.warmup):
         step_resident()

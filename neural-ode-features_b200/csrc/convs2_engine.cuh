@@ -112,23 +112,46 @@ __global__ void __launch_bounds__(Tile<HO, WO>::P, 1) k_convs2(const ConvS2Args 
     for (int pass = 0; pass < 2; ++pass) {
       // ---- stage the two planes of this pass (loads first, then wait until the previous pass' MMAs have read the images)
       if (pass == 1 && !timeout && !ptx::mbar_wait_relaxed(bar_pass, job & 1)) timeout = true;
-#pragma unroll 1
-      for (int ps = 0; ps < 2; ++ps) {
-        const int pr = pass == 0 ? 1 : 0, pc = ps == 0 ? 1 : 0;
-        const int ii = 2 * oi + pr, ij = 2 * oj + pc;
-        const bool inb = valid && ii < HI && ij < WI;
-        const size_t g0 = inb ? ((size_t)img * kC * HWI + (size_t)ii * WI + ij) : 0;
-        const uint32_t row = planes + (uint32_t)ps * 2 * T::A_PART + (uint32_t)(T::HALO + tid) * 16;
+      if constexpr (WI % 2 == 0) {
+        // even width: the two column parities of a row pair are adjacent floats - one 8-byte load feeds both planes
+        const int pr = pass == 0 ? 1 : 0;
+        const int ii = 2 * oi + pr;
+        const bool inb = valid && ii < HI;
+        const size_t g0 = inb ? ((size_t)img * kC * HWI + (size_t)ii * WI + 2 * oj) : 0;
+        const uint32_t row = planes + (uint32_t)(T::HALO + tid) * 16;
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
-          float x[32];
+          float x0[32], x1[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) x[c] = ptx::ldg_ordered(a.act + g0 + (size_t)(32 * hb + c) * HWI);
-          if (!inb) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = 0.f;
+          for (int c = 0; c < 32; ++c) {
+            float2 v;
+            asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a.act + g0 + (size_t)(32 * hb + c) * HWI));
+            x0[c] = inb ? v.x : 0.f; x1[c] = inb ? v.y : 0.f;
           }
-          if (valid) raw_to_A<T>(row + 4 * hb * T::LBO, x, sa);
+          if (valid) {
+            raw_to_A<T>(row + 4 * hb * T::LBO, x1, sa);                          // plane slot 0: pc = 1
+            raw_to_A<T>(row + 2 * T::A_PART + 4 * hb * T::LBO, x0, sa);          // plane slot 1: pc = 0
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ps = 0; ps < 2; ++ps) {
+          const int pr = pass == 0 ? 1 : 0, pc = ps == 0 ? 1 : 0;
+          const int ii = 2 * oi + pr, ij = 2 * oj + pc;
+          const bool inb = valid && ii < HI && ij < WI;
+          const size_t g0 = inb ? ((size_t)img * kC * HWI + (size_t)ii * WI + ij) : 0;
+          const uint32_t row = planes + (uint32_t)ps * 2 * T::A_PART + (uint32_t)(T::HALO + tid) * 16;
+#pragma unroll 1
+          for (int hb = 0; hb < 2; ++hb) {
+            float x[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) x[c] = ptx::ldg_ordered(a.act + g0 + (size_t)(32 * hb + c) * HWI);
+            if (!inb) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) x[c] = 0.f;
+            }
+            if (valid) raw_to_A<T>(row + 4 * hb * T::LBO, x, sa);
+          }
         }
       }
       ptx::fence_proxy_async();

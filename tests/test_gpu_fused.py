@@ -220,3 +220,23 @@ def test_cuda_graph_replay_of_the_solve(native_lib, golden, monkeypatch):
         assert torch.equal(c[0], h1)
         outs[mode] = (b.clone(), c.clone())
     assert torch.equal(outs['0'][0], outs['1'][0]) and torch.equal(outs['0'][1], outs['1'][1])
+
+
+@pytest.mark.parametrize('tol', [1e-4, 1e-2, 1e-1])
+def test_tolerance_sweep_matches_oracle(native_lib, golden, tol):
+    """cfg5's sweep (adversarial/reproduce.sh:9-10: tol 1e-4 ... 1e-1) on a small batch: NFE, accept/reject sequence and
+    outputs against the oracle evaluated here on the CPU."""
+    from node_b200 import odeint, solver
+    g = golden('cifar_res_n8')
+    func = load_odefunc(g, DEV)
+    p = odefunc_params(g)
+    h0 = torch.from_numpy(g['h0'])[:4].contiguous()
+    t = torch.tensor([0., 1.])
+    tr = dopri5_port.Trace()
+    ref = dopri5_port.dopri5_solve(lambda tt, y: odefunc_port.odefunc_forward(p, tt, y), h0, t, tol, tol, trace=tr)
+    with torch.no_grad():
+        out = odeint(func, h0.to(DEV), t.to(DEV), rtol=tol, atol=tol, method='dopri5')
+    st = dict(solver.last_stats)
+    assert st['route'] == 'fused' and st['nfe'] == tr.nfe
+    assert [int(a) for a in st['trace']['accepted']] == [int(s[2]) for s in tr.steps]
+    assert rel(out.cpu(), ref) < TOL_OUT
