@@ -118,9 +118,9 @@ extern "C" int node_b200_groupnorm_relu(const float* x, float* y, const float* g
 // ---- stem: conv0 (Conv2d(CIN, 64, 3, 1), bias) -> GroupNorm(32, 64) -> ReLU in one pass ------------------------------------
 // The first layer of the reference's ResDownsample / ConvDownsample (model.py:119-178) followed by the first GroupNorm:
 // cuDNN + ATen run it as convolution, bias add, row moments, affine apply, ReLU = 5 passes over the [N,64,HO,WO] tensor;
-// here one CTA owns one image, one thread one output pixel: the 27 (9) inputs of the pixel stay in registers, the 64
-// output channels are produced 8 at a time (4 GroupNorm cells), their two-pass statistics are block reductions, and only
-// relu(GN(conv(x))) is written - 1 pass. Plain fp32 FFMA (K = 27: no tensor-core shape).
+// here one CTA of 256 threads owns one image (4 images resident per SM), a thread 4 output pixels: the 64 output channels
+// are produced 8 at a time (4 GroupNorm cells) from the shared-memory copy of the image, their statistics are block
+// reductions, and only relu(GN(conv(x))) is written - 1 pass. Plain fp32 FFMA (K = 27: no tensor-core shape).
 namespace node {
 
 // Sum NV per-thread values over the CTA: warp shuffles, one partial per warp, warp 0 folds the partials, everyone reads
@@ -151,12 +151,14 @@ __device__ __forceinline__ void block_sum_n(float (&v)[NV], float* scratch, floa
   for (int i = 0; i < NV; ++i) v[i] = total[i];
 }
 
+constexpr int kStemThreads = 256;
+
 template <int CIN, int HIN, int WIN>
-__global__ void __launch_bounds__(((HIN - 2) * (WIN - 2) + 31) / 32 * 32, 1)
+__global__ void __launch_bounds__(kStemThreads, 4)
 k_stem_gn_relu(const float* __restrict__ x, const float* __restrict__ cw, const float* __restrict__ cb, const float* __restrict__ gamma,
                const float* __restrict__ beta, float* __restrict__ out, float eps) {
-  constexpr int HO = HIN - 2, WO = WIN - 2, NPIX = HO * WO, K = CIN * 9, NT = (NPIX + 31) / 32 * 32;
-  static_assert(NT / 32 <= 32, "one partial per warp, folded by one warp");
+  // 256 threads per image, 4 images resident per SM (their barrier phases interleave); a thread owns PPT output pixels
+  constexpr int HO = HIN - 2, WO = WIN - 2, NPIX = HO * WO, K = CIN * 9, NT = kStemThreads, PPT = (NPIX + NT - 1) / NT;
   __shared__ float s_in[CIN * HIN * WIN];
   __shared__ __align__(16) float s_w[64 * K];        // [pass of 8 channels][k][8 channels]
   __shared__ float s_b[64], s_g[64], s_be[64];
@@ -169,36 +171,49 @@ k_stem_gn_relu(const float* __restrict__ x, const float* __restrict__ cw, const 
   }
   if (tid < 64) { s_b[tid] = cb[tid]; s_g[tid] = gamma[tid]; s_be[tid] = beta[tid]; }
   __syncthreads();
-  const bool valid = tid < NPIX;
-  const int p = valid ? tid : 0, oy = p / WO, ox = p % WO;
-  float in[K];
+  int base[PPT];
+  bool valid[PPT];
 #pragma unroll
-  for (int ci = 0; ci < CIN; ++ci)
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) in[(ci * 3 + dy) * 3 + dx] = s_in[(ci * HIN + oy + dy) * WIN + ox + dx];
+  for (int q = 0; q < PPT; ++q) {
+    const int p = tid + q * NT;
+    valid[q] = p < NPIX;
+    const int pp = valid[q] ? p : 0;
+    base[q] = (pp / WO) * WIN + pp % WO;
+  }
   constexpr float inv_n = 1.0f / (float)(2 * NPIX);
 #pragma unroll 1
   for (int ps = 0; ps < 8; ++ps) {
-    float acc[8];
+    float acc[PPT][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = s_b[8 * ps + j];
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = s_b[8 * ps + j];
     const float4* w4 = reinterpret_cast<const float4*>(s_w + (size_t)ps * K * 8);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const float4 a = w4[2 * k], b = w4[2 * k + 1];
-      acc[0] = fmaf(in[k], a.x, acc[0]); acc[1] = fmaf(in[k], a.y, acc[1]); acc[2] = fmaf(in[k], a.z, acc[2]); acc[3] = fmaf(in[k], a.w, acc[3]);
-      acc[4] = fmaf(in[k], b.x, acc[4]); acc[5] = fmaf(in[k], b.y, acc[5]); acc[6] = fmaf(in[k], b.z, acc[6]); acc[7] = fmaf(in[k], b.w, acc[7]);
+      const int off = (k / 9) * HIN * WIN + ((k % 9) / 3) * WIN + k % 3;
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        const float v = s_in[base[q] + off];
+        acc[q][0] = fmaf(v, a.x, acc[q][0]); acc[q][1] = fmaf(v, a.y, acc[q][1]); acc[q][2] = fmaf(v, a.z, acc[q][2]); acc[q][3] = fmaf(v, a.w, acc[q][3]);
+        acc[q][4] = fmaf(v, b.x, acc[q][4]); acc[q][5] = fmaf(v, b.y, acc[q][5]); acc[q][6] = fmaf(v, b.z, acc[q][6]); acc[q][7] = fmaf(v, b.w, acc[q][7]);
+      }
     }
     // one round: sums and sums of squares of the 4 GroupNorm cells; E[x^2] - mean^2 is redone in two passes when a cell
     // is ill-conditioned (CTA-uniform decision: every thread sees the same totals)
     float s[8];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      s[g] = valid ? acc[2 * g] + acc[2 * g + 1] : 0.f;
-      s[4 + g] = valid ? fmaf(acc[2 * g], acc[2 * g], acc[2 * g + 1] * acc[2 * g + 1]) : 0.f;
-    }
+    for (int g = 0; g < 8; ++g) s[g] = 0.f;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (valid[q]) {
+          s[g] += acc[q][2 * g] + acc[q][2 * g + 1];
+          s[4 + g] += fmaf(acc[q][2 * g], acc[q][2 * g], acc[q][2 * g + 1] * acc[q][2 * g + 1]);
+        }
+      }
     block_sum_n<8>(s, scratch, total, NT / 32);
     bool ill = false;
 #pragma unroll
@@ -208,26 +223,28 @@ k_stem_gn_relu(const float* __restrict__ x, const float* __restrict__ cw, const 
       ill |= s[g] * s[g] > 16.0f * s[4 + g];
     }
     if (ill) {
-      float q[4];
+      float qq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float d0 = acc[2 * g] - s[g], d1 = acc[2 * g + 1] - s[g];
-        q[g] = valid ? fmaf(d0, d0, d1 * d1) : 0.f;
-      }
-      block_sum_n<4>(q, scratch, total, NT / 32);
+      for (int q = 0; q < PPT; ++q)
 #pragma unroll
-      for (int g = 0; g < 4; ++g) s[4 + g] = q[g] * inv_n;
-    }
-    if (valid) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float rstd = 1.0f / sqrtf(s[4 + g] + eps);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = 8 * ps + 2 * g + h;
-          const float r = fmaf(acc[2 * g + h] - s[g], rstd * s_g[c], s_be[c]);
-          out[((size_t)n * 64 + c) * NPIX + p] = fmaxf(r, 0.f);
+        for (int g = 0; g < 4; ++g) {
+          const float d0 = acc[q][2 * g] - s[g], d1 = acc[q][2 * g + 1] - s[g];
+          if (valid[q]) qq[g] += fmaf(d0, d0, d1 * d1);
         }
+      block_sum_n<4>(qq, scratch, total, NT / 32);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) s[4 + g] = qq[g] * inv_n;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float rstd = 1.0f / sqrtf(s[4 + g] + eps);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 8 * ps + 2 * g + h;
+        const float ga = rstd * s_g[c], be = s_be[c];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+          if (valid[q]) out[((size_t)n * 64 + c) * NPIX + tid + q * NT] = fmaxf(fmaf(acc[q][2 * g + h] - s[g], ga, be), 0.f);
       }
     }
   }
@@ -241,9 +258,9 @@ extern "C" int node_b200_stem_gn_relu(const float* x, const float* conv_w, const
   if (N < 1) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   if (CIN == 3 && HIN == 32 && WIN == 32) {
-    k_stem_gn_relu<3, 32, 32><<<N, (30 * 30 + 31) / 32 * 32, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
+    k_stem_gn_relu<3, 32, 32><<<N, kStemThreads, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
   } else if (CIN == 1 && HIN == 28 && WIN == 28) {
-    k_stem_gn_relu<1, 28, 28><<<N, (26 * 26 + 31) / 32 * 32, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
+    k_stem_gn_relu<1, 28, 28><<<N, kStemThreads, 0, st>>>(x, conv_w, conv_b, gn_w, gn_b, out, eps);
   } else {
     return (int)cudaErrorInvalidValue;      // the caller keeps its own ops
   }
