@@ -216,12 +216,15 @@ int node_b200_groupnorm_relu(const float* x, float* y, const float* gamma, const
  * as one tcgen05 kernel (fp32 contract by fp16 operand splitting, like the ODE-Net step engine). x, shortcut, out are
  * contiguous NCHW fp32 [N,64,H,W]; supported maps: 15x15, 8x8 (CIFAR), 13x13, 7x7 (MNIST) - workspace_bytes returns 0
  * otherwise and the caller keeps its own ops. prepare() packs the live conv weight [64,64,3,3] and the operand scales
- * into the workspace (once per parameter version). */
+ * into the workspace (once per parameter version). With next_gn_w / next_gn_b (the affine parameters of the FOLLOWING
+ * block's norm1, same eps; NULL to disable) the kernel writes relu(GroupNorm(out)) instead of out - the following block
+ * consumes nothing else when it has a projection shortcut (model.py:167-172). */
 int64_t node_b200_resconv_workspace_bytes(int C, int H, int W);
 int node_b200_resconv_prepare(void* workspace, int C, int H, int W, const float* conv_w, const float* gn_w, const float* gn_b,
                               void* stream);
 int node_b200_resconv_forward(void* workspace, const float* x, const float* shortcut, float* out, const float* gn_w,
-                              const float* gn_b, int N, int C, int H, int W, float eps, void* stream);
+                              const float* gn_b, const float* next_gn_w, const float* next_gn_b, int N, int C, int H, int W,
+                              float eps, void* stream);
 
 /* Callers of the hot path: the head of the reference's strided ResBlock (model.py:156-178) on the already
  * normalised activation a = relu(norm1(x)), contiguous NCHW fp32 [N,64,HI,WI]:

@@ -165,11 +165,12 @@ extern "C" int node_b200_resconv_prepare(void* workspace, int C, int H, int W, c
 }
 
 extern "C" int node_b200_resconv_forward(void* workspace, const float* x, const float* shortcut, float* out, const float* gn_w,
-                                         const float* gn_b, int N, int C, int H, int W, float eps, void* stream) {
+                                         const float* gn_b, const float* next_gn_w, const float* next_gn_b, int N, int C, int H,
+                                         int W, float eps, void* stream) {
   if (N < 1 || node_b200_resconv_workspace_bytes(C, H, W) <= 0) return (int)cudaErrorInvalidValue;
   ResConvWs w; resconv_layout(workspace, &w);
   ResConvArgs a{};
-  a.w16 = w.w16; a.scal = w.scal; a.gamma = gn_w; a.beta = gn_b; a.x = x; a.shortcut = shortcut; a.out = out; a.N = N; a.eps = eps;
+  a.w16 = w.w16; a.scal = w.scal; a.gamma = gn_w; a.beta = gn_b; a.gamma_next = next_gn_w; a.beta_next = next_gn_w != nullptr ? next_gn_b : nullptr; a.x = x; a.shortcut = shortcut; a.out = out; a.N = N; a.eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   if (H == 15) return launch_resconv_15x15(a, st);
   if (H == 8) return launch_resconv_8x8(a, st);

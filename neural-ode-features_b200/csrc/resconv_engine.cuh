@@ -14,13 +14,14 @@ struct ResConvArgs {
   const uint16_t* w16;       // [9 taps][128 rows][64 halves] weight tiles (hi rows 0..63, lo rows 64..127), SW128 image
   const float* scal;         // [0] activation scale, [1] weight scale, [2] 1 / (sa * sw)
   const float* gamma; const float* beta;
+  const float* gamma_next; const float* beta_next;   // optional: the NEXT block's norm1 - out = relu(norm1_next(conv + shortcut))
   const float* x; const float* shortcut; float* out;
   int N; float eps;
 };
 
 __host__ __device__ constexpr size_t resconv_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
   return 1024 + (size_t)kNW * kW16TileBytes + (size_t)NSLOT * 2 * A_PART + (size_t)NSLOT * NWARP * 64 * 4 +
-         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 32 * 16 + 16 * 8 + 64;
+         (size_t)NSLOT * G * 32 * 8 + (size_t)NSLOT * G * 32 * 16 + 2 * 32 * 16 + 16 * 8 + 64;
 }
 
 template <int H_, int W_, int NSLOT>
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
     sm.part = reinterpret_cast<float*>(base + o); o += (size_t)NSLOT * T::NWARP * 64 * 4;
     sm.stat = reinterpret_cast<float2*>(base + o); o += (size_t)NSLOT * T::G * 32 * 8;
     sm.aff = reinterpret_cast<float4*>(base + o); o += (size_t)NSLOT * T::G * 32 * 16;
-    sm.gnp = reinterpret_cast<float4*>(base + o); o += 32 * 16;
+    sm.gnp = reinterpret_cast<float4*>(base + o); o += 2 * 32 * 16;
     sm.tb = nullptr; sm.bias = nullptr; sm.tmapc = nullptr; sm.coef = nullptr; sm.scratch = nullptr; sm.ring = nullptr;
     sm.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
     sm.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
@@ -51,8 +52,11 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
     uint4* az = reinterpret_cast<uint4*>(base + (size_t)kNW * kW16TileBytes);   // padding rows / columns stay zero
     for (int i = tid; i < NSLOT * 2 * T::A_PART / 16; i += blockDim.x) az[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  for (int g = tid; g < 32; g += blockDim.x)
+  const bool norm_next = a.gamma_next != nullptr;
+  for (int g = tid; g < 32; g += blockDim.x) {
     sm.gnp[g] = make_float4(a.gamma[2 * g], a.gamma[2 * g + 1], a.beta[2 * g], a.beta[2 * g + 1]);
+    if (norm_next) sm.gnp[32 + g] = make_float4(a.gamma_next[2 * g], a.gamma_next[2 * g + 1], a.beta_next[2 * g], a.beta_next[2 * g + 1]);
+  }
   if (tid < 2) sm.illcond[tid] = 0u;
   if (tid == 0) {
     for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
@@ -123,13 +127,28 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
       conv_read<T, false>(sm, me, hb, x, tmem, 0, inv, true, valid);
-      if (!valid) continue;
       const size_t p0 = goff + (size_t)(32 * hb) * HW;
-      float sc[32];
+      {
+        float sc[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) sc[c] = ptx::ldg_ordered(a.shortcut + p0 + (size_t)c * HW);
+        for (int c = 0; c < 32; ++c) sc[c] = ptx::ldg_ordered(a.shortcut + p0 + (size_t)c * HW);   // padding threads: image 0, discarded
 #pragma unroll
-      for (int c = 0; c < 32; ++c) a.out[p0 + (size_t)c * HW] = x[c] + sc[c];
+        for (int c = 0; c < 32; ++c) x[c] = valid ? x[c] + sc[c] : 0.f;
+      }
+      if (norm_next) {           // kernel-uniform: the next block's GroupNorm -> ReLU on the block output (model.py:167)
+        gn_affine<T>(sm, me, hb, 1, x, valid, a.eps);
+        const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          const float4 p = af[g];
+          x[2 * g] = fmaxf(fmaf(x[2 * g], p.x, p.z), 0.f);
+          x[2 * g + 1] = fmaxf(fmaf(x[2 * g + 1], p.y, p.w), 0.f);
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a.out[p0 + (size_t)c * HW] = x[c];
+      }
     }
   }
   ptx::tc_fence_before();

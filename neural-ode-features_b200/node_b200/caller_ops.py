@@ -76,11 +76,17 @@ def _resconv_ok(norm, conv, x, shortcut):
     return native.lib().node_b200_resconv_workspace_bytes(64, int(x.shape[2]), int(x.shape[3])) > 0
 
 
-def res_conv(norm, conv, x, shortcut):
+def res_conv(norm, conv, x, shortcut, next_norm=None):
     """conv(relu(norm(x))) + shortcut for the ResBlock tail; one tcgen05 kernel when the shape is served and no gradient
-    is needed, the modules' own ops otherwise."""
+    is needed, the modules' own ops otherwise. With `next_norm` (the following block's norm1) the result is
+    relu(next_norm(.)) of that - fused into the same kernel when next_norm is a GroupNorm(32, 64) with the same eps."""
+    fuse_next = (next_norm is not None and isinstance(next_norm, nn.GroupNorm) and next_norm.weight is not None
+                 and next_norm.num_groups == 32 and next_norm.num_channels == 64 and isinstance(norm, nn.GroupNorm)
+                 and next_norm.eps == norm.eps
+                 and not (torch.is_grad_enabled() and (next_norm.weight.requires_grad or next_norm.bias.requires_grad)))
     if not _resconv_ok(norm, conv, x, shortcut):
-        return conv(torch.relu(norm(x))) + shortcut
+        out = conv(torch.relu(norm(x))) + shortcut
+        return out if next_norm is None else group_norm_relu(next_norm, out)
     x, shortcut = x.contiguous(), shortcut.contiguous()
     N, C, H, W = (int(v) for v in x.shape)
     lib = native.lib()
@@ -95,9 +101,13 @@ def res_conv(norm, conv, x, shortcut):
                                                    native.ptr(norm.bias), native.stream_ptr()), 'resconv_prepare')
         ent = _resconv_ws[key] = (buf, ver)
     out = torch.empty_like(x)
+    nw = native.ptr(next_norm.weight) if fuse_next else None
+    nb = native.ptr(next_norm.bias) if fuse_next else None
     native.check(lib.node_b200_resconv_forward(native.ptr(ent[0]), native.ptr(x), native.ptr(shortcut), native.ptr(out),
-                                               native.ptr(norm.weight), native.ptr(norm.bias), N, C, H, W, float(norm.eps),
+                                               native.ptr(norm.weight), native.ptr(norm.bias), nw, nb, N, C, H, W, float(norm.eps),
                                                native.stream_ptr()), 'resconv_forward')
+    if next_norm is not None and not fuse_next:
+        return group_norm_relu(next_norm, out)
     return out
 
 

@@ -133,16 +133,18 @@ class ResBlock(nn.Module):
         out = group_norm_relu(self.norm1, x) if isinstance(self.norm1, nn.GroupNorm) else self.relu(self.norm1(x))
         return self.forward_act(out, x)
 
-    def forward_act(self, out, x=None):
-        """The block after its first normalisation: out = relu(norm1(x)) (x is only needed for an identity shortcut)."""
+    def forward_act(self, out, x=None, next_norm=None):
+        """The block after its first normalisation: out = relu(norm1(x)) (x is only needed for an identity shortcut).
+        With `next_norm` (the following block's norm1) the result is relu(next_norm(block output))."""
         if self.downsample is not None and isinstance(self.norm1, nn.GroupNorm):
             out, shortcut = res_head(self.norm1, self.conv1, self.downsample, out)   # one kernel when served (caller_ops)
         else:
             shortcut = x if self.downsample is None else self.downsample(out)
             out = self.conv1(out)
         if isinstance(self.norm2, nn.GroupNorm):
-            return res_conv(self.norm2, self.conv2, out, shortcut)        # one kernel when served (caller_ops)
-        return self.conv2(self.relu(self.norm2(out))) + shortcut
+            return res_conv(self.norm2, self.conv2, out, shortcut, next_norm)        # one kernel when served (caller_ops)
+        out = self.conv2(self.relu(self.norm2(out))) + shortcut
+        return out if next_norm is None else group_norm_relu(next_norm, out)
 
 
 def _conv1x1(cin, cout, stride):
@@ -195,7 +197,10 @@ class ResDownsample(_Wrapped):
         if isinstance(rb1.norm1, nn.GroupNorm) and rb1.downsample is not None:
             # conv0's raw output feeds nothing but rb1.norm1 (the shortcut branches off AFTER the normalisation,
             # model.py:170-172): stem convolution, GroupNorm and ReLU in one pass (caller_ops.stem_gn_relu)
-            return rb2(rb1.forward_act(stem_gn_relu(conv0, rb1.norm1, x)))
+            a1 = stem_gn_relu(conv0, rb1.norm1, x)
+            if isinstance(rb2.norm1, nn.GroupNorm) and rb2.downsample is not None:     # rb2 too reads only relu(norm1(.))
+                return rb2.forward_act(rb1.forward_act(a1, next_norm=rb2.norm1))
+            return rb2(rb1.forward_act(a1))
         return rb2(rb1(conv0(x)))
 
 

@@ -72,7 +72,7 @@ def _declare(lib):
     lib.node_b200_resconv_workspace_bytes.argtypes = [_i, _i, _i]
     lib.node_b200_resconv_workspace_bytes.restype = _i64
     lib.node_b200_resconv_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]
-    lib.node_b200_resconv_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
+    lib.node_b200_resconv_forward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
     lib.node_b200_convs2_workspace_bytes.argtypes = [_i, _i, _i]
     lib.node_b200_convs2_workspace_bytes.restype = _i64
     lib.node_b200_convs2_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]

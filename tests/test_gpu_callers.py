@@ -73,6 +73,11 @@ def test_resblock_tail_matches_aten(native_lib, shape):
         got = caller_ops.res_conv(norm, conv, x, sc)
         torch.cuda.synchronize()
         assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+        nxt = nn.GroupNorm(32, 64).to(DEV)
+        nxt.weight.uniform_(0.5, 1.5); nxt.bias.uniform_(-0.5, 0.5)
+        ref_n = torch.relu(nxt(ref))                # the following block's norm1 -> ReLU fused into the same kernel
+        got_n = caller_ops.res_conv(norm, conv, x, sc, next_norm=nxt)
+        assert float((got_n - ref_n).abs().max()) <= 3e-5 * float(ref_n.abs().max())
         conv.weight.mul_(2.0)                       # in-place parameter update: the weight tiles are re-packed
         ref2 = conv(torch.relu(norm(x))) + sc
         got2 = caller_ops.res_conv(norm, conv, x, sc)
