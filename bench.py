@@ -235,6 +235,49 @@ def train_step_rate(dev, batch, steps, warmup):
                      'downsampler / classifier autograd in PyTorch fp32')
 
 
+def other_configs(dev):
+    """The other configurations of SURVEY 8(d), measured briefly beside the headline (device-timed, inputs resident):
+    cfg4 ICMR feature extraction (10 output times, dense output costs no extra evaluations), the `one-shot`
+    downsampler (16x16 maps), and n_filters=256 (paper CIFAR setting: served by the generic route, K2-K6 kernels +
+    PyTorch dynamics)."""
+    import numpy as np
+    from node_b200 import models, solver
+    out = {}
+
+    def rate(fn, batch, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return batch * reps / (a.elapsed_time(b) * 1e-3)
+
+    with torch.no_grad():
+        torch.manual_seed(0)
+        net = models.ODENet(3, n_filters=64, downsample='residual', tol=TOL).eval().to(dev)
+        net.to_features_extractor()
+        net.odeblock.t1 = np.linspace(0, 1, 10).tolist()
+        x = torch.rand(2220, 3, 32, 32, device=dev)
+        r = rate(lambda: net(x), 2220)
+        out['cfg4_features_t10'] = dict(images_per_s=r, batch=2220, output_times=10, nfe=solver.last_stats.get('nfe'),
+                                        route=solver.last_stats.get('route'), features_shape=list(net(x).shape))
+        torch.manual_seed(0)
+        net = models.ODENet(3, n_filters=64, downsample='one-shot', tol=TOL).eval().to(dev)
+        x = torch.rand(1024, 3, 32, 32, device=dev)
+        r = rate(lambda: net(x), 1024)
+        out['one_shot_16x16'] = dict(images_per_s=r, batch=1024, nfe=solver.last_stats.get('nfe'), route=solver.last_stats.get('route'))
+        torch.manual_seed(0)
+        net = models.ODENet(3, n_filters=256, downsample='residual', tol=TOL).eval().to(dev)
+        x = torch.rand(256, 3, 32, 32, device=dev)
+        r = rate(lambda: net(x), 256, reps=3)
+        out['n_filters_256'] = dict(images_per_s=r, batch=256, nfe=solver.last_stats.get('nfe'), route=solver.last_stats.get('route'))
+    return out
+
+
 def small_batch_latency(net, dev, batch=128, reps=30):
     """ODE block at the reference's default batch (train.py:207), where a solve is bound by its ~35 launches:
     direct enqueue against CUDA-graph replay of the same launch sequence (north_star 3)."""
@@ -413,6 +456,7 @@ def main():
     if world == 1:
         line['roofline_rk'] = rk_roofline(dev, pk)
         line['latency_b128'] = small_batch_latency(net, dev)
+        line['other_configs'] = other_configs(dev)
         if args.train_batch > 0:
             line['train_step'] = train_step_rate(dev, args.train_batch, max(2, args.steps // 2), 2)
         if not args.skip_cpu:
