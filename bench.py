@@ -363,10 +363,13 @@ def main():
 
     launches = [0]
 
+    from node_b200 import caller_ops
+
     def step_resident():
+        c0 = caller_ops.launches
         with torch.no_grad():
             net(x_dev)
-        launches[0] += solver.last_stats.get('launches', 0)
+        launches[0] += solver.last_stats.get('launches', 0) + (caller_ops.launches - c0)
 
     # End to end: every step copies ITS input batch from pinned host memory and reads ITS logits back to the host. The
     # input of step i+1 is prefetched on a copy stream while step i computes (the usual pinned-memory data-loader pattern:

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
 #pragma unroll
         for (int c = 0; c < 32; ++c) x[c] = 0.f;
       }
-      gn_affine<T>(sm, me, hb, 0, x, valid, a.eps);
-      affine_to_A<T>(sm, me, hb, x, sa, valid, true);
+      gn_affine<T>(sm, me, hb, 0, x, valid, a.eps, sa);
+      affine_to_A<T>(sm, me, hb, x, valid, true);
     }
     conv_run<T, NSLOT>(sm, me, jb, a.w16, tmem, njob, nfull, timeout, true);
 #pragma unroll 1

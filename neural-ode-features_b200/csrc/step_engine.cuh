@@ -238,7 +238,8 @@ __device__ __forceinline__ void gn_stats(const StepSmem& sm, const Who& me, int 
 // mean^2 > kGnIllCond * var raises the slot's flag and the whole slot repeats the statistics with the two-pass scheme
 // of the reference's native_group_norm (gn_reduce with squared deviations) - rare, slot-uniform, deterministic.
 template <class T>
-__device__ __forceinline__ void gn_affine(const StepSmem& sm, const Who& me, int hb, int n, const float (&x)[32], bool valid, float eps) {
+__device__ __forceinline__ void gn_affine(const StepSmem& sm, const Who& me, int hb, int n, const float (&x)[32], bool valid, float eps,
+                                          float post = 1.0f) {
   constexpr float inv_n = 1.0f / (float)(kCpg * T::HW);
   float* part = sm.part + (me.slot * T::NWARP + me.warp) * 64;
 #pragma unroll
@@ -267,8 +268,8 @@ __device__ __forceinline__ void gn_affine(const StepSmem& sm, const Who& me, int
   auto publish = [&](float mean, float var) {
     const float rstd = 1.0f / sqrtf(var + eps);
     const float4 p = sm.gnp[n * 32 + 16 * hb + fg];
-    const float a0 = rstd * p.x, a1 = rstd * p.y;
-    sm.aff[(me.slot * T::G + fimg) * 32 + 16 * hb + fg] = make_float4(a0, a1, p.z - a0 * mean, p.w - a1 * mean);
+    const float a0 = rstd * p.x, a1 = rstd * p.y;      // `post` (a power of two or +-1: exact) is the operand scale / time sign
+    sm.aff[(me.slot * T::G + fimg) * 32 + 16 * hb + fg] = make_float4(a0 * post, a1 * post, (p.z - a0 * mean) * post, (p.w - a1 * mean) * post);
   };
   if (folder) {
     const float* pp = sm.part + me.slot * T::NWARP * 64;
@@ -332,8 +333,7 @@ __device__ __forceinline__ void gn_affine(const StepSmem& sm, const Who& me, int
 // relu(a*x + b) * scale (sm.aff of this thread's image) split into fp16 hi + lo and written into this position's row
 // of the A image (k-chunks [4*hb, 4*hb+4)).
 template <class T>
-__device__ __forceinline__ void affine_to_A(const StepSmem& sm, const Who& me, int hb, const float (&x)[32], float scale, bool valid,
-                                            bool split) {
+__device__ __forceinline__ void affine_to_A(const StepSmem& sm, const Who& me, int hb, const float (&x)[32], bool valid, bool split) {
   const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
   const uint32_t row = sm.abase + me.slot * 2 * T::A_PART + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
 #pragma unroll
@@ -343,8 +343,8 @@ __device__ __forceinline__ void affine_to_A(const StepSmem& sm, const Who& me, i
     for (int j = 0; j < 4; ++j) {
       const int g = kc * 4 + j;
       const float4 p = af[g];
-      const float r0 = fmaxf(fmaf(x[2 * g], p.x, p.z), 0.f) * scale;
-      const float r1 = fmaxf(fmaf(x[2 * g + 1], p.y, p.w), 0.f) * scale;
+      const float r0 = fmaxf(fmaf(x[2 * g], p.x, p.z), 0.f);         // the operand scale is folded into p (gn_affine `post`)
+      const float r1 = fmaxf(fmaf(x[2 * g + 1], p.y, p.w), 0.f);
       const __half2 h = __floats2half2_rn(r0, r1);
       const float2 hf = __half22float2(h);
       const __half2 l = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
@@ -792,9 +792,9 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
             }
           }
           NODE_STAMP(1);
-          gn_affine<T>(sm, me, hb, 0, x, valid, a.eps);
+          gn_affine<T>(sm, me, hb, 0, x, valid, a.eps, w.scal[0]);
           NODE_STAMP(2);
-          affine_to_A<T>(sm, me, hb, x, w.scal[0], valid, split);
+          affine_to_A<T>(sm, me, hb, x, valid, split);
           NODE_STAMP(3);
         }
         conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
@@ -805,9 +805,9 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
         for (int hb = 0; hb < 2; ++hb) {
           conv_read<T>(sm, me, hb, x, tmem, 0, w.scal[4], split, valid);
           NODE_STAMP(5);
-          gn_affine<T>(sm, me, hb, 1, x, valid, a.eps);
+          gn_affine<T>(sm, me, hb, 1, x, valid, a.eps, w.scal[1]);
           NODE_STAMP(6);
-          affine_to_A<T>(sm, me, hb, x, w.scal[1], valid, split);
+          affine_to_A<T>(sm, me, hb, x, valid, split);
           NODE_STAMP(7);
         }
         make_tb<T>(sm, me, 1, t);
@@ -819,15 +819,15 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
         for (int hb = 0; hb < 2; ++hb) {
           conv_read<T>(sm, me, hb, x, tmem, 1, w.scal[5], split, valid);
           NODE_STAMP(9);
-          gn_affine<T>(sm, me, hb, 2, x, valid, a.eps);
+          gn_affine<T>(sm, me, hb, 2, x, valid, a.eps, a.tsign);
           NODE_STAMP(10);
           {
             const float4* af = sm.aff + (me.slot * T::G + min(me.img_l, T::G - 1)) * 32 + 16 * hb;
 #pragma unroll
             for (int g = 0; g < 16; ++g) {
               const float4 p = af[g];
-              x[2 * g] = fmaf(x[2 * g], p.x, p.z) * a.tsign;
-              x[2 * g + 1] = fmaf(x[2 * g + 1], p.y, p.w) * a.tsign;
+              x[2 * g] = fmaf(x[2 * g], p.x, p.z);              // the time sign is folded into p
+              x[2 * g + 1] = fmaf(x[2 * g + 1], p.y, p.w);
             }
           }
           if (!valid) continue;

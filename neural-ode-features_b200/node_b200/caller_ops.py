@@ -8,6 +8,8 @@ import torch.nn as nn
 
 from . import native
 
+launches = 0        # kernels launched by this module (bench.py's gpu_launches)
+
 
 def _fusable(norm, x):
     if not isinstance(norm, nn.GroupNorm) or norm.weight is None or norm.bias is None:
@@ -32,6 +34,8 @@ def group_norm_relu(norm, x, relu=True):
                                                N, C, int(norm.num_groups), x.numel() // (N * C), float(norm.eps),
                                                1 if relu else 0, native.stream_ptr())
     native.check(err, 'groupnorm_relu')
+    global launches
+    launches += 1
     return y
 
 
@@ -106,6 +110,8 @@ def res_conv(norm, conv, x, shortcut, next_norm=None):
     native.check(lib.node_b200_resconv_forward(native.ptr(ent[0]), native.ptr(x), native.ptr(shortcut), native.ptr(out),
                                                native.ptr(norm.weight), native.ptr(norm.bias), nw, nb, N, C, H, W, float(norm.eps),
                                                native.stream_ptr()), 'resconv_forward')
+    global launches
+    launches += 1
     if next_norm is not None and not fuse_next:
         return group_norm_relu(next_norm, out)
     return out
@@ -155,6 +161,8 @@ def res_head(norm, conv, down, a):
     sc = torch.empty_like(c)
     native.check(lib.node_b200_convs2_forward(native.ptr(ent[0]), native.ptr(a), native.ptr(c), native.ptr(sc), N, C, HI, WI,
                                               native.stream_ptr()), 'convs2_forward')
+    global launches
+    launches += 1
     return c, sc
 
 
@@ -182,4 +190,6 @@ def stem_gn_relu(conv, norm, x):
     native.check(native.lib().node_b200_stem_gn_relu(native.ptr(x), native.ptr(conv.weight), native.ptr(conv.bias), native.ptr(norm.weight),
                                                      native.ptr(norm.bias), native.ptr(out), N, CIN, HIN, WIN, float(norm.eps),
                                                      native.stream_ptr()), 'stem_gn_relu')
+    global launches
+    launches += 1
     return out
