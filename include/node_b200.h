@@ -246,6 +246,12 @@ int node_b200_convs2_forward(void* workspace, const float* act, float* c_out, fl
 int node_b200_stem_gn_relu(const float* x, const float* conv_w, const float* conv_b, const float* gn_w, const float* gn_b,
                            float* out, int N, int CIN, int HIN, int WIN, float eps, void* stream);
 
+/* Callers of the hot path: the reference's FCClassifier (model.py:231-250) - GroupNorm(32, 64) -> ReLU ->
+ * global average pool -> Linear(64, n_out) on a contiguous NCHW fp32 [N,64,HW] tensor in one pass; lin_w == NULL stops
+ * after the pool (feature mode, model.py:39-40) and writes [N,64]. No dropout (inference). */
+int node_b200_head(const float* x, const float* gn_w, const float* gn_b, const float* lin_w, const float* lin_b, float* out,
+                   int64_t N, int C, int HW, int n_out, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

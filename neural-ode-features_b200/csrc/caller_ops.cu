@@ -266,3 +266,53 @@ extern "C" int node_b200_stem_gn_relu(const float* x, const float* conv_w, const
   }
   return (int)cudaGetLastError();
 }
+
+// ---- classifier head: GroupNorm(32, 64) -> ReLU -> global average pool (-> Linear(64, n_out)) in one pass ----------------
+// The reference's FCClassifier (model.py:231-250), also applied per output time in feature mode (model.py:39-40). One
+// 256-thread CTA per image: thread t owns channel t / 4 and a quarter of its pixels, the 8 threads of a GroupNorm cell
+// and the 4 threads of a channel are neighbours in a warp (shuffles only), two-pass statistics, the 64 pooled values
+// meet in shared memory for the optional linear layer. Reads the [N,64,HW] tensor once, writes [N,64] or [N,n_out].
+namespace node {
+
+__global__ void __launch_bounds__(256) k_head(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ out, int HW,
+                                              int n_out, float eps) {
+  __shared__ float pooled[64];
+  const int tid = threadIdx.x, c = tid >> 2, q = tid & 3;
+  const float* xc = x + ((size_t)blockIdx.x * 64 + c) * HW;
+  float s = 0.f;
+  for (int p = q; p < HW; p += 4) s += xc[p];
+  s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+  const float inv_n = 1.0f / (float)(2 * HW);
+  const float mean = s * inv_n;
+  float d2 = 0.f;
+  for (int p = q; p < HW; p += 4) { const float d = xc[p] - mean; d2 = fmaf(d, d, d2); }      // second pass: L1 / L2 hits
+  d2 += __shfl_xor_sync(0xffffffffu, d2, 1); d2 += __shfl_xor_sync(0xffffffffu, d2, 2); d2 += __shfl_xor_sync(0xffffffffu, d2, 4);
+  const float rstd = 1.0f / sqrtf(d2 * inv_n + eps);
+  const float a = rstd * gamma[c], b = beta[c] - mean * a;
+  float acc = 0.f;
+  for (int p = q; p < HW; p += 4) acc += fmaxf(fmaf(xc[p], a, b), 0.f);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  const float avg = acc / (float)HW;
+  if (lw == nullptr) {
+    if (q == 0) out[(size_t)blockIdx.x * 64 + c] = avg;
+    return;
+  }
+  if (q == 0) pooled[c] = avg;
+  __syncthreads();
+  if (tid < n_out) {
+    float r = lb != nullptr ? lb[tid] : 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) r = fmaf(pooled[k], lw[tid * 64 + k], r);
+    out[(size_t)blockIdx.x * n_out + tid] = r;
+  }
+}
+
+}  // namespace node
+
+extern "C" int node_b200_head(const float* x, const float* gn_w, const float* gn_b, const float* lin_w, const float* lin_b, float* out,
+                              int64_t N, int C, int HW, int n_out, float eps, void* stream) {
+  if (N < 1 || N > 0x7fffffffLL || C != 64 || HW < 1 || (lin_w != nullptr && (n_out < 1 || n_out > 256))) return (int)cudaErrorInvalidValue;
+  node::k_head<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(x, gn_w, gn_b, lin_w, lin_b, out, HW, n_out, eps);
+  return (int)cudaGetLastError();
+}

@@ -193,3 +193,36 @@ def stem_gn_relu(conv, norm, x):
     global launches
     launches += 1
     return out
+
+
+# ---- fused classifier head: GroupNorm -> ReLU -> global average pool (-> Linear) (csrc/caller_ops.cu k_head) ---------------
+
+def head(seq, x):
+    """FCClassifier.module (model.py:231-250) applied to x: one CUDA pass when the layer list is exactly
+    [GroupNorm(32, 64), ReLU, AdaptiveAvgPool2d(1), (Dropout in eval mode,) Flatten, Linear(64, k) or an empty Sequential]
+    and no gradient is needed; run_sequential otherwise."""
+    mods = [m for m in seq.children() if not (isinstance(m, nn.Dropout) and not m.training)]
+    ok = (len(mods) == 5 and isinstance(mods[0], nn.GroupNorm) and isinstance(mods[1], nn.ReLU)
+          and isinstance(mods[2], nn.AdaptiveAvgPool2d) and mods[2].output_size in (1, (1, 1)) and type(mods[3]).__name__ == 'Flatten'
+          and (isinstance(mods[4], nn.Linear) or (type(mods[4]) is nn.Sequential and len(mods[4]) == 0)))
+    norm = mods[0] if ok else None
+    if ok:
+        lin = mods[4] if isinstance(mods[4], nn.Linear) else None
+        ok = (norm.weight is not None and norm.num_groups == 32 and norm.num_channels == 64 and x.is_cuda and x.dtype == torch.float32
+              and x.dim() == 4 and x.shape[1] == 64 and x.shape[0] > 0
+              and (lin is None or (lin.in_features == 64 and lin.out_features <= 256 and lin.weight.dtype == torch.float32))
+              and not (torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad
+                                                    or (lin is not None and lin.weight.requires_grad))))
+    if not ok:
+        return run_sequential(seq, x)
+    x = x.contiguous()
+    N, HW = int(x.shape[0]), int(x.shape[2] * x.shape[3])
+    n_out = lin.out_features if lin is not None else 64
+    out = torch.empty((N, n_out), dtype=x.dtype, device=x.device)
+    lw = native.ptr(lin.weight.contiguous()) if lin is not None else None
+    lb = native.ptr(lin.bias) if lin is not None and lin.bias is not None else None
+    native.check(native.lib().node_b200_head(native.ptr(x), native.ptr(norm.weight), native.ptr(norm.bias), lw, lb, native.ptr(out),
+                                             N, 64, HW, n_out, float(norm.eps), native.stream_ptr()), 'head')
+    global launches
+    launches += 1
+    return out

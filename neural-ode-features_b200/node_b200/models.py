@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from .solver import odeint, odeint_adjoint
-from .caller_ops import group_norm_relu, res_conv, res_head, run_sequential, stem_gn_relu
+from .caller_ops import group_norm_relu, head, res_conv, res_head, run_sequential, stem_gn_relu
 
 
 def _norm_factory(kind='group'):
@@ -246,6 +246,9 @@ class FCClassifier(_Wrapped):
             layers.append(nn.Dropout(dropout))
         layers += [Flatten(), nn.Linear(in_ch, out)]
         self.module = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return head(self.module, x)          # GroupNorm -> ReLU -> pool -> linear in one pass when served (caller_ops)
 
 
 _DOWNSAMPLERS = {

@@ -33,7 +33,7 @@ EXPORTS = (
     'node_b200_fused_ctl', 'node_b200_vjp_workspace_bytes', 'node_b200_odefunc_vjp', 'node_b200_wgrad',
     'node_b200_vjp_buffer', 'node_b200_groupnorm_relu', 'node_b200_resconv_workspace_bytes', 'node_b200_resconv_prepare',
     'node_b200_resconv_forward', 'node_b200_convs2_workspace_bytes', 'node_b200_convs2_prepare', 'node_b200_convs2_forward',
-    'node_b200_stem_gn_relu',
+    'node_b200_stem_gn_relu', 'node_b200_head',
 )
 
 _lib = None
@@ -78,6 +78,7 @@ def _declare(lib):
     lib.node_b200_convs2_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
     lib.node_b200_convs2_forward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
     lib.node_b200_stem_gn_relu.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
+    lib.node_b200_head.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp]
 
 
 def lib():

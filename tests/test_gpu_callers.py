@@ -123,3 +123,26 @@ def test_stem_conv_groupnorm_relu_matches_aten(native_lib, shape):
         torch.cuda.synchronize()
         assert got.shape == ref.shape
         assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('features', [False, True])
+@pytest.mark.parametrize('shape', [(37, 64, 8, 8), (5, 64, 7, 7), (3, 64, 16, 16), (2, 64, 6, 6)])
+def test_classifier_head_matches_aten(native_lib, shape, features):
+    """FCClassifier (model.py:231-250) - GroupNorm -> ReLU -> average pool -> Linear, and the feature-mode variant that
+    stops after the pool (model.py:39-40, to_features_extractor) - in one pass."""
+    from node_b200 import models, caller_ops
+    torch.manual_seed(5)
+    clf = models.FCClassifier(64, 10, dropout=0.5).eval().to(DEV)
+    if features:
+        clf.module[-1] = nn.Sequential()
+    with torch.no_grad():
+        clf.module[0].weight.uniform_(0.5, 1.5)
+        clf.module[0].bias.uniform_(-0.5, 0.5)
+        x = torch.randn(shape, device=DEV) * 1.5 + 0.3
+        ref = clf.module(x)
+        c0 = caller_ops.launches
+        got = clf(x)
+        torch.cuda.synchronize()
+        assert caller_ops.launches == c0 + 1                 # the fused kernel ran
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
