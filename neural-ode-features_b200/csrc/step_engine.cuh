@@ -454,7 +454,14 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
   if (lead && blockIdx.x == 0 && nth < 256) g_step_dbg[(s * 256 + nth) * 4 + 1] = clock64();
 #endif
   ptx::tc_fence_after();
+  // Descriptors as (low word + compile-time constant, constant high word): the start-address field is the low 14 bits
+  // (shared memory < 256 KiB, 16-byte units), so a tap, an M tile, a K step or the lo part is ONE 32-bit add on the low
+  // word - the leader shares its scheduler with busy worker warps, every instruction it does not issue shortens the job.
   const uint32_t abase = sm.abase + s * 2 * T::A_PART + T::HALO * 16;
+  const uint32_t a_lo0 = ((abase & 0x3FFFFu) >> 4) | (((uint32_t)T::LBO >> 4) << 16);
+  constexpr uint32_t a_hiw = (128u >> 4) | (1u << 14);                      // SBO = 128 B, descriptor version 1
+  constexpr uint32_t b_hiw = (1024u >> 4) | (1u << 14) | (2u << 29);        // SBO = 1024 B, version 1, SWIZZLE_128B
+  auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
     const uint32_t tile = job * 9 + tap, slot = tile % kNW;
@@ -467,7 +474,8 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
 #endif
     ptx::tc_fence_after();
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
-    const uint64_t b0 = ptx::make_desc_sw128(sm.wring + slot * kW16TileBytes);
+    const uint32_t a_tap = a_lo0 + (uint32_t)off;                            // never borrows: the image starts HALO rows in
+    const uint32_t b_lo0 = ((sm.wring + slot * kW16TileBytes) & 0x3FFFFu) >> 4;
 #ifdef NODE_STEP_DEBUG
     const long long q2 = clock64();
 #endif
@@ -475,14 +483,13 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
 #pragma unroll
       for (int mt = 0; mt < T::MT; ++mt) {
         const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
-        const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-          const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
+          const uint64_t a_hi = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO) >> 4), a_hiw);
+          const uint64_t bk = pack(b_lo0 + (uint32_t)((ks * 32) >> 4), b_hiw);
           const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
           if (split) {
-            const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
+            const uint64_t a_lo = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO + T::A_PART) >> 4), a_hiw);
             ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);   // a_hi * [w_hi ; w_lo] -> columns [0,64) and [64,128)
             ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);       // a_lo * w_hi         -> columns [0,64)
           } else {
