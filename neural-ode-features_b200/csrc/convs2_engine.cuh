@@ -174,17 +174,21 @@ __global__ void __launch_bounds__(Tile<HO, WO>::P, 1) k_convs2(const ConvS2Args 
           else { ps = q < 2 ? 0 : 1; bi = 0; bj = q == 0 ? -1 : 0; }
           const bool shortcut = lt == 9;
           const int off = bi * T::Wp + bj;
-          const uint64_t b0 = ptx::make_desc_sw128(wring + slot * kW16TileBytes);
+          // descriptors as low-word adds (see issue_conv_job in step_engine.cuh)
+          constexpr uint32_t a_hiw = (128u >> 4) | (1u << 14), b_hiw = (1024u >> 4) | (1u << 14) | (2u << 29);
+          auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+          const uint32_t a_tap = ((((planes + (uint32_t)ps * 2 * T::A_PART + (uint32_t)(T::HALO * 16)) & 0x3FFFFu) >> 4) |
+                                  (((uint32_t)T::LBO >> 4) << 16)) + (uint32_t)off;
+          const uint32_t b_lo0 = ((wring + slot * kW16TileBytes) & 0x3FFFFu) >> 4;
           if (lead) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               const uint32_t d = tmem + (uint32_t)(mt * 256 + (shortcut ? 128 : 0));
-              const uint32_t arow = planes + (uint32_t)ps * 2 * T::A_PART + (uint32_t)((T::HALO + mt * 128 + off) * 16);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-                const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
-                const uint64_t bk = b0 + (uint64_t)((ks * 32) >> 4);
+                const uint64_t a_hi = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO) >> 4), a_hiw);
+                const uint64_t a_lo = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO + T::A_PART) >> 4), a_hiw);
+                const uint64_t bk = pack(b_lo0 + (uint32_t)((ks * 32) >> 4), b_hiw);
                 const uint32_t first = ((lt == 0 || shortcut) && ks == 0) ? 0u : 1u;
                 ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);
                 ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);
