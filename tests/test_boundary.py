@@ -119,3 +119,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(native, 'LIB_PATH', '/nonexistent/libnode_b200.so')
     with pytest.raises(RuntimeError, match='no CPU or PyTorch fallback'):
         native.lib()
+
+
+def test_caller_modules_keep_the_reference_ops_off_the_gpu_or_with_gradients():
+    """node_b200.models routes the callers' hot spots to CUDA kernels only for CUDA tensors without autograd; on the CPU
+    (and for training) ResDownsample / FCClassifier are the reference's PyTorch ops (model.py:119-178, 231-250)."""
+    from node_b200 import models
+    torch.manual_seed(0)
+    for name in ('residual', 'convolution', 'minimal', 'one-shot'):
+        net = models.ODENet(3, n_filters=64, downsample=name, tol=1e-3).eval()
+        x = torch.rand(2, 3, 32, 32)
+        with torch.no_grad():
+            got = net.downsample(x)
+            ref = net.downsample.module(x)                 # plain nn.Sequential forward
+            assert torch.equal(got, ref)
+            logits = net.classifier(got)
+            assert torch.equal(logits, net.classifier.module(got))
+    net = models.ODENet(3, n_filters=64, downsample='residual', tol=1e-3).train()
+    x = torch.rand(2, 3, 32, 32, requires_grad=True)
+    h = net.downsample(x)
+    net.classifier(h).sum().backward()
+    assert x.grad is not None and net.downsample.module[1].conv1.weight.grad is not None
