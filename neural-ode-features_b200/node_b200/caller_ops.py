@@ -3,6 +3,8 @@
 
 Used by `node_b200.models` for inference (no autograd graph); with gradients enabled the modules run their own
 PyTorch ops, exactly as in the reference. The module tree - and so the state_dict keys - is unchanged."""
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -97,13 +99,16 @@ def res_conv(norm, conv, x, shortcut, next_norm=None):
     key = (id(conv), id(norm), str(x.device), H, W)
     ent = _resconv_ws.get(key)
     ver = (conv.weight.data_ptr(), conv.weight._version, norm.weight.data_ptr(), norm.weight._version, norm.bias._version)
+    live = (conv.weight, norm.weight, norm.bias)
+    if ent is not None and not all(r() is p for r, p in zip(ent[2], live)):      # id() reused by a new module
+        ent = None
     if ent is None or ent[1] != ver:
         if len(_resconv_ws) > 32:
             _resconv_ws.clear()
         buf = ent[0] if ent is not None else torch.zeros(lib.node_b200_resconv_workspace_bytes(C, H, W), dtype=torch.uint8, device=x.device)
         native.check(lib.node_b200_resconv_prepare(native.ptr(buf), C, H, W, native.ptr(conv.weight), native.ptr(norm.weight),
                                                    native.ptr(norm.bias), native.stream_ptr()), 'resconv_prepare')
-        ent = _resconv_ws[key] = (buf, ver)
+        ent = _resconv_ws[key] = (buf, ver, [weakref.ref(p) for p in live])
     out = torch.empty_like(x)
     nw = native.ptr(next_norm.weight) if fuse_next else None
     nb = native.ptr(next_norm.bias) if fuse_next else None
@@ -150,13 +155,16 @@ def res_head(norm, conv, down, a):
     ent = _convs2_ws.get(key)
     ver = (conv.weight.data_ptr(), conv.weight._version, down.weight.data_ptr(), down.weight._version, norm.weight._version,
            norm.bias._version)
+    live = (conv.weight, down.weight, norm.weight, norm.bias)
+    if ent is not None and not all(r() is p for r, p in zip(ent[2], live)):      # id() reused by a new module
+        ent = None
     if ent is None or ent[1] != ver:
         if len(_convs2_ws) > 32:
             _convs2_ws.clear()
         buf = ent[0] if ent is not None else torch.zeros(lib.node_b200_convs2_workspace_bytes(C, HI, WI), dtype=torch.uint8, device=a.device)
         native.check(lib.node_b200_convs2_prepare(native.ptr(buf), C, HI, WI, native.ptr(conv.weight), native.ptr(down.weight),
                                                   native.ptr(norm.weight), native.ptr(norm.bias), native.stream_ptr()), 'convs2_prepare')
-        ent = _convs2_ws[key] = (buf, ver)
+        ent = _convs2_ws[key] = (buf, ver, [weakref.ref(p) for p in live])
     c = torch.empty((N, C, HO, WO), dtype=a.dtype, device=a.device)
     sc = torch.empty_like(c)
     native.check(lib.node_b200_convs2_forward(native.ptr(ent[0]), native.ptr(a), native.ptr(c), native.ptr(sc), N, C, HI, WI,

@@ -167,14 +167,19 @@ class FusedWorkspace(object):
         self.sums = self.buf[off:off + 8 * 2 * L['max_seg']].view(torch.float64)
 
     def prepare(self, params):
+        # (address, version) alone can repeat when a model is freed and another one is built in the same process
+        # (evaluate.py walks over runs): the weak references pin the identity of the live nn.Parameters as well.
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if key == self.param_key:
+        refs = getattr(self, 'param_refs', None)
+        same = refs is not None and len(refs) == len(params) and all(r() is p for r, p in zip(refs, params))
+        if key == self.param_key and same:
             return
         N, C, H, W = self.shape
         err = native.lib().node_b200_fused_prepare(native.ptr(self.buf), C, H, W, *[native.ptr(p) for p in params],
                                                   1e-5, native.stream_ptr())
         native.check(err, 'fused_prepare')
         self.param_key = key
+        self.param_refs = [weakref.ref(p) for p in params]
         self.param_key_fresh = True
 
 

@@ -146,3 +146,31 @@ def test_classifier_head_matches_aten(native_lib, shape, features):
         assert caller_ops.launches == c0 + 1                 # the fused kernel ran
         assert got.shape == ref.shape
         assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_weight_tile_caches_follow_the_live_parameters(native_lib, monkeypatch):
+    """Models built, used and freed one after the other in one process (evaluate.py walks over runs): the packed weight
+    tiles must always belong to the live parameters, also when addresses / ids are recycled."""
+    import gc
+    from node_b200 import models, caller_ops
+    torch.backends.cudnn.allow_tf32 = False
+    x = torch.rand(8, 3, 32, 32, device=DEV)
+    outs = []
+    for seed in (0, 1, 2, 1):
+        torch.manual_seed(seed)
+        net = models.ODENet(3, n_filters=64, downsample='residual', tol=1e-3).eval().to(DEV)
+        with torch.no_grad():
+            got = net(x)
+            with monkeypatch.context() as m:
+                m.setattr(caller_ops, '_fusable', lambda norm, x: False)
+                m.setattr(caller_ops, '_resconv_ok', lambda *a: False)
+                m.setattr(caller_ops, '_convs2_ok', lambda *a: False)
+                m.setattr(caller_ops, '_stem_ok', lambda *a: False)
+                plain_down = net.downsample(x)
+            assert float((net.downsample(x) - plain_down).abs().max()) <= 1e-4 * float(plain_down.abs().max())
+        outs.append(got.clone())
+        del net
+        gc.collect()
+        torch.cuda.empty_cache()
+    assert torch.equal(outs[1], outs[3])                     # same seed, same weights, same logits
+    assert not torch.equal(outs[0], outs[1])
