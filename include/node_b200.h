@@ -137,7 +137,7 @@ int node_b200_interp_eval(const node_ctl_t* ctl, int dtype, const double* t_out,
 /* Bytes of workspace the fused solver needs for a [N,C,H,W] shard. Host function. */
 int64_t node_b200_fused_workspace_bytes(int N, int C, int H, int W);
 
-/* Pre-arrange the live parameters for the kernels: 3xTF32 hi/lo split weight tiles in the
+/* Pre-arrange the live parameters for the kernels: fp16 (and, for the first engine, TF32) hi/lo split weight tiles in the
  * UMMA K-major 128B-swizzled layout, the position-dependent time map Tmap[c,h,w]
  *  and packed GroupNorm affine terms. Pointers are the reference's own
  * nn.Parameters (model.py:329-334): conv weights [C, C+1, 3, 3] with the time plane at
@@ -148,7 +148,8 @@ int node_b200_fused_prepare(void* workspace, int C, int H, int W,
                             const float* gn3_w, const float* gn3_b, float eps, void* stream);
 
 /* One evaluation k = tsign * ODEfunc(tsign * t, y) on a [N,C,H,W] tensor (model.py:339-348);
- * conv_mode 0 = tcgen05 3xTF32 (fp32 contract), 1 = tcgen05 1xTF32, 2 = SIMT fp32 FFMA. */
+ * conv_mode 0 = tcgen05 fp16 operand split (fp32 contract, the step engine), 1 = single fp16 product, 2 = SIMT fp32 FFMA,
+ * 3 = tcgen05 3xTF32 (fp32 contract, first engine), 4 = single TF32 product. */
 int node_b200_odefunc_forward(void* workspace, const float* y, float t, float tsign, float* k,
                               int N, int C, int H, int W, int conv_mode, void* stream);
 
