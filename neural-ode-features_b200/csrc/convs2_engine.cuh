@@ -102,6 +102,21 @@ __global__ void __launch_bounds__(Tile<HO, WO>::P, 1) k_convs2(const ConvS2Args 
   // (plane slot, pr, pc) of the two passes and their taps (bi, bj) in weight-tile order
   // pass 0: slot 0 = plane (1,1): (-1,-1) (-1,0) (0,-1) (0,0); slot 1 = plane (1,0): (-1,0) (0,0)
   // pass 1: slot 0 = plane (0,1): (0,-1) (0,0);               slot 1 = plane (0,0): (0,0) and the shortcut (0,0)
+  // Even widths: the first 32 channels of the NEXT staging unit (next pass, or pass 0 of the next image) are requested
+  // right after a pass' MMAs have been issued, so their DRAM latency hides behind the MMAs / the epilogue.
+  float2 pf[32];
+  bool pf_inb = false;
+  auto prefetch = [&](int jn2, int pass2) {
+    if (jn2 >= njobs) return;
+    const int img2 = (blockIdx.x + jn2 * gridDim.x) * T::G + img_l;
+    const int ii2 = 2 * oi + (pass2 == 0 ? 1 : 0);
+    pf_inb = inimg && img2 < a.N && ii2 < HI;
+    const size_t g2 = pf_inb ? ((size_t)img2 * kC * HWI + (size_t)ii2 * WI + 2 * oj) : 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(pf[c].x), "=f"(pf[c].y) : "l"(a.act + g2 + (size_t)c * HWI));
+  };
+  if constexpr (WI % 2 == 0) prefetch(0, 0);
 #pragma unroll 1
   for (int jn = 0; jn < njobs; ++jn) {
     const int st = blockIdx.x + jn * gridDim.x;
@@ -122,11 +137,16 @@ __global__ void __launch_bounds__(Tile<HO, WO>::P, 1) k_convs2(const ConvS2Args 
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
           float x0[32], x1[32];
+          if (hb == 0) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float2 v;
-            asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a.act + g0 + (size_t)(32 * hb + c) * HWI));
-            x0[c] = inb ? v.x : 0.f; x1[c] = inb ? v.y : 0.f;
+            for (int c = 0; c < 32; ++c) { x0[c] = pf_inb ? pf[c].x : 0.f; x1[c] = pf_inb ? pf[c].y : 0.f; }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float2 v;
+              asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(a.act + g0 + (size_t)(32 * hb + c) * HWI));
+              x0[c] = inb ? v.x : 0.f; x1[c] = inb ? v.y : 0.f;
+            }
           }
           if (valid) {
             raw_to_A<T>(row + 4 * hb * T::LBO, x1, sa);                          // plane slot 0: pc = 1
@@ -213,6 +233,7 @@ __global__ void __launch_bounds__(Tile<HO, WO>::P, 1) k_convs2(const ConvS2Args 
         }
         __syncwarp();
       }
+      if constexpr (WI % 2 == 0) prefetch(pass == 0 ? jn : jn + 1, pass == 0 ? 1 : 0);
     }
     // ---- epilogue
     if (!timeout && !ptx::mbar_wait_relaxed(bar_acc, job & 1)) timeout = true;

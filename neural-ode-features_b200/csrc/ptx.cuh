@@ -44,12 +44,15 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
+#ifndef NODE_RELAX_NS
+#define NODE_RELAX_NS 64
+#endif
 // Same, for waits that are expected to last thousands of cycles (a whole conv job): back off between polls so
 // the polling warps do not compete for issue / MIO slots with the warps that still have work.
 __device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return true;
   for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
-    __nanosleep(64);
+    __nanosleep(NODE_RELAX_NS);
     if (mbar_try_wait(bar, parity)) return true;
   }
   return false;
