@@ -240,3 +240,32 @@ def test_tolerance_sweep_matches_oracle(native_lib, golden, tol):
     assert st['route'] == 'fused' and st['nfe'] == tr.nfe
     assert [int(a) for a in st['trace']['accepted']] == [int(s[2]) for s in tr.steps]
     assert rel(out.cpu(), ref) < TOL_OUT
+
+
+@pytest.mark.parametrize('n', [445, 900, 1337])
+def test_two_slot_step_kernel_matches_oracle(native_lib, golden, n):
+    """Batches above 444 images run the two-slot variant of the step kernel (NST > 148 super-tiles), including its tail
+    rounds where only slot 0 has work: one evaluation and a whole solve against the oracle on the CPU."""
+    from node_b200 import odeint, solver
+    g = golden('cifar_res_n8')
+    func = load_odefunc(g, DEV)
+    p = odefunc_params(g)
+    base = torch.from_numpy(g['h0'])
+    gen = torch.Generator().manual_seed(n)
+    reps = (n + base.shape[0] - 1) // base.shape[0]
+    h0 = (base.repeat(reps, 1, 1, 1)[:n] * (0.8 + 0.4 * torch.rand(n, 1, 1, 1, generator=gen))).contiguous()
+    ref_k = odefunc_port.odefunc_forward(p, torch.tensor(0.37), h0)
+    k = solver.odefunc_forward(func, 0.37, h0.to(DEV))
+    assert rel(k.cpu(), ref_k) < 2e-5
+    t = torch.tensor([0., 1.])
+    tr = dopri5_port.Trace()
+    ref = dopri5_port.dopri5_solve(lambda tt, y: odefunc_port.odefunc_forward(p, tt, y), h0, t, 1e-3, 1e-3, trace=tr)
+    with torch.no_grad():
+        out = odeint(func, h0.to(DEV), t.to(DEV), rtol=1e-3, atol=1e-3, method='dopri5')
+    st = dict(solver.last_stats)
+    assert st['route'] == 'fused' and st['nfe'] == tr.nfe
+    assert [int(a) for a in st['trace']['accepted']] == [int(s[2]) for s in tr.steps]
+    assert rel(out.cpu(), ref) < TOL_OUT
+    # per image, not only in the maximum norm
+    per = (out[-1].cpu() - ref[-1]).flatten(1).abs().amax(1) / ref[-1].flatten(1).abs().amax(1)
+    assert float(per.max()) < 2 * TOL_OUT
