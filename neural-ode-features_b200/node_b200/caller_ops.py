@@ -47,6 +47,11 @@ def run_sequential(seq, x):
     i = 0
     while i < len(mods):
         m = mods[i]
+        if (isinstance(m, nn.Conv2d) and i + 2 < len(mods) and isinstance(mods[i + 1], nn.GroupNorm)
+                and isinstance(mods[i + 2], nn.ReLU) and _stem_ok(m, mods[i + 1], x)):
+            x = stem_gn_relu(m, mods[i + 1], x)          # stem convolution + GroupNorm + ReLU in one pass
+            i += 3
+            continue
         if isinstance(m, nn.GroupNorm):
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(nxt, nn.ReLU):

@@ -36,19 +36,30 @@ def test_groupnorm_relu_keeps_autograd_path(native_lib):
     assert x.grad is not None and norm.weight.grad is not None
 
 
+@pytest.mark.parametrize('in_ch,size', [(3, 32), (1, 28)])
 @pytest.mark.parametrize('downsample', ['residual', 'convolution', 'minimal'])
-def test_odenet_forward_same_with_fused_callers(native_lib, monkeypatch, downsample):
+def test_odenet_forward_same_with_fused_callers(native_lib, monkeypatch, downsample, in_ch, size):
+    """Whole forward (CIFAR- and MNIST-shaped) with the callers' kernels against the same model with every caller
+    kernel switched off (the reference's own PyTorch ops): identical NFE and top-1, logits within 1e-4."""
     from node_b200 import models, caller_ops
     torch.manual_seed(0)
-    net = models.ODENet(3, n_filters=64, downsample=downsample, tol=1e-3).eval().to(DEV)
-    x = torch.rand(16, 3, 32, 32, device=DEV)
+    net = models.ODENet(in_ch, n_filters=64, downsample=downsample, tol=1e-3).eval().to(DEV)
+    x = torch.rand(16, in_ch, size, size, device=DEV)
     torch.backends.cudnn.allow_tf32 = False
     with torch.no_grad():
         net.nfe(reset=True)
+        c0 = caller_ops.launches
         fused = net(x)
+        assert caller_ops.launches > c0
         nfe_f = net.nfe(reset=True)
         monkeypatch.setattr(caller_ops, '_fusable', lambda norm, x: False)
+        monkeypatch.setattr(caller_ops, '_resconv_ok', lambda *a: False)
+        monkeypatch.setattr(caller_ops, '_convs2_ok', lambda *a: False)
+        monkeypatch.setattr(caller_ops, '_stem_ok', lambda *a: False)
+        monkeypatch.setattr(models, 'head', lambda seq, x: seq(x))
+        c1 = caller_ops.launches
         plain = net(x)
+        assert caller_ops.launches == c1                     # nothing but PyTorch ops outside the ODE block
         nfe_p = net.nfe(reset=True)
     assert nfe_f == nfe_p
     assert float((fused - plain).abs().max()) <= 1e-4 * float(plain.abs().max())
