@@ -230,7 +230,7 @@ def train_step_rate(dev, batch, steps, warmup):
     torch.cuda.synchronize()
     dt = a.elapsed_time(b) * 1e-3
     return dict(images_per_s=batch * steps / dt, ms_per_step=1e3 * dt / steps, batch=batch, steps=steps, nfe_forward=nfe[0],
-                nfe_backward=nfe[1], adjoint_vjp=solver.last_stats.get('adjoint_vjp'), loss=float(loss),
+                nfe_backward=nfe[1], adjoint_vjp=solver.last_stats.get('adjoint_vjp'), loss=float(loss.detach()),
                 note='forward + CE loss + odeint_adjoint backward (native VJP kernels, tol 1e-3) + SGD step; '
                      'downsampler / classifier autograd in PyTorch fp32')
 
