@@ -10,6 +10,7 @@
 namespace node {
 
 constexpr int kThreads = 256;
+constexpr int kNormThreads = 512;     // the read-only norm kernel wants more bytes in flight per SM than the grid cap of 296 CTAs gives at 256
 constexpr int kPartialBlocks = 296;  // 2 x 148 SMs
 
 struct KPtrs { const void* p[7]; };
@@ -112,7 +113,7 @@ static void launch_stage_combine(int row, int grid, cudaStream_t st, const node_
 
 // ---- K3: error estimate + per-member sum of squared ratios -----------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_error_norm(const node_ctl_t* __restrict__ ctl, const T* __restrict__ y0,
+__global__ void __launch_bounds__(kNormThreads) k_error_norm(const node_ctl_t* __restrict__ ctl, const T* __restrict__ y0,
                                                          const T* __restrict__ y1, KPtrs ks, Segs segs,
                                                          double* __restrict__ partials, int* __restrict__ nonfinite) {
   using A = Arith<T>;
@@ -555,10 +556,10 @@ extern "C" int node_b200_rk_error_norm(const node_ctl_t* ctl, int dtype, const v
   const Segs segs = make_segs(seg_off, seg_len, n_seg);
   if (dtype == NODE_F32) {
     dim3 g(grid_for(mx / 4 + 1), n_seg);
-    k_error_norm<float><<<g, kThreads, 0, st>>>(ctl, (const float*)y0, (const float*)y1, kp, segs, partials, nonfinite_flag);
+    k_error_norm<float><<<g, kNormThreads, 0, st>>>(ctl, (const float*)y0, (const float*)y1, kp, segs, partials, nonfinite_flag);
   } else {
     dim3 g(grid_for(mx / 2 + 1), n_seg);
-    k_error_norm<double><<<g, kThreads, 0, st>>>(ctl, (const double*)y0, (const double*)y1, kp, segs, partials, nonfinite_flag);
+    k_error_norm<double><<<g, kNormThreads, 0, st>>>(ctl, (const double*)y0, (const double*)y1, kp, segs, partials, nonfinite_flag);
   }
   return (int)cudaGetLastError();
 }
