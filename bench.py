@@ -312,7 +312,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=1024)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
-    ap.add_argument('--train-batch', type=int, default=2048, help='batch of the adjoint training-step measurement (0 = skip)')
+    ap.add_argument('--train-batch', type=int, default=4440, help='batch of the adjoint training-step measurement (0 = skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
     if args.impl == 'reference':
