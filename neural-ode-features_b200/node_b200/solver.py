@@ -189,6 +189,8 @@ def fused_workspace(device, N, C, H, W):
     if ws is None:
         if len(_ws_cache) > 8:
             _ws_cache.clear()
+            _graph_cache.clear()          # captured graphs point into the workspaces that are being released
+            _graph_failed.clear()
         ws = _ws_cache[key] = FusedWorkspace(device, N, C, H, W)
     return ws
 
@@ -388,13 +390,14 @@ class _FusedGraph(object):
 
 
 def _fused_graph(ws, y, th, t_host, common, E, conv_mode, tsign, guess):
-    key = (ws.buf.data_ptr(), tuple(float(v) for v in t_host), common[2], common[3], conv_mode, tsign, guess)
+    key = (id(ws), ws.shape, str(y.device), tuple(float(v) for v in t_host), common[2], common[3], conv_mode, tsign, guess)
     g = _graph_cache.get(key)
     if g is not None or key in _graph_failed:
         return g
     if len(_graph_cache) >= 16:
         _graph_cache.clear()
     g = _FusedGraph(y, len(t_host))
+    g.ws = ws                                 # the graph's kernels point into this workspace: keep it alive with the graph
     try:
         with torch.cuda.graph(g.graph):
             err = native.lib().node_b200_fused_solve(native.ptr(ws.buf), native.ptr(g.y), *common, E, native.ptr(g.out),

@@ -269,3 +269,32 @@ def test_two_slot_step_kernel_matches_oracle(native_lib, golden, n):
     # per image, not only in the maximum norm
     per = (out[-1].cpu() - ref[-1]).flatten(1).abs().amax(1) / ref[-1].flatten(1).abs().amax(1)
     assert float(per.max()) < 2 * TOL_OUT
+
+
+def test_cuda_graphs_survive_workspace_recycling(native_lib, golden, monkeypatch):
+    """More shapes than the workspace cache holds: graphs captured against released workspaces must never be replayed
+    (device addresses get recycled across shapes)."""
+    from node_b200 import odeint, solver
+    monkeypatch.setenv('NODE_B200_GRAPH', '1')
+    g = golden('cifar_res_n8')
+    func = load_odefunc(g, DEV)
+    base = torch.from_numpy(g['h0']).to(DEV)
+    t = torch.from_numpy(g['t']).to(DEV)
+    tol = float(g['tol'])
+    ref = {}
+    with torch.no_grad():
+        for rnd in range(2):
+            for n in list(range(1, 9)) + [8, 7, 3, 1]:
+                h0 = base[:n].contiguous()
+                for _ in range(2):                                   # direct, then replayed
+                    out = odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')
+                assert out.shape == (len(t), n) + tuple(base.shape[1:])
+                assert solver.last_stats['status'] == 0
+                if n in ref:
+                    assert torch.equal(out, ref[n])
+                else:
+                    ref[n] = out.clone()
+            for shape in [(2, 64, 6, 6), (2, 64, 7, 7), (2, 64, 14, 14), (3, 64, 8, 8), (5, 64, 6, 6), (4, 64, 7, 7)]:   # evict
+                y = torch.randn(shape, device=DEV)
+                odeint(func, y, t, rtol=tol, atol=tol, method='dopri5')
+                odeint(func, y, t, rtol=tol, atol=tol, method='dopri5')
