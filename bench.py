@@ -48,7 +48,7 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
