@@ -125,73 +125,81 @@ __device__ __forceinline__ void grad_to_A(const VjpSmem& sm, const Who& me, int 
   }
 }
 
-// Leader thread: one conv job = 9 taps of MT x 4 k-steps x 3 MMAs (hi*hi, lo*hi, hi*lo) into `dcol`.
-struct VjpRing { uint32_t issued, tapx, total; };
+// One conv job = 9 taps of MT x 4 k-steps x 3 MMAs (hi*hi, lo*hi, hi*lo) into `dcol`. As in the step engine the weight
+// tiles form one sequence (tile i = tap i % 9 of job i / 9; set of job j: conv1, conv2, dgrad2, dgrad1), the leader
+// (warp 0) only waits for tiles to land and issues, the producer (warp 1) requests tile i once tile i - kNW has retired.
 __device__ __forceinline__ int vjp_set_of(uint32_t job) { const uint32_t k = job & 3u; return k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 3 : 2)); }
 
+__device__ __forceinline__ void vjp_request_tile(const VjpSmem& sm, const uint16_t* __restrict__ w16, uint32_t i) {
+  const uint32_t slot = i % kNW, set = (uint32_t)vjp_set_of(i / 9), tp = i % 9;
+  ptx::mbar_expect_tx(sm.s.bar_wfull + 8 * slot, kW16TileBytes);
+  ptx::bulk_g2s(sm.s.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(set * 9 + tp) * kW16TileBytes, kW16TileBytes,
+                sm.s.bar_wfull + 8 * slot);
+}
+
+__device__ __forceinline__ void vjp_produce_job(const VjpSmem& sm, const uint16_t* __restrict__ w16, uint32_t job, uint32_t total,
+                                                bool& timeout) {
+  const bool lead = ptx::elect_one();
+#pragma unroll 1
+  for (uint32_t i = job * 9 + kWAhead; i < job * 9 + kWAhead + 9 && i < total; ++i) {
+    const uint32_t slot = i % kNW;
+    if (i >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.s.bar_wfree + 8 * slot, ((i / kNW) - 1) & 1)) timeout = true;
+    if (lead) vjp_request_tile(sm, w16, i);
+  }
+  __syncwarp();
+}
+
 template <class T>
-__device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, VjpRing& rg, const uint16_t* __restrict__ w16, uint32_t tmem,
-                                              uint32_t dcol, uint32_t idesc, bool& timeout) {
+__device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t job,
+                                              bool& timeout) {
   // whole first warp, warp-uniform arguments, asynchronous instructions by one elected lane (see step_engine.cuh)
   const bool lead = ptx::elect_one();
   ptx::tc_fence_after();
   const uint32_t abase = sm.s.abase + T::HALO * 16;
+  const uint32_t a_lo0 = ((abase & 0x3FFFFu) >> 4) | (((uint32_t)T::LBO >> 4) << 16);
+  constexpr uint32_t a_hiw = (128u >> 4) | (1u << 14), b_hiw = (1024u >> 4) | (1u << 14) | (2u << 29);
+  auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
-    while (rg.issued < rg.total && rg.issued <= rg.tapx + (kNW - kWGap)) {
-      const uint32_t slot = rg.issued % kNW;
-      if (rg.issued >= (uint32_t)kNW && !timeout && !ptx::mbar_wait(sm.s.bar_wfree + 8 * slot, ((rg.issued / kNW) - 1) & 1)) timeout = true;
-      const uint32_t set = (uint32_t)vjp_set_of(rg.issued / 9), tp = rg.issued % 9;
-      if (lead) {
-        ptx::mbar_expect_tx(sm.s.bar_wfull + 8 * slot, kW16TileBytes);
-        ptx::bulk_g2s(sm.s.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(set * 9 + tp) * kW16TileBytes, kW16TileBytes,
-                      sm.s.bar_wfull + 8 * slot);
-      }
-      ++rg.issued;
-    }
-    const uint32_t slot = rg.tapx % kNW;
-    if (!timeout && !ptx::mbar_wait(sm.s.bar_wfull + 8 * slot, (rg.tapx / kNW) & 1)) timeout = true;
+    const uint32_t tile = job * 9 + tap, slot = tile % kNW;
+    if (!timeout && !ptx::mbar_wait(sm.s.bar_wfull + 8 * slot, (tile / kNW) & 1)) timeout = true;
     ptx::tc_fence_after();
     const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
-    const uint64_t b_hi0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes);
-    const uint64_t b_lo0 = ptx::make_desc_sw128(sm.s.wring + slot * kW16TileBytes + 64 * 128);
+    const uint32_t a_tap = a_lo0 + (uint32_t)off;
+    const uint32_t b_hi0 = ((sm.s.wring + slot * kW16TileBytes) & 0x3FFFFu) >> 4, b_lo0 = b_hi0 + (uint32_t)((64 * 128) >> 4);
     if (lead) {
 #pragma unroll
       for (int mt = 0; mt < T::MT; ++mt) {
         const uint32_t d = tmem + dcol + (uint32_t)(mt * 64);
-        const uint32_t arow = abase + (uint32_t)((mt * 128 + off) * 16);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t a_hi = ptx::make_desc_nosw(arow + 2 * ks * T::LBO, T::LBO, 128);
-          const uint64_t a_lo = ptx::make_desc_nosw(arow + T::A_PART + 2 * ks * T::LBO, T::LBO, 128);
-          const uint64_t kadv = (uint64_t)((ks * 32) >> 4);
-          ptx::mma_f16_ss(d, a_hi, b_hi0 + kadv, idesc, (tap == 0 && ks == 0) ? 0u : 1u);
-          ptx::mma_f16_ss(d, a_lo, b_hi0 + kadv, idesc, 1u);
-          ptx::mma_f16_ss(d, a_hi, b_lo0 + kadv, idesc, 1u);
+          const uint64_t a_hi = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO) >> 4), a_hiw);
+          const uint64_t a_lo = pack(a_tap + (uint32_t)((mt * 128 * 16 + 2 * ks * T::LBO + T::A_PART) >> 4), a_hiw);
+          const uint32_t kadv = (uint32_t)((ks * 32) >> 4);
+          ptx::mma_f16_ss(d, a_hi, pack(b_hi0 + kadv, b_hiw), idesc, (tap == 0 && ks == 0) ? 0u : 1u);
+          ptx::mma_f16_ss(d, a_lo, pack(b_hi0 + kadv, b_hiw), idesc, 1u);
+          ptx::mma_f16_ss(d, a_hi, pack(b_lo0 + kadv, b_hiw), idesc, 1u);
         }
       }
       ptx::tc_commit(sm.s.bar_wfree + 8 * slot);
     }
-    ++rg.tapx;
   }
   if (lead) ptx::tc_commit(sm.s.bar_acc);
   __syncwarp();
 }
 
 template <class T>
-__device__ __forceinline__ void vjp_conv_run(const VjpSmem& sm, const Who& me, VjpRing& rg, const uint16_t* __restrict__ w16,
+__device__ __forceinline__ void vjp_conv_run(const VjpSmem& sm, const Who& me, uint32_t total, const uint16_t* __restrict__ w16,
                                              uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t& njob, bool& timeout) {
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   slot_sync(0, T::P);
-  if (__shfl_sync(0xffffffffu, me.warp, 0) == 0) {     // shuffles: tell the compiler these values are warp-uniform
-    VjpRing ru;
-    ru.issued = __shfl_sync(0xffffffffu, rg.issued, 0); ru.tapx = __shfl_sync(0xffffffffu, rg.tapx, 0);
-    ru.total = __shfl_sync(0xffffffffu, rg.total, 0);
-    vjp_issue_job<T>(sm, ru, w16, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, dcol, 0),
-                     __shfl_sync(0xffffffffu, idesc, 0), timeout);
-    rg = ru;
-  }
+  const int wu = __shfl_sync(0xffffffffu, me.warp, 0);     // shuffles: tell the compiler these values are warp-uniform
+  if (wu == 0)
+    vjp_issue_job<T>(sm, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, dcol, 0), __shfl_sync(0xffffffffu, idesc, 0),
+                     __shfl_sync(0xffffffffu, njob, 0), timeout);
+  else if (wu == 1)
+    vjp_produce_job(sm, w16, __shfl_sync(0xffffffffu, njob, 0), __shfl_sync(0xffffffffu, total, 0), timeout);
   if (!timeout && !ptx::mbar_wait_relaxed(sm.s.bar_acc, njob & 1)) timeout = true;
   ++njob;
   ptx::tc_fence_after();
@@ -316,7 +324,9 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
 
   const int NST = (a.g.N + T::G - 1) / T::G;
   const int nst = (int)blockIdx.x < NST ? (NST - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  VjpRing rg{0u, 0u, (uint32_t)nst * 4u * 9u};
+  const uint32_t total = (uint32_t)nst * 4u * 9u;
+  if (tid == 0)                     // the first tiles of the weight sequence; later ones are requested by the producer warp
+    for (uint32_t i = 0; i < kWAhead && i < total; ++i) vjp_request_tile(sm, w.w16, i);
   bool timeout = false;
   uint32_t njob = 0;
   float tacc = 0.f;
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       gn_stats<T>(st1, me, hb, x, valid, a.eps);
       act_to_A<T>(sm, me, hb, x, 0, w.scal[0], valid, a.R[0], p0);
     }
-    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC1, kIdF16N64, njob, timeout);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC1, kIdF16N64, njob, timeout);
     // ---- c1 -> GN2 -> ReLU -> conv2 (model.py:344-346)
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       gn_stats<T>(st2, me, hb, x, valid, a.eps);
       act_to_A<T>(sm, me, hb, x, 1, w.scal[1], valid, a.R[1], p0);
     }
-    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);
     // ---- c2 -> GN3 = f; backward of GN3 with cotangent -a (adjoint.py:43)
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       }
       grad_to_A<T>(sm, me, hb, g, valid);
     }
-    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr2 over c2's columns
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr2 over c2's columns
     // ---- ReLU mask of GN2's output, backward of GN2
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
@@ -423,7 +433,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       }
       grad_to_A<T>(sm, me, hb, g, valid);
     }
-    vjp_conv_run<T>(sm, me, rg, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr1
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr1
     // ---- ReLU mask of GN1's output, backward of GN1 -> vjp_y
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
