@@ -23,6 +23,9 @@ namespace node {
 
 constexpr uint32_t kIdBF16N64 = kIdF16N64 | (1u << 7) | (1u << 10);   // kind::f16 with bf16 A and B
 
+constexpr int kTmPitch = 65;   // floats per (conv, border class) row of the time map in shared memory: lanes of different
+                               // classes then hit different banks (a pitch of 64 makes every class collide)
+
 struct VjpSmem {
   StepSmem s;            // wring, abase, part, stat (set 0), gnp, bias, tmapc, scratch, barriers of the step engine
   float2* stat3;         // [3][G][32] (mean, rstd) of GN1, GN2, GN3
@@ -219,7 +222,7 @@ __device__ __forceinline__ void vjp_tmem_read(const VjpSmem& sm, const Who& me, 
     for (int j = 0; j < 16; ++j) {
       const float acc = __uint_as_float(v[j]) * mul;
       if (cv >= 0) {
-        const float extra = fmaf(t, sm.s.tmapc[(cv * 9 + me.cls) * 64 + 32 * hb + c0 + j], sm.s.bias[cv * 64 + 32 * hb + c0 + j]);
+        const float extra = fmaf(t, sm.s.tmapc[(cv * 9 + me.cls) * kTmPitch + 32 * hb + c0 + j], sm.s.bias[cv * 64 + 32 * hb + c0 + j]);
         x[c0 + j] = valid ? acc + extra : 0.f;
       } else {
         x[c0 + j] = valid ? acc : 0.f;
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
     sm.chacc = reinterpret_cast<float*>(base + o); o += (size_t)T::NWARP * 12 * 32 * 4;
     sm.s.gnp = reinterpret_cast<float4*>(base + o); o += 3 * 32 * 16;
     sm.s.bias = reinterpret_cast<float*>(base + o); o += 2 * 64 * 4;
-    sm.s.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * 64 * 4;
+    sm.s.tmapc = reinterpret_cast<float*>(base + o); o += 2 * 9 * kTmPitch * 4 + 8;
     sm.s.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.s.bar_wfull = al + (uint32_t)o; o += 8 * kNW;
     sm.s.bar_wfree = al + (uint32_t)o; o += 8 * kNW;
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
                               w.gn[(2 * n + 1) * kC + 2 * g + 1]);
   }
   for (int i = tid; i < 2 * 64; i += blockDim.x) sm.s.bias[i] = w.bias[i];
-  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.s.tmapc[i] = w.tmapc[i];
+  for (int i = tid; i < 2 * 9 * 64; i += blockDim.x) sm.s.tmapc[(i >> 6) * kTmPitch + (i & 63)] = w.tmapc[i];
   if (tid == 0) {
     for (int i = 0; i < kNW; ++i) { ptx::mbar_init(sm.s.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.s.bar_wfree + 8 * i, 1); }
     ptx::mbar_init(sm.s.bar_acc, 1);
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) { const float v = a.adj[p0 + (size_t)c * HW]; g[c] = valid ? -v : 0.f; }
       gn_backward<T>(sm, me, hb, 2, x, g);
-      const float* tm = sm.s.tmapc + (9 + me.cls) * 64 + 32 * hb;
+      const float* tm = sm.s.tmapc + (9 + me.cls) * kTmPitch + 32 * hb;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         if (valid) { a.GC[1][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
         }
       }
       gn_backward<T>(sm, me, hb, 1, x, g);
-      const float* tm = sm.s.tmapc + me.cls * 64 + 32 * hb;
+      const float* tm = sm.s.tmapc + me.cls * kTmPitch + 32 * hb;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         if (valid) { a.GC[0][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
@@ -484,7 +487,7 @@ constexpr size_t vjp_smem_bytes() {
   using T = Tile<H_, W_>;
   return 1024 + (size_t)kNW * kW16TileBytes + (size_t)2 * T::A_PART + (size_t)T::NWARP * 32 * 4 + (size_t)T::NWARP * 64 * 4 +
          (size_t)3 * T::G * 32 * 8 + (size_t)T::G * 32 * 4 + (size_t)T::NWARP * 12 * 32 * 4 + 3 * 32 * 16 + 2 * 64 * 4 +
-         2 * 9 * 64 * 4 + 32 * 8 + 16 * kNW + 8 + 64;
+         2 * 9 * kTmPitch * 4 + 8 + 32 * 8 + 16 * kNW + 8 + 64;
 }
 
 template <int H_, int W_>
