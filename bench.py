@@ -41,7 +41,7 @@ def peaks():
 
 
 class ClockSampler(object):
-    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
@@ -52,9 +52,16 @@ class ClockSampler(object):
         except OSError:
             self.p = None
 
+    def mark(self):
+        """Wall-clock window of the timed region: only samples inside it count (the sampler itself starts earlier, before
+        the warm-up, because nvidia-smi needs ~100 ms to produce its first line)."""
+        self.t0 = time.time()
+
     def stop(self):
         if self.p is None:
             return None
+        t1 = time.time()
+        time.sleep(0.03)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -63,20 +70,27 @@ class ClockSampler(object):
         self.f.flush()
         rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], 0.0, set()
+        import datetime
+        t0 = getattr(self, 't0', 0.0)
+        sm, mx, reasons, n_all = [], 0.0, set(), 0
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
             try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                ts = datetime.datetime.strptime(r[0].strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                clk, cmax = float(r[1]), float(r[2])
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[3:7]):
+            n_all += 1
+            mx = max(mx, cmax)
+            if not (t0 - 0.02 <= ts <= t1 + 0.02):
+                continue
+            sm.append(clk)
+            for n, v in zip(names, r[4:8]):
                 if v.strip().lower().startswith('active'):
                     reasons.add(n)
         if not sm:
             return None
-        busy = [c for c in sm if c >= 0.5 * max(sm)] or sm
-        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), samples_total=n_all)
 
 
 def build_model(device, adjoint=False):
@@ -402,11 +416,14 @@ def main():
         logits_host.copy_(out, non_blocking=True)
         main.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step_resident()
     solver.PROFILE_STEP_EVENTS = []
     launches[0] = 0
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        torch.cuda.synchronize()
+        sampler.mark()
     t_res = timed_loop(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     step_events = solver.PROFILE_STEP_EVENTS
