@@ -91,17 +91,20 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
       const uint32_t row = half == 0 ? grow : rrow;
       const uint32_t cstride = half == 0 ? (uint32_t)WT::G_STRIDE : (uint32_t)WT::R_STRIDE;
       const uint32_t lo_chunk0 = half == 0 ? 8u : 10u;
-#pragma unroll 2
-      for (int kc = 0; kc < 8; ++kc) {
-        float v[8];
+      // all 64 loads of this half in flight at once (the kernel has one CTA per SM and registers to spare; staging
+      // is latency-bound and never overlaps the MMAs of the same super-tile)
+      float v[64];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = valid ? src[goff + (size_t)(kc * 8 + j) * HW] : 0.f;
+      for (int c = 0; c < 64; ++c) v[c] = ptx::ldg_ordered(src + goff + (size_t)c * HW);
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          const float v0 = valid ? v[kc * 8 + 2 * j] : 0.f, v1 = valid ? v[kc * 8 + 2 * j + 1] : 0.f;
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
           const float2 hf = __bfloat1622float2(h);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
           hi[j] = *reinterpret_cast<const uint32_t*>(&h);
           lo[j] = *reinterpret_cast<const uint32_t*>(&l);
         }
