@@ -79,6 +79,17 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
   const int NST = (a.g.N + T::G - 1) / T::G;
   bool timeout = false;
   uint32_t it = 0;
+  // The GC half of the NEXT super-tile is requested into registers before the wait for this super-tile's MMAs, so its
+  // latency hides behind them (the shared-memory images themselves are single-buffered).
+  float pf[64];
+  auto prefetch = [&](int st2) {
+    if (st2 >= NST) return;
+    const int img2 = st2 * T::G + img_l;
+    const size_t g2 = (inimg && img2 < a.g.N) ? (size_t)img2 * kC * HW + pix : 0;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) pf[c] = ptx::ldg_ordered(Gsrc + g2 + (size_t)c * HW);
+  };
+  prefetch(split);
 #pragma unroll 1
   for (int st = split; st < NST; st += a.nsplit, ++it) {
     const int img = st * T::G + img_l;
@@ -94,8 +105,13 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
       // all 64 loads of this half in flight at once (the kernel has one CTA per SM and registers to spare; staging
       // is latency-bound and never overlaps the MMAs of the same super-tile)
       float v[64];
+      if (half == 0) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) v[c] = ptx::ldg_ordered(src + goff + (size_t)c * HW);
+        for (int c = 0; c < 64; ++c) v[c] = pf[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) v[c] = ptx::ldg_ordered(src + goff + (size_t)c * HW);
+      }
 #pragma unroll
       for (int kc = 0; kc < 8; ++kc) {
         uint32_t hi[4], lo[4];
@@ -141,6 +157,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
       if (lead) ptx::tc_commit(bar);
       __syncwarp();
     }
+    prefetch(st + a.nsplit);
     if (!timeout && !ptx::mbar_wait_relaxed(bar, it & 1)) timeout = true;   // operands free again / accumulators current
     ptx::tc_fence_after();
   }
