@@ -119,7 +119,8 @@ int node_b200_reduce_partials(const double* partials, int n_rows, double* sums, 
 
 /* K6 - device-side controller. mode 0: INIT_A (misc.py:123-131), 1: INIT_B (misc.py:136-143,
  * dopri5.py:80-83), 2: STEP (dopri5.py:109-121, misc.py:160-170, dopri5.py:88-92 output
- * scheduling). t_out: the requested times as float64 [n_out] (already sign-flipped if the
+ * scheduling), 3: FIXED FIRST STEP (dopri5.py:81-82, options['first_step'] given: dt = sums[0], no
+ * probe evaluation). t_out: the requested times as float64 [n_out] (already sign-flipped if the
  * caller integrates backwards, misc.py:184-187). */
 int node_b200_controller(node_ctl_t* ctl, int mode, const double* sums, const int* nonfinite_flag,
                          const double* t_out, void* stream);

@@ -272,11 +272,7 @@ static int launch_convs2_shape(const ConvS2Args& a, cudaStream_t st) {
   using T = Tile<HO, WO>;
   constexpr size_t smem = convs2_smem_bytes(T::A_PART);
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_convs2<HO, WO, HI, WI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  NODE_SET_SMEM_ONCE((k_convs2<HO, WO, HI, WI>), smem);
   const int NST = (a.N + T::G - 1) / T::G;
   const int grid = NST < kMaxGrid ? NST : kMaxGrid;
   k_convs2<HO, WO, HI, WI><<<grid, T::P, smem, st>>>(a);

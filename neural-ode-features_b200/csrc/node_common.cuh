@@ -6,6 +6,19 @@
 
 #define NODE_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per device whether this kernel has it
+// (a process that moves a model to cuda:1 would otherwise launch with the 48 KB default there).
+#define NODE_SET_SMEM_ONCE(kernel, bytes)                                                                         \
+  do {                                                                                                            \
+    static bool done__[64] = {};                                                                                  \
+    int dev__ = 0;                                                                                                \
+    NODE_CUDA_OK(cudaGetDevice(&dev__));                                                                          \
+    if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                                             \
+      NODE_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      if (dev__ >= 0 && dev__ < 64) done__[dev__] = true;                                                         \
+    }                                                                                                             \
+  } while (0)
+
 namespace node {
 
 // Dormand-Prince / Shampine tableau (reference dopri5.py:11-36), evaluated in double exactly

@@ -655,11 +655,7 @@ static size_t fused_smem_bytes(const Geo& g, int conv_mode, int nw) {
 
 template <int H_, int W_>
 static int launch_shape(const FusedArgs& a, size_t smem, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_fused<H_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  NODE_SET_SMEM_ONCE((k_fused<H_, W_>), 227 * 1024);
   k_fused<H_, W_><<<grid, kBlock, smem, st>>>(a);
   return (int)cudaGetLastError();
 }

@@ -1,6 +1,7 @@
 // f16-split engine of the fused ODE-Net route: parameter preparation and shape dispatch.
 // The kernel itself is the template in step_engine.cuh, instantiated per shape in step_shape_*.cu.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "fused_common.cuh"
 
 namespace node {
@@ -82,6 +83,7 @@ int launch_prepare16(const FusedWs& w, int H, int W, const float* c1w, const flo
 }
 
 int launch_step_8x8(const FusedArgs& a, cudaStream_t st);
+int launch_step8_dense(const FusedArgs& a, cudaStream_t st);      // step8.cu: dense 8x8 tiling, software-pipelined chain
 int launch_step_7x7(const FusedArgs& a, cudaStream_t st);
 int launch_step_6x6(const FusedArgs& a, cudaStream_t st);
 int launch_step_14x14(const FusedArgs& a, cudaStream_t st);
@@ -93,7 +95,11 @@ bool step_engine_supports(int H, int W) {
 
 int launch_step_engine(const FusedArgs& a, cudaStream_t st) {
   const int H = a.g.H, W = a.g.W;
-  if (H == 8 && W == 8) return launch_step_8x8(a, st);
+  if (H == 8 && W == 8) {
+    static const char* dense = getenv("NODE_B200_STEP8");          // "0": the strip-tiled two-slot kernel (cross-check / tuning aid)
+    if (dense != nullptr && dense[0] == '0') return launch_step_8x8(a, st);
+    return launch_step8_dense(a, st);
+  }
   if (H == 7 && W == 7) return launch_step_7x7(a, st);
   if (H == 6 && W == 6) return launch_step_6x6(a, st);
   if (H == 14 && W == 14) return launch_step_14x14(a, st);

@@ -136,6 +136,12 @@ __device__ __forceinline__ float ldg_ordered(const float* p) {
   return v;
 }
 
+__device__ __forceinline__ float4 ldg128_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -162,11 +162,7 @@ static int launch_resconv_slots(const ResConvArgs& a, cudaStream_t st) {
   using T = Tile<H_, W_>;
   constexpr size_t smem = resconv_smem_bytes(T::A_PART, NSLOT, T::NWARP, T::G);
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_resconv<H_, W_, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  NODE_SET_SMEM_ONCE((k_resconv<H_, W_, NSLOT>), smem);
   const int NST = (a.N + T::G - 1) / T::G;
   int grid = (NST + NSLOT - 1) / NSLOT;
   if (grid > kMaxGrid) grid = kMaxGrid;

@@ -293,6 +293,18 @@ __device__ void controller_impl(node_ctl_t* c, int mode, const double* sums, con
     prepare_attempt<T>(c);
     return;
   }
+  if (mode == 3) {
+    // options['first_step'] given (dopri5.py:81-82): the first step is the constant 0.01 whatever the value, and the
+    // initial-step probe is never evaluated; sums[0] carries the constant as the reference rounds it.
+    c->dt = sums[0];
+    c->t0 = c->t1 = t_out[0];
+    c->next_out = 1;
+    c->out_lo = c->out_hi = 1;
+    c->steps_this_advance = 0;
+    c->nfe += 1;  // f0 only (dopri5.py:78)
+    prepare_attempt<T>(c);
+    return;
+  }
   // mode 2: dopri5.py:109-121
   if (nonfinite != nullptr && *nonfinite) { c->status |= NODE_ST_NONFINITE; c->done = 1; c->out_lo = c->out_hi = c->next_out; return; }
   bool accept = true;

@@ -497,11 +497,7 @@ static int launch_vjp_shape(const VjpArgs& a, cudaStream_t st) {
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static_assert(2 * T::MT * 64 <= kTmemCols, "tensor memory budget");
   static_assert(T::G == strip_images(H_, W_), "strip_images out of sync");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_vjp<H_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  NODE_SET_SMEM_ONCE((k_vjp<H_, W_>), smem);
   const int NST = (a.g.N + T::G - 1) / T::G;
   const int grid = NST < kMaxGrid ? NST : kMaxGrid;
   k_vjp<H_, W_><<<grid, T::P, smem, st>>>(a);

@@ -198,11 +198,7 @@ static int launch_wgrad_shape(WgradArgs a, cudaStream_t st) {
   using WT = WgTile<H_, W_>;
   static_assert(WT::smem <= 227 * 1024, "shared memory budget");
   static_assert(128 * (kWgCols + 1) * 4 <= WT::GCH * WT::G_STRIDE + WT::RCH * WT::R_STRIDE, "drain staging");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NODE_CUDA_OK(cudaFuncSetAttribute(k_wgrad<H_, W_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT::smem));
-    attr_set = true;
-  }
+  NODE_SET_SMEM_ONCE((k_wgrad<H_, W_>), WT::smem);
   const int NST = (a.g.N + T::G - 1) / T::G;
   a.nsplit = NST < kWgSplits ? NST : kWgSplits;
   k_wgrad<H_, W_><<<dim3(a.nsplit, 2, 2), T::P, WT::smem, st>>>(a);

@@ -24,6 +24,7 @@ def _fusable(norm, x):
     return x.shape[1] == norm.num_channels and 0 < cell <= 4096 and x.shape[0] > 0
 
 
+@native.on_device_of(1)
 def group_norm_relu(norm, x, relu=True):
     """relu(norm(x)) (or norm(x)) for an nn.GroupNorm `norm`; one CUDA pass when no gradient is needed."""
     if not _fusable(norm, x):
@@ -87,6 +88,7 @@ def _resconv_ok(norm, conv, x, shortcut):
     return native.lib().node_b200_resconv_workspace_bytes(64, int(x.shape[2]), int(x.shape[3])) > 0
 
 
+@native.on_device_of(2)
 def res_conv(norm, conv, x, shortcut, next_norm=None):
     """conv(relu(norm(x))) + shortcut for the ResBlock tail; one tcgen05 kernel when the shape is served and no gradient
     is needed, the modules' own ops otherwise. With `next_norm` (the following block's norm1) the result is
@@ -147,6 +149,7 @@ def _convs2_ok(norm, conv, down, a):
     return native.lib().node_b200_convs2_workspace_bytes(64, int(a.shape[2]), int(a.shape[3])) > 0
 
 
+@native.on_device_of(3)
 def res_head(norm, conv, down, a):
     """(conv(a), down(a)) for a = relu(norm(x)) already computed: one tcgen05 kernel when the shape is served and no gradient
     is needed, the modules' own ops otherwise. `norm` only supplies the bound of |a| for the fp16 operand split."""
@@ -193,6 +196,7 @@ def _stem_ok(conv, norm, x):
     return (int(x.shape[1]), int(x.shape[2]), int(x.shape[3])) in ((3, 32, 32), (1, 28, 28)) and conv.in_channels == x.shape[1]
 
 
+@native.on_device_of(2)
 def stem_gn_relu(conv, norm, x):
     """relu(norm(conv(x))): one CUDA pass when served and no gradient is needed, the modules' own ops otherwise."""
     if not _stem_ok(conv, norm, x):
@@ -210,6 +214,7 @@ def stem_gn_relu(conv, norm, x):
 
 # ---- fused classifier head: GroupNorm -> ReLU -> global average pool (-> Linear) (csrc/caller_ops.cu k_head) ---------------
 
+@native.on_device_of(1)
 def head(seq, x):
     """FCClassifier.module (model.py:231-250) applied to x: one CUDA pass when the layer list is exactly
     [GroupNorm(32, 64), ReLU, AdaptiveAvgPool2d(1), (Dropout in eval mode,) Flatten, Linear(64, k) or an empty Sequential]

@@ -13,7 +13,6 @@ enable(group) switches the solver into sharded mode for this process; disable() 
 import torch
 
 _group = None
-_numel_cache = {}
 
 
 def enable(process_group=None):
@@ -22,13 +21,11 @@ def enable(process_group=None):
     if not dist.is_initialized():
         raise RuntimeError('torch.distributed is not initialised')
     _group = process_group if process_group is not None else dist.group.WORLD
-    _numel_cache.clear()
 
 
 def disable():
     global _group
     _group = None
-    _numel_cache.clear()
 
 
 def group():
@@ -46,11 +43,10 @@ def all_reduce_sum(t):
 
 
 def global_numel(local_numel, device):
-    """Sum of the shard sizes over the group (one tiny all-reduce, cached per local size)."""
+    """Sum of the shard sizes over the group: one tiny all-reduce per call, by EVERY rank. Never cached - a cache keyed by
+    the local size would skip the collective on the ranks whose shard size did not change when the global batch did
+    (uneven last batch), and the ranks' collective sequences would diverge."""
     import torch.distributed as dist
-    key = (int(local_numel), str(device))
-    if key not in _numel_cache:
-        v = torch.tensor([int(local_numel)], dtype=torch.int64, device=device)
-        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=_group)
-        _numel_cache[key] = int(v.item())
-    return _numel_cache[key]
+    v = torch.tensor([int(local_numel)], dtype=torch.int64, device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.SUM, group=_group)
+    return int(v.item())

@@ -5,6 +5,7 @@ not on a CUDA device, the solver raises.  Build with `python __graft_entry__.py 
 `python -c "import __graft_entry__ as g; g.build()"`) - nvcc cross-compiles for sm_100a.
 """
 import ctypes
+import functools
 import os
 
 import numpy as np
@@ -113,6 +114,24 @@ def layout():
 def check(err, what):
     if err != 0:
         raise RuntimeError('node_b200: %s failed with CUDA error %d' % (what, err))
+
+
+def on_device_of(argpos):
+    """Decorator: run the wrapped entry point with the CUDA device of its `argpos`-th argument (a tensor, or a tuple whose
+    first member is one) current. The kernels are launched on torch's CURRENT stream and the per-device kernel attributes
+    are looked up through cudaGetDevice, so a tensor on cuda:1 must be served with cuda:1 current."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kw):
+            t = args[argpos]
+            if isinstance(t, (tuple, list)) and t:
+                t = t[0]
+            if torch.is_tensor(t) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kw)
+            return fn(*args, **kw)
+        return wrapper
+    return deco
 
 
 def stream_ptr():

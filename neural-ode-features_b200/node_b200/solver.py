@@ -195,6 +195,7 @@ def fused_workspace(device, N, C, H, W):
     return ws
 
 
+@native.on_device_of(2)
 def odefunc_forward(func, t, y, tsign=1.0, conv_mode=None):
     """One evaluation of the recognised dynamics by the fused kernel (used by tests / the adjoint)."""
     params = recognise_odefunc(func)
@@ -229,6 +230,7 @@ def _vjp_workspace(device, N, C, H, W):
     return buf
 
 
+@native.on_device_of(2)
 def odefunc_vjp(func, t, y, adj_y, tsign=1.0, out=None):
     """One evaluation of the adjoint's augmented dynamics (adjoint.py:32-55) by the native kernels:
     returns (f, vjp_y, vjp_t, vjp_params) with cotangent -adj_y, all multiplied by tsign and evaluated at
@@ -508,17 +510,21 @@ class _GenericSolve(object):
         ctl = native.ptr(self.ctl)
         t0d = torch.tensor(self.t_host[0], dtype=self.dtype, device=self.device)
         self._eval(t0d, Y0, F0)                                               # dopri5.py:78
-        native.check(lib.node_b200_init_norms(ctl, self.code, 0, native.ptr(self.bufs[Y0]), native.ptr(self.bufs[F0]),
-                                              native._vp(0), *segs, native.ptr(self.partials), sp), 'init_norms')
-        self._reduce_and_control(0)
-        native.check(lib.node_b200_rk_stage_combine(ctl, self.code, 7, native.ptr(self.bufs[YI]), native.ptr(self.bufs[Y0]),
-                                                    self._kptrs([F0]), 1, self.L, sp), 'probe')
-        self._eval(self.ts[1], YI, K2)                                        # misc.py:134
-        native.check(lib.node_b200_init_norms(ctl, self.code, 1, native.ptr(self.bufs[Y0]), native.ptr(self.bufs[F0]),
-                                              native.ptr(self.bufs[K2]), *segs, native.ptr(self.partials), sp), 'init_norms')
-        self._reduce_and_control(1)
-        if self.first_step is not None:
-            raise NotImplementedError('options["first_step"] is not supported')
+        if self.first_step is None:
+            native.check(lib.node_b200_init_norms(ctl, self.code, 0, native.ptr(self.bufs[Y0]), native.ptr(self.bufs[F0]),
+                                                  native._vp(0), *segs, native.ptr(self.partials), sp), 'init_norms')
+            self._reduce_and_control(0)
+            native.check(lib.node_b200_rk_stage_combine(ctl, self.code, 7, native.ptr(self.bufs[YI]), native.ptr(self.bufs[Y0]),
+                                                        self._kptrs([F0]), 1, self.L, sp), 'probe')
+            self._eval(self.ts[1], YI, K2)                                    # misc.py:134
+            native.check(lib.node_b200_init_norms(ctl, self.code, 1, native.ptr(self.bufs[Y0]), native.ptr(self.bufs[F0]),
+                                                  native.ptr(self.bufs[K2]), *segs, native.ptr(self.partials), sp), 'init_norms')
+            self._reduce_and_control(1)
+        else:
+            # dopri5.py:81-82: ANY non-None first_step means "start with 0.01" (built in the default dtype, then widened)
+            self.sums[0] = _dflt(0.01)
+            native.check(lib.node_b200_controller(ctl, 3, native.ptr(self.sums), native._vp(0), native.ptr(self.t_dev), sp),
+                         'controller')
         self.out[0].copy_(self.bufs[Y0])
         cur = 0
         view = native.CtlView(self.ctl)
@@ -570,6 +576,7 @@ def _is_iterable(x):
         return False
 
 
+@native.on_device_of(1)
 def _solve(func, y0, t, rtol, atol, options):
     """Shared by odeint and the adjoint's forward/backward: y0 is a tuple, returns a tuple."""
     for y in y0:
