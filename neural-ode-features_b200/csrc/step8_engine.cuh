@@ -37,6 +37,15 @@ constexpr int kWorkerRegs = 112, kAuxRegs = 32;            // setmaxnreg moves r
                                                            // warpgroup frees 128*(96-32) = 8192, the workers take 512*(112-96) = 8192
 constexpr int kImgs = 4;                          // images per super-tile
 
+// Tuning aid (-DNODE_STEP8_DEBUG): CTA 0 accumulates clock64() deltas per phase for worker thread 0 ([0..15]), the
+// issuer ([16..23]) and the producer ([24..31]); read back with node_b200_step8_phase_read.
+#ifdef NODE_STEP8_DEBUG
+static __device__ long long g_s8_phase[32];
+#define S8_STAMP(i) do { if (rec_ph) { const long long now_ = clock64(); g_s8_phase[(i)] += now_ - last_ph; last_ph = now_; } } while (0)
+#else
+#define S8_STAMP(i) do { } while (0)
+#endif
+
 struct Smem {
   uint32_t wring, abase;           // shared addresses (ring 1024-aligned)
   float* part;                     // [16 warps][2][32] warp partials of the GroupNorm reductions
@@ -60,22 +69,26 @@ static_assert(smem_bytes() <= 227 * 1024, "shared memory budget");
 
 // Super-tile / conv-job schedule of a CTA, shared by the workers and the aux warp: rounds of (S0, S1); in every round, for
 // every evaluation: conv1 of each active virtual slot, then conv2 of each.
+// Virtual slot 1 runs `lag` evaluations behind slot 0 (3 of the 6 stages of an attempted step): the k tensors an image
+// needs grow from 2 to 7 over the stages of a step, and with every CTA at the same stage the live set of the 1184 images
+// in flight (132 MB at the last stage) exceeded the L2 - de-phased, the two slots of a CTA peak at different times (104 MB).
 struct Sched {
-  int rounds, rounds2;     // rounds / rounds in which both virtual slots hold a super-tile
-  int nevals;
+  int rounds, rounds2;     // super-tiles of virtual slot 0 / of virtual slot 1 (rounds2 <= rounds)
+  int nevals, lag;
   __device__ __forceinline__ uint32_t jobs() const { return (uint32_t)(rounds + rounds2) * (uint32_t)nevals * 2u; }
+  __device__ __forceinline__ int iters() const { const int a = rounds * nevals, b = rounds2 > 0 ? rounds2 * nevals + lag : 0; return a > b ? a : b; }
+  __device__ __forceinline__ bool active(int it, int v) const {
+    return v == 0 ? it < rounds * nevals : (it >= lag && it - lag < rounds2 * nevals);
+  }
 };
 
-struct JobIter {
-  int r = 0, ev = 0, cv = 0, v = 0;
+struct JobIter {        // conv jobs in issue order: for every iteration, conv1 of each active slot, then conv2 of each
+  int it = 0, cv = 0, v = 0;
   __device__ __forceinline__ void next(const Sched& s) {
-    const int nv = r < s.rounds2 ? 2 : 1;
-    if (++v < nv) return;
-    v = 0;
-    if (++cv < 2) return;
-    cv = 0;
-    if (++ev < s.nevals) return;
-    ev = 0; ++r;
+    const int n = s.iters();
+    do {
+      if (++v == 2) { v = 0; if (++cv == 2) { cv = 0; ++it; } }
+    } while (it < n && !s.active(it, v));
   }
 };
 
@@ -247,7 +260,7 @@ template <int NK>
 __device__ __forceinline__ void stage_in_quad(float (&x)[8][4], const float* __restrict__ y, const float* const (&src)[6],
                                               const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid) {
   using A = Arith<float>;
-  constexpr int B = NK <= 1 ? 4 : (NK <= 3 ? 2 : 1);       // channels per batch: about 8-12 128-bit loads in flight
+  constexpr int B = NK <= 1 ? 4 : 2;       // channels per batch (one or two GroupNorm groups): 8-12 128-bit loads in flight
 #pragma unroll
   for (int c0 = 0; c0 < 8; c0 += B) {
     float4 yv[B], kv[NK][B];
@@ -403,6 +416,42 @@ __device__ __forceinline__ void producer_loop(const Smem& sm, const Sched& sc, c
   __syncwarp();
 }
 
+// Aux warp 18: L2 prefetcher. The k tensors of the ~1200 images in flight do not stay in the L2 between two stages of a
+// step (live set ~130 MB, reuse distance one iteration), so about half of the stage-combination loads used to be DRAM
+// round trips in the middle of a latency-bound worker phase. This warp follows the conv-job schedule and, when conv2 of
+// (slot v, evaluation e) completes - i.e. while the workers run W3 of v and a whole phase of the other slot - asks the
+// TMA engine to bring the inputs of v's NEXT stage combination (y, k1..k_{e+1} of its 4 images; for e = 5 the y and k1 of
+// the next super-tile) back into the L2: one 64 KB bulk prefetch per tensor. Mistimed prefetches are harmless.
+__device__ __forceinline__ void prefetch_loop(const Smem& sm, const Sched& sc, const FusedArgs& a, int cur, int stride) {
+  if (a.mode != MODE_STEP) return;
+  const bool lead = ptx::elect_one();
+  const FusedWs& w = a.w;
+  auto fetch = [&](int v, int k) {          // inputs of slot v's k-th evaluation
+    const int r = k / sc.nevals, e = k - r * sc.nevals;
+    if (r >= (v == 0 ? sc.rounds : sc.rounds2)) return;
+    const int img0 = ((int)blockIdx.x * 2 + v + r * stride) * kImgs;
+    int n = a.g.N - img0; n = n > kImgs ? kImgs : n;
+    if (n <= 0) return;
+    const size_t off = (size_t)img0 * kC * 64;
+    const uint32_t bytes = (uint32_t)n * kC * 64 * 4;
+    ptx::bulk_prefetch_l2(w.Y[cur] + off, bytes);
+    ptx::bulk_prefetch_l2(w.F[cur] + off, bytes);
+    for (int j = (e == 5 ? 1 : 0); j < e && j < 5; ++j) ptx::bulk_prefetch_l2(w.K[j] + off, bytes);
+  };
+  if (lead) { fetch(0, 0); fetch(1, 0); }
+  JobIter it;
+  uint32_t nacc[2] = {0u, 0u};
+  const uint32_t njobs = sc.jobs();
+#pragma unroll 1
+  for (uint32_t job = 0; job < njobs; ++job) {
+    const int v = it.v;
+    if (!ptx::mbar_wait_relaxed(sm.bar_acc + 8 * v, nacc[v] & 1)) return;      // (a stuck barrier is reported by the workers)
+    ++nacc[v];
+    if (it.cv == 1 && lead) fetch(v, it.it - (v ? sc.lag : 0) + 1);
+    it.next(sc);
+  }
+}
+
 __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uint32_t tmem, bool split, bool& timeout) {
   const bool lead = ptx::elect_one();
   JobIter it;
@@ -412,10 +461,16 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
   uint32_t nready[2] = {0u, 0u};
   uint32_t tile = 0;
   const uint32_t njobs = sc.jobs();
+#ifdef NODE_STEP8_DEBUG
+  const bool rec_ph = blockIdx.x == 0 && lead;
+  long long last_ph = clock64();
+#endif
 #pragma unroll 1
   for (uint32_t job = 0; job < njobs; ++job) {
     const int v = it.v;
+    S8_STAMP(16);
     if (!timeout && !ptx::mbar_wait(sm.bar_ready + 8 * v, nready[v] & 1)) timeout = true;
+    S8_STAMP(17);
     ++nready[v];
     ptx::tc_fence_after();
     const uint32_t abase = sm.abase + (uint32_t)v * kVBytes + kLead + 2 * kSlotB;       // tile 0, slot 0, chunk 0, hi part
@@ -423,7 +478,9 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap, ++tile) {
       const uint32_t slot = tile % kRing;
+      S8_STAMP(18);
       if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tile / kRing) & 1)) timeout = true;
+      S8_STAMP(19);
       ptx::tc_fence_after();
       const int off = (tap / 3 - 1) * 2 * kSlotB + (tap % 3 - 1) * 16;
       const uint32_t a_tap = a_lo0 + (uint32_t)(off >> 4);           // arithmetic shift: off may be negative, never borrows
@@ -531,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   const int stride = gridDim.x * 2;
   Sched sc;
   sc.nevals = a.mode == MODE_STEP ? 6 : 1;
+  sc.lag = a.mode == MODE_STEP ? 3 : 0;
   {
     const int u0 = blockIdx.x * 2, u1 = u0 + 1;
     sc.rounds = u0 < NST ? (NST - u0 + stride - 1) / stride : 0;
@@ -540,12 +598,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   bool timeout = false;
   double acc0 = 0.0, acc1 = 0.0;
   bool bad = false;
+  const bool prefetch_on = (a.nw & 1) == 0;          // tuning switch (NODE_B200_STEP8_PREFETCH=0 sets bit 0)
 
   if (tid >= kWorkers) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
     const int aw = __shfl_sync(0xffffffffu, (tid - kWorkers) >> 5, 0);
     if (aw == 0) issuer_loop(sm, sc, tmem, split, timeout);
     else if (aw == 1) producer_loop(sm, sc, w.w16, timeout);
+    else if (aw == 2 && prefetch_on) prefetch_loop(sm, sc, a, a.mode == MODE_STEP ? ctl->cur : 0, stride);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
     Pos me;
@@ -572,6 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
     float* const Ycur = w.Y[cur];
     const float* const Fcur = w.F[cur];
     uint32_t nacc[2] = {0u, 0u};
+#ifdef NODE_STEP8_DEBUG
+    const bool rec_ph = blockIdx.x == 0 && tid == 0 && a.mode == MODE_STEP;
+    long long last_ph = clock64();
+#endif
     auto publish = [&](int v) {
       ptx::fence_proxy_async();          // my entries of the A image -> visible to the tensor core
       ptx::tc_fence_before();            // my tcgen05.ld of the previous accumulators are done
@@ -584,17 +648,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
       ptx::tc_fence_after();
     };
 
+    const int n_iters = sc.iters();
+    constexpr int nv = 2;
 #pragma unroll 1
-    for (int r = 0; r < sc.rounds; ++r) {
-      const int nv = r < sc.rounds2 ? 2 : 1;
-#pragma unroll 1
-      for (int ev = 0; ev < sc.nevals; ++ev) {
-        const float t_state = a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit);
-        const float t = a.tsign * t_state;                  // reversed-time wrapper (misc.py:184-187)
+    for (int it = 0; it < n_iters; ++it) {
+      {
 
         // ---- W1: stage input (rk_common.py:49-51) -> GN1 -> ReLU -> A image of conv1, quad mapping
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
+          if (!sc.active(it, v)) continue;
+          const int kk_ = it - (v ? sc.lag : 0), r = kk_ / sc.nevals, ev = kk_ - r * sc.nevals;
           const int st = blockIdx.x * 2 + v + r * stride;
           const int img = st * kImgs + qd.il;
           const bool valid = img < a.g.N;
@@ -644,109 +708,150 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
               stage_in_quad<5>(x, Ycur, src, hc, ynew, p0, valid);
             }
           }
+          S8_STAMP(0);
           float4 af[4];
           gn_affine_quad(sm, qd, 0, x, a.eps, w.scal[0], af);
+          S8_STAMP(1);
           affine_to_A_quad(qd, sm.abase + (uint32_t)v * kVBytes, x, af, split);
           publish(v);
+          S8_STAMP(2);
         }
 
         // ---- W2: conv1 epilogue -> GN2 -> ReLU -> A image of conv2 (model.py:343-346), position mapping
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
+          if (!sc.active(it, v)) continue;
+          const int kk_ = it - (v ? sc.lag : 0), r = kk_ / sc.nevals, ev = kk_ - r * sc.nevals;
+          const float t = a.tsign * (a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit));   // misc.py:184-187
+          S8_STAMP(15);
           wait_acc(v);
+          S8_STAMP(3);
           float x[32];
           conv_read_pos(sm, me, x, tmem, v, 0, w.scal[4], t, split);
+          S8_STAMP(4);
           gn_affine_pos(sm, me, 1, x, a.eps, w.scal[1]);
+          S8_STAMP(5);
           affine_to_A_pos(sm, me, sm.abase + (uint32_t)v * kVBytes, x, split);
           publish(v);
+          S8_STAMP(6);
         }
 
-        // ---- W3: conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller
+        // ---- W3: conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller.
+        // The accumulators are read in the position mapping (tensor-memory lanes), staged as fp32 through the data entries
+        // of the now idle A image (a position's 16 entries of 16 B hold exactly its 64 channels; chunk kc <- channels
+        // 8kc..8kc+7, so a quad warp reads back exactly the entries it overwrites in its next W1) and everything else -
+        // GroupNorm 3, the k store, error norm / dense-output mid-point - runs in the quad mapping with 128-bit accesses.
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
+          if (!sc.active(it, v)) continue;
+          const int kk_ = it - (v ? sc.lag : 0), r = kk_ / sc.nevals, ev = kk_ - r * sc.nevals;
+          const float t = a.tsign * (a.mode == MODE_STEP ? ctl->ts32[ev + 1] : (a.mode == MODE_PROBE ? ctl->ts32[1] : a.t_explicit));   // misc.py:184-187
+          S8_STAMP(15);
           wait_acc(v);
-          const int st = blockIdx.x * 2 + v + r * stride;
-          const int img = st * kImgs + me.il;
-          const bool valid = img < a.g.N;
-          float x[32];
-          conv_read_pos(sm, me, x, tmem, v, 1, w.scal[5], t, split);
-          gn_affine_pos(sm, me, 2, x, a.eps, a.tsign);
+          S8_STAMP(7);
+          const uint32_t vbase = sm.abase + (uint32_t)v * kVBytes;
           {
-            const float4* af = sm.aff + me.il * 32 + 16 * me.h;
+            float x[32];
+            conv_read_pos(sm, me, x, tmem, v, 1, w.scal[5], t, split);
+            const uint32_t row = vbase + me.arow;
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
-              const float4 p = af[g];
-              x[2 * g] = fmaf(x[2 * g], p.x, p.z);              // the time sign is folded into p
-              x[2 * g + 1] = fmaf(x[2 * g + 1], p.y, p.w);
+            for (int j = 0; j < 4; ++j) {
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + j * kLBO), "f"(x[8 * j]), "f"(x[8 * j + 1]), "f"(x[8 * j + 2]), "f"(x[8 * j + 3]) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + kAPart + j * kLBO), "f"(x[8 * j + 4]), "f"(x[8 * j + 5]), "f"(x[8 * j + 6]), "f"(x[8 * j + 7]) : "memory");
             }
           }
-          if (!valid) continue;
-          const size_t p0 = (size_t)img * kC * HW + (size_t)(32 * me.h) * HW + me.pix;
-          float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : w.F[cur ^ 1]) : (a.mode == MODE_F0 ? w.F[cur] : (a.mode == MODE_EVAL ? a.k_out : nullptr));
-          if (kdst != nullptr) {
+          S8_STAMP(8);
+          group_sync(me.grp);
+          const int st = blockIdx.x * 2 + v + r * stride;
+          const int img = st * kImgs + qd.il;
+          const bool valid = img < a.g.N;
+          float x[8][4];
+          {
+            const uint32_t row = vbase + qd.arow;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) kdst[p0 + (size_t)c * HW] = x[c];
+            for (int e = 0; e < 4; ++e) {
+              float4 lo4, hi4;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo4.x), "=f"(lo4.y), "=f"(lo4.z), "=f"(lo4.w) : "r"(row + e * 16));
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi4.x), "=f"(hi4.y), "=f"(hi4.z), "=f"(hi4.w) : "r"(row + kAPart + e * 16));
+              x[0][e] = valid ? lo4.x : 0.f; x[1][e] = valid ? lo4.y : 0.f; x[2][e] = valid ? lo4.z : 0.f; x[3][e] = valid ? lo4.w : 0.f;
+              x[4][e] = valid ? hi4.x : 0.f; x[5][e] = valid ? hi4.y : 0.f; x[6][e] = valid ? hi4.z : 0.f; x[7][e] = valid ? hi4.w : 0.f;
+            }
           }
+          float4 af[4];
+          gn_affine_quad(sm, qd, 2, x, a.eps, a.tsign, af);        // the time sign is folded into (a, b)
+          S8_STAMP(9);
+          if (!valid) continue;
+          const size_t p0 = (size_t)img * kC * HW + (size_t)(8 * qd.kc) * HW + qd.pix;
+          float* kdst = a.mode == MODE_STEP ? (ev < 5 ? w.K[ev] : w.F[cur ^ 1]) : (a.mode == MODE_F0 ? w.F[cur] : (a.mode == MODE_EVAL ? a.k_out : nullptr));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 p = af[c >> 1];
+            const float aa = (c & 1) ? p.y : p.x, bb = (c & 1) ? p.w : p.z;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[c][e] = fmaf(x[c][e], aa, bb);
+            if (kdst != nullptr) *reinterpret_cast<float4*>(kdst + p0 + (size_t)c * HW) = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
+          }
+          S8_STAMP(10);
           if (a.mode == MODE_F0) {               // misc.py:121-126
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float y = a.y_in[p0 + (size_t)c * HW];
-              const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-              const float uu = A::div(y, scale), vv = A::div(x[c], scale);
-              acc0 += (double)A::mul(uu, uu);
-              acc1 += (double)A::mul(vv, vv);
+            for (int c = 0; c < 8; ++c) {
+              const float4 y4 = ptx::ldg128_ordered(a.y_in + p0 + (size_t)c * HW);
+              const float ya[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float scale = A::add(atol, A::mul(fabsf(ya[e]), rtol));
+                const float uu = A::div(ya[e], scale), vv = A::div(x[c][e], scale);
+                acc0 += (double)A::mul(uu, uu);
+                acc1 += (double)A::mul(vv, vv);
+              }
             }
           } else if (a.mode == MODE_PROBE) {     // misc.py:136
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float y = Ycur[p0 + (size_t)c * HW];
-              const float scale = A::add(atol, A::mul(fabsf(y), rtol));
-              const float uu = A::div(A::sub(x[c], Fcur[p0 + (size_t)c * HW]), scale);
-              acc0 += (double)A::mul(uu, uu);
+            for (int c = 0; c < 8; ++c) {
+              const float4 y4 = ptx::ldg128_ordered(Ycur + p0 + (size_t)c * HW), f4 = ptx::ldg128_ordered(Fcur + p0 + (size_t)c * HW);
+              const float ya[4] = {y4.x, y4.y, y4.z, y4.w}, fa[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float scale = A::add(atol, A::mul(fabsf(ya[e]), rtol));
+                const float uu = A::div(A::sub(x[c][e], fa[e]), scale);
+                acc0 += (double)A::mul(uu, uu);
+              }
             }
           } else if (a.mode == MODE_STEP && ev == 5) {      // rk_common.py:60, misc.py:146-157, dopri5.py:39-42
             const float* ce = sm.coef + 7 * 8;
             const float* cm = sm.coef + 6 * 8;
             const float* const Ynew = w.Y[cur ^ 1];
+            const float* const srcs[7] = {Ycur, Ynew, Fcur, w.K[1], w.K[2], w.K[3], w.K[4]};
             float part = 0.f;
-            float ld[2][2][6];
-            auto load = [&](int b, int c) {
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const size_t o = p0 + (size_t)(c + i) * HW;
-                ld[b][i][0] = ptx::ldg_ordered(Ycur + o); ld[b][i][1] = ptx::ldg_ordered(Ynew + o);
-                ld[b][i][2] = ptx::ldg_ordered(Fcur + o); ld[b][i][3] = ptx::ldg_ordered(w.K[1] + o);
-                ld[b][i][4] = ptx::ldg_ordered(w.K[2] + o); ld[b][i][5] = ptx::ldg_ordered(w.K[3] + o);
-              }
-            };
-            load(0, 0);
+            for (int c = 0; c < 8; ++c) {
+              float4 ld[1][7];
+              constexpr int b = 0;
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const int b = (c >> 1) & 1;
-              const float k6a = ptx::ldg_ordered(w.K[4] + p0 + (size_t)c * HW), k6b = ptx::ldg_ordered(w.K[4] + p0 + (size_t)(c + 1) * HW);
-              if (c + 2 < 32) load(b ^ 1, c + 2);
-              __syncwarp(__activemask());
+              for (int j = 0; j < 7; ++j) ld[0][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)c * HW);
+              float mid[4];
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const size_t o = p0 + (size_t)(c + i) * HW;
-                const float y0 = ld[b][i][0], y1 = ld[b][i][1];
-                const float kk[7] = {ld[b][i][2], 0.f, ld[b][i][3], ld[b][i][4], ld[b][i][5], i == 0 ? k6a : k6b, x[c + i]};
-                float e = 0.f, md = 0.f;
+              for (int e = 0; e < 4; ++e) {
+                auto el = [&](const float4& q) { return e == 0 ? q.x : (e == 1 ? q.y : (e == 2 ? q.z : q.w)); };
+                const float y0 = el(ld[b][0]), y1 = el(ld[b][1]);
+                const float kk[7] = {el(ld[b][2]), 0.f, el(ld[b][3]), el(ld[b][4]), el(ld[b][5]), el(ld[b][6]), x[c][e]};
+                float er = 0.f, md = 0.f;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) {
                   if (j == 1) continue;
-                  e = A::add(e, A::mul(ce[j], kk[j]));
+                  er = A::add(er, A::mul(ce[j], kk[j]));
                   md = A::add(md, A::mul(cm[j], kk[j]));
                 }
                 bad |= !isfinite(y0);
                 const float tol = A::add(atol, A::mul(rtol, A::max(fabsf(y0), fabsf(y1))));
-                const float qv = A::div(e, tol);
+                const float qv = A::div(er, tol);
                 part += A::mul(qv, qv);
-                w.YMID[o] = A::add(y0, md);
+                mid[e] = A::add(y0, md);
               }
-              __syncwarp(__activemask());
+              *reinterpret_cast<float4*>(w.YMID + p0 + (size_t)c * HW) = make_float4(mid[0], mid[1], mid[2], mid[3]);
             }
             acc0 += (double)part;
+            S8_STAMP(11);
           }
         }
       }
@@ -768,8 +873,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   if (tid < 32) ptx::tmem_dealloc(tmem, kTmemCols);
 }
 
-static int launch_step8(const FusedArgs& a, cudaStream_t st) {
+static int launch_step8(const FusedArgs& a_in, cudaStream_t st) {
   constexpr size_t smem = smem_bytes();
+  FusedArgs a = a_in;
+  static const char* pf = getenv("NODE_B200_STEP8_PREFETCH");
+  a.nw = (pf != nullptr && pf[0] == '0') ? 1 : 0;
   NODE_SET_SMEM_ONCE(k_step8, smem);
   const int NST = (a.g.N + kImgs - 1) / kImgs;
   int grid = (NST + 1) / 2;
@@ -779,3 +887,11 @@ static int launch_step8(const FusedArgs& a, cudaStream_t st) {
 }
 
 }}  // namespace node::s8
+
+#ifdef NODE_STEP8_DEBUG
+extern "C" int node_b200_step8_phase_read(long long* host, int clear) {
+  int rc = (int)cudaMemcpyFromSymbol(host, node::s8::g_s8_phase, sizeof(long long) * 32);
+  if (clear) { static long long z[32]; rc |= (int)cudaMemcpyToSymbol(node::s8::g_s8_phase, z, sizeof(z)); }
+  return rc;
+}
+#endif

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libnode_b200.so')
+LIB_PATH = os.environ.get('NODE_B200_LIB') or os.path.join(_HERE, 'lib', 'libnode_b200.so')   # override: tuning builds
 ABI_VERSION = 1
 
 F32, F64 = 0, 1
