@@ -59,6 +59,25 @@ __global__ void k_prepare16_tiles(FusedWs w, int H, int W, const float* c1w, con
     const int64_t dst = ((int64_t)(cv * 9 + tap) * 128 + row) * 64 + chunk * 8 + (cin & 7);
     w.w16[dst] = *reinterpret_cast<const uint16_t*>(&val);
   }
+  // CTA-pair half tiles (tcgen05.mma.cta_group::2: each CTA of the pair holds half of the B rows). Row order chosen so that
+  // all three products of the split land in the right accumulator columns (see step8_engine.cuh / tools/pair_test.cu):
+  //   CTA 0: rows 0..31 = w_hi[0..31],  rows 32..63 = w_lo[32..63];   CTA 1: rows 0..31 = w_hi[32..63], rows 32..63 = w_lo[0..31]
+  for (int i = tid; i < 2 * 9 * 2 * 64 * 64; i += nth) {
+    int r = i;
+    const int cin = r % 64; r /= 64;
+    const int row = r % 64; r /= 64;
+    const int cta = r % 2; r /= 2;
+    const int tap = r % 9; r /= 9;
+    const int cv = r;
+    const bool is_hi = row < 32;
+    const int co = cta == 0 ? row : (is_hi ? 32 + row : row - 32);
+    const float v = cw[cv][((int64_t)co * (kC + 1) + cin + 1) * 9 + tap] * w.scal[2 + cv];
+    const __half hi = __float2half_rn(v);
+    const __half val = is_hi ? hi : __float2half_rn(v - __half2float(hi));
+    const int chunk = (cin >> 3) ^ (row & 7);
+    const int64_t dst = (((int64_t)(cv * 9 + tap) * 2 + cta) * 64 + row) * 64 + chunk * 8 + (cin & 7);
+    w.w16p[dst] = *reinterpret_cast<const uint16_t*>(&val);
+  }
   // Tmap border classes: class = 3*rowclass + colclass, 0 = first, 1 = interior, 2 = last row / column
   for (int i = tid; i < 2 * 9 * kC; i += nth) {
     const int co = i % kC, cls = (i / kC) % 9, cv = i / (9 * kC);

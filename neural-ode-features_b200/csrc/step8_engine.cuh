@@ -7,17 +7,20 @@
 //     two zero slots separate the tiles. With the A descriptor's stride-byte-offset = 144 a 3x3 tap (dy, dx) is the byte
 //     offset dy*288 + dx*16: no im2col, no per-tap staging, and NO padding rows in M (the strip tiling of step_engine.cuh
 //     multiplies 25 % zeros at 8x8). tools/sbo_test.cu checks the layout against a scalar reference on the device.
+//   * CTA PAIRS (tcgen05.mma.cta_group::2, cluster of two CTAs on one TPC). One MMA covers 256 rows - the 128-row tile of
+//     EACH CTA - and each CTA holds only HALF of the weight rows of a tap (8 KB instead of 16 KB): the shared-memory
+//     operand traffic that bound the single-CTA SS-mode stream drops below the math time, the weight ring is 6 taps deep
+//     in the same 48 KB, and the L2 -> SM weight stream halves. The pair's leader CTA issues; the peer's workers signal
+//     "A image ready" on the leader's mbarrier through DSMEM, a relay warp of the peer forwards "weight half landed",
+//     and tcgen05.commit multicasts completion to both CTAs. tools/pair_test.cu is the stand-alone check of this protocol
+//     and of the column bookkeeping of the fp16 split under the N split.
 //   * ONE SOFTWARE-PIPELINED CHAIN PER CTA instead of two independent slots: all 512 worker threads work on super-tile
 //     S0 (4 images, M = 256), publish its A image and move straight on to super-tile S1 while a dedicated warp issues
-//     S0's tcgen05.mma stream; the threads only come back to S0 when they have finished S1's phase. The workers never
-//     idle on a conv job (the two-slot kernel spent 40 % of its time there) and the issuing thread never competes with
-//     its own worker role.
-//   * TWO THREADS PER POSITION (32 channels each) in the accumulator epilogues, and a QUAD mapping (4 pixels x 8 channels
-//     per thread, 128-bit global accesses, GroupNorm statistics inside a half warp: no shared memory, no barrier) for the
-//     Runge-Kutta stage combination -> GroupNorm 1 -> ReLU -> A image phase, which needs no tensor-memory access.
-//   * the aux warp is weight producer and MMA issuer in one: after issuing tap i it requests tile i+2 into the ring slot
-//     tap i-1 has just retired from (3-deep ring of 16 KB tiles, TMA bulk copies).
-// fp32 contract by FP16 operand splitting exactly as in step_engine.cuh (a_hi*[w_hi;w_lo] N=128 + a_lo*w_hi N=64).
+//     S0's tcgen05.mma stream; the threads only come back to S0 when they have finished S1's phase.
+//   * TWO THREADS PER POSITION (32 channels each) where tensor memory is read, and a QUAD mapping (4 pixels x 8 channels
+//     per thread, 128-bit global accesses, GroupNorm statistics inside a half warp: no shared memory, no barrier)
+//     everywhere else; the conv2 accumulators are transposed into the quad mapping through the idle A image.
+// fp32 contract by FP16 operand splitting as in step_engine.cuh (a_hi*[w_hi;w_lo] N=128 + a_lo*w_hi N=64).
 #pragma once
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -31,7 +34,8 @@ constexpr int kLBO = kChunkSlots * kSlotB;        // 5184 B between k-chunks
 constexpr int kAPart = 8 * kLBO;                  // hi or lo part of one super-tile image
 constexpr int kLead = kSlotB, kTail = 2 * kSlotB;
 constexpr int kVBytes = kLead + 2 * kAPart + kTail;   // one virtual slot: 83,376 B
-constexpr int kRing = 3;                          // weight ring depth (taps)
+constexpr int kRing = 6;                          // weight ring depth (taps)
+constexpr int kHalfTile = kW16TileBytes / 2;      // one CTA's half of a tap's weight rows
 constexpr int kWorkers = 512, kThreads = kWorkers + 128;   // + one aux warpgroup: warp 16 issues the MMAs, warp 17 streams weights
 constexpr int kWorkerRegs = 112, kAuxRegs = 32;            // setmaxnreg moves registers INSIDE the CTA's launch allocation (640 x 96): the aux
                                                            // warpgroup frees 128*(96-32) = 8192, the workers take 512*(112-96) = 8192
@@ -41,9 +45,13 @@ constexpr int kImgs = 4;                          // images per super-tile
 // issuer ([16..23]) and the producer ([24..31]); read back with node_b200_step8_phase_read.
 #ifdef NODE_STEP8_DEBUG
 static __device__ long long g_s8_phase[32];
-#define S8_STAMP(i) do { if (rec_ph) { const long long now_ = clock64(); g_s8_phase[(i)] += now_ - last_ph; last_ph = now_; } } while (0)
+// accumulate in a private local array (registers: the indices are literals), flush once at the end
+#define S8_STAMP(i) do { if (rec_ph) { const long long now_ = clock64(); ph_acc[(i) & 15] += now_ - last_ph; last_ph = now_; } } while (0)
+#define S8_FLUSH(base) do { if (rec_ph) { for (int i_ = 0; i_ < 16; ++i_) g_s8_phase[(base) + i_] += ph_acc[i_]; } } while (0)
+static __shared__ long long s8_dbg_shared[16];
 #else
 #define S8_STAMP(i) do { } while (0)
+#define S8_FLUSH(base) do { } while (0)
 #endif
 
 struct Smem {
@@ -57,13 +65,13 @@ struct Smem {
   float* coef;                     // [8][8] h * coefficient
   double* scratch;                 // 32 doubles
   uint32_t* illcond;               // [4] per 128-thread group
-  uint32_t bar_wfull, bar_wfree, bar_ready, bar_acc;
+  uint32_t bar_wfull, bar_wfree, bar_wpeer, bar_ready, bar_acc;    // wpeer / ready are used in the leader CTA only
   uint32_t* tmem_slot;
 };
 
 constexpr size_t smem_bytes() {
-  return 1024 + (size_t)kRing * kW16TileBytes + 2 * (size_t)kVBytes + 16 * 64 * 4 + 4 * 32 * 16 + 4 * 32 * 4 + 3 * 32 * 16 +
-         2 * 16 * 9 * 16 + 2 * 16 * 16 + 64 * 4 + 32 * 8 + 16 + 8 * (2 * kRing + 4) + 16;
+  return 1024 + (size_t)kRing * kHalfTile + 2 * (size_t)kVBytes + 16 * 64 * 4 + 4 * 32 * 16 + 4 * 32 * 4 + 3 * 32 * 16 +
+         2 * 16 * 9 * 16 + 2 * 16 * 16 + 64 * 4 + 32 * 8 + 16 + 8 * (3 * kRing + 4) + 16;
 }
 static_assert(smem_bytes() <= 227 * 1024, "shared memory budget");
 
@@ -226,14 +234,18 @@ __device__ __forceinline__ void affine_to_A_pos(const Smem& sm, const Pos& me, u
 // x <- acc/scale + bias + t*Tmap for output channels [32h, 32h+32) of this thread's position.
 __device__ __forceinline__ void conv_read_pos(const Smem& sm, const Pos& me, float (&x)[32], uint32_t tmem, int v, int cv, float inv_scale,
                                               float t, bool split) {
-  const uint32_t taddr = tmem + me.tcol + (uint32_t)(v * 256);
+  // columns of a pair accumulator: [hi 0-31 (+ a_lo*w_hi) | lo 32-63 (+ a_lo*w_hi 32-63) | hi 32-63 | lo 0-31]: output channel n is
+  // column n + column (n < 32 ? 96 + n : 32 + n); without the split, channel n is column n.
+  const uint32_t tbase = tmem + me.tcol + (uint32_t)(v * 256);
+  const uint32_t taddr = split ? tbase + (me.h ? 64u : 0u) : tbase + (uint32_t)(32 * me.h);
+  const uint32_t taddr2 = tbase + (me.h ? 32u : 96u);
   const float4* tm = sm.tm4 + (cv * 16 + 8 * me.h) * 9 + me.cls;
   const float4* bs = sm.bias4 + cv * 16 + 8 * me.h;
 #pragma unroll
   for (int c0 = 0; c0 < 32; c0 += 8) {
     uint32_t v0[8], v1[8];
     ptx::tmem_ld8(taddr + c0, v0);
-    if (split) ptx::tmem_ld8(taddr + 64 + c0, v1);
+    if (split) ptx::tmem_ld8(taddr2 + c0, v1);
     const float4 m0 = tm[(c0 >> 2) * 9], m1 = tm[((c0 >> 2) + 1) * 9], b0 = bs[c0 >> 2], b1 = bs[(c0 >> 2) + 1];
     const float ex[8] = {fmaf(t, m0.x, b0.x), fmaf(t, m0.y, b0.y), fmaf(t, m0.z, b0.z), fmaf(t, m0.w, b0.w),
                          fmaf(t, m1.x, b1.x), fmaf(t, m1.y, b1.y), fmaf(t, m1.z, b1.z), fmaf(t, m1.w, b1.w)};
@@ -391,66 +403,61 @@ __device__ __forceinline__ void affine_to_A_quad(const Quad& me, uint32_t vbase,
   }
 }
 
-__device__ __forceinline__ void request_tile(const Smem& sm, const uint16_t* __restrict__ w16, uint32_t slot, int cv, int tap) {
-  ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kW16TileBytes);
-  ptx::bulk_g2s(sm.wring + slot * kW16TileBytes, (const char*)w16 + (size_t)(cv * 9 + tap) * kW16TileBytes, kW16TileBytes,
+__device__ __forceinline__ void request_tile(const Smem& sm, const uint16_t* __restrict__ w16p, uint32_t slot, int cv, int tap, int cta) {
+  ptx::mbar_expect_tx(sm.bar_wfull + 8 * slot, kHalfTile);
+  ptx::bulk_g2s(sm.wring + slot * kHalfTile, (const char*)w16p + (size_t)((cv * 9 + tap) * 2 + cta) * kHalfTile, kHalfTile,
                 sm.bar_wfull + 8 * slot);
 }
 
-// The aux warps. Warp 17 streams the weight tiles (tile i = tap i % 9 of conv job i / 9, ring slot i % kRing, requested as
-// soon as tile i - kRing has retired); warp 16 waits for a virtual slot's A image, for the tiles to land, and issues the
-// tcgen05.mma stream of every conv job of the CTA in schedule order. Warp-uniform control flow, descriptors in uniform
-// registers, asynchronous instructions by one elected lane.
-__device__ __forceinline__ void producer_loop(const Smem& sm, const Sched& sc, const uint16_t* __restrict__ w16, bool& timeout) {
+// The aux warps. Warp 17 of EACH CTA streams that CTA's half tiles (tile i = tap i % 9 of conv job i / 9, ring slot
+// i % kRing, requested as soon as tile i - kRing has retired: the retirement is multicast to both CTAs). Warp 16 of the PEER
+// relays "my half of tile i has landed" to the leader's mbarrier. Warp 16 of the LEADER waits for a virtual slot's A image
+// (32 warp arrivals: both CTAs), for both halves of a tile, and issues the tcgen05.mma.cta_group::2 stream of every conv job
+// of the pair in schedule order. Warp-uniform control flow, descriptors in uniform registers, asynchronous instructions
+// by one elected lane.
+__device__ __forceinline__ void producer_loop(const Smem& sm, const Sched& sc, const uint16_t* __restrict__ w16p, int cta, bool& timeout) {
   const bool lead = ptx::elect_one();
   const uint32_t total = sc.jobs() * 9u;
   JobIter pit;
   int ptap = 0;
+#ifdef NODE_STEP8_DEBUG
+  const bool rec_ph = blockIdx.x == 0 && lead;
+  long long last_ph = clock64();
+  long long ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 #pragma unroll 1
   for (uint32_t i = 0; i < total; ++i) {
     const uint32_t slot = i % kRing;
+    S8_STAMP(8);
     if (i >= (uint32_t)kRing && !timeout && !ptx::mbar_wait(sm.bar_wfree + 8 * slot, ((i / kRing) - 1) & 1)) timeout = true;
-    if (lead) request_tile(sm, w16, slot, pit.cv, ptap);
+    S8_STAMP(9);
+    if (lead) request_tile(sm, w16p, slot, pit.cv, ptap, cta);
     if (++ptap == 9) { ptap = 0; pit.next(sc); }
+  }
+  __syncwarp();
+#ifdef NODE_STEP8_DEBUG
+  if (rec_ph) { g_s8_phase[24] += ph_acc[8]; g_s8_phase[25] += ph_acc[9]; }
+#endif
+}
+
+__device__ __forceinline__ void relay_loop(const Smem& sm, const Sched& sc, bool& timeout) {
+  // One lane per ring slot, each with its own chain tile -> wait -> signal: a single chain forwards one tile per DSMEM
+  // round trip (~1.6k clocks measured), slower than the tensor cores consume them.
+  const uint32_t total = sc.jobs() * 9u;
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane < (uint32_t)kRing) {
+    const uint32_t peer = ptx::mapa(sm.bar_wpeer + 8 * lane, 0);
+#pragma unroll 1
+    for (uint32_t i = lane; i < total; i += kRing) {
+      if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * lane, (i / kRing) & 1)) timeout = true;
+      ptx::mbar_arrive_cluster_relaxed(peer);
+    }
   }
   __syncwarp();
 }
 
-// Aux warp 18: L2 prefetcher. The k tensors of the ~1200 images in flight do not stay in the L2 between two stages of a
-// step (live set ~130 MB, reuse distance one iteration), so about half of the stage-combination loads used to be DRAM
-// round trips in the middle of a latency-bound worker phase. This warp follows the conv-job schedule and, when conv2 of
-// (slot v, evaluation e) completes - i.e. while the workers run W3 of v and a whole phase of the other slot - asks the
-// TMA engine to bring the inputs of v's NEXT stage combination (y, k1..k_{e+1} of its 4 images; for e = 5 the y and k1 of
-// the next super-tile) back into the L2: one 64 KB bulk prefetch per tensor. Mistimed prefetches are harmless.
-__device__ __forceinline__ void prefetch_loop(const Smem& sm, const Sched& sc, const FusedArgs& a, int cur, int stride) {
-  if (a.mode != MODE_STEP) return;
-  const bool lead = ptx::elect_one();
-  const FusedWs& w = a.w;
-  auto fetch = [&](int v, int k) {          // inputs of slot v's k-th evaluation
-    const int r = k / sc.nevals, e = k - r * sc.nevals;
-    if (r >= (v == 0 ? sc.rounds : sc.rounds2)) return;
-    const int img0 = ((int)blockIdx.x * 2 + v + r * stride) * kImgs;
-    int n = a.g.N - img0; n = n > kImgs ? kImgs : n;
-    if (n <= 0) return;
-    const size_t off = (size_t)img0 * kC * 64;
-    const uint32_t bytes = (uint32_t)n * kC * 64 * 4;
-    ptx::bulk_prefetch_l2(w.Y[cur] + off, bytes);
-    ptx::bulk_prefetch_l2(w.F[cur] + off, bytes);
-    for (int j = (e == 5 ? 1 : 0); j < e && j < 5; ++j) ptx::bulk_prefetch_l2(w.K[j] + off, bytes);
-  };
-  if (lead) { fetch(0, 0); fetch(1, 0); }
-  JobIter it;
-  uint32_t nacc[2] = {0u, 0u};
-  const uint32_t njobs = sc.jobs();
-#pragma unroll 1
-  for (uint32_t job = 0; job < njobs; ++job) {
-    const int v = it.v;
-    if (!ptx::mbar_wait_relaxed(sm.bar_acc + 8 * v, nacc[v] & 1)) return;      // (a stuck barrier is reported by the workers)
-    ++nacc[v];
-    if (it.cv == 1 && lead) fetch(v, it.it - (v ? sc.lag : 0) + 1);
-    it.next(sc);
-  }
-}
+constexpr uint32_t kIdF16N128M256 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t kIdF16N64M256 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
 
 __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uint32_t tmem, bool split, bool& timeout) {
   const bool lead = ptx::elect_one();
@@ -464,12 +471,13 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
 #ifdef NODE_STEP8_DEBUG
   const bool rec_ph = blockIdx.x == 0 && lead;
   long long last_ph = clock64();
+  long long ph_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 #pragma unroll 1
   for (uint32_t job = 0; job < njobs; ++job) {
     const int v = it.v;
     S8_STAMP(16);
-    if (!timeout && !ptx::mbar_wait(sm.bar_ready + 8 * v, nready[v] & 1)) timeout = true;
+    if (!timeout && !ptx::mbar_wait_cluster(sm.bar_ready + 8 * v, nready[v] & 1)) timeout = true;
     S8_STAMP(17);
     ++nready[v];
     ptx::tc_fence_after();
@@ -481,10 +489,12 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
       S8_STAMP(18);
       if (!timeout && !ptx::mbar_wait(sm.bar_wfull + 8 * slot, (tile / kRing) & 1)) timeout = true;
       S8_STAMP(19);
+      if (!timeout && !ptx::mbar_wait_cluster(sm.bar_wpeer + 8 * slot, (tile / kRing) & 1)) timeout = true;
+      S8_STAMP(20);
       ptx::tc_fence_after();
       const int off = (tap / 3 - 1) * 2 * kSlotB + (tap % 3 - 1) * 16;
       const uint32_t a_tap = a_lo0 + (uint32_t)(off >> 4);           // arithmetic shift: off may be negative, never borrows
-      const uint32_t b_lo0 = ((sm.wring + slot * kW16TileBytes) & 0x3FFFFu) >> 4;
+      const uint32_t b_lo0 = ((sm.wring + slot * kHalfTile) & 0x3FFFFu) >> 4;
       if (lead) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -496,23 +506,24 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
             const uint32_t first = (tap == 0 && ks == 0) ? 0u : 1u;
             if (split) {
               const uint64_t a_lo = pack(a_tap + (uint32_t)((mt * 18 * kSlotB + 2 * ks * kLBO + kAPart) >> 4), a_hiw);
-              ptx::mma_f16_ss(d, a_hi, bk, kIdF16N128, first);
-              ptx::mma_f16_ss(d, a_lo, bk, kIdF16N64, 1u);
+              ptx::mma2_f16_ss(d, a_hi, bk, kIdF16N128M256, first);
+              ptx::mma2_f16_ss(d, a_lo, bk, kIdF16N64M256, 1u);
             } else {
-              ptx::mma_f16_ss(d, a_hi, bk, kIdF16N64, first);
+              ptx::mma2_f16_ss(d, a_hi, bk, kIdF16N64M256, first);
             }
           }
         }
-        ptx::tc_commit(sm.bar_wfree + 8 * slot);
+        ptx::tc_commit_pair(sm.bar_wfree + 8 * slot, 3);
       }
     }
-    if (lead) ptx::tc_commit(sm.bar_acc + 8 * v);
+    if (lead) ptx::tc_commit_pair(sm.bar_acc + 8 * v, 3);
     __syncwarp();
     it.next(sc);
   }
+  S8_FLUSH(16);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   using A = Arith<float>;
   constexpr int HW = 64;
   extern __shared__ uint8_t smem_raw[];
@@ -520,7 +531,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   node_ctl_t* ctl = w.ctl;
   const int tid = threadIdx.x;
 
-  if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform
+  if ((a.mode == MODE_STEP || a.mode == MODE_PROBE) && ctl->done) return;   // uniform over the grid
+  const int cta = (int)ptx::cluster_ctarank();
 
   Smem sm;
   {
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
     const uint32_t al = (s0 + 1023u) & ~1023u;
     uint8_t* base = smem_raw + (al - s0);
     size_t o = 0;
-    sm.wring = al; o += (size_t)kRing * kW16TileBytes;
+    sm.wring = al; o += (size_t)kRing * kHalfTile;
     sm.abase = al + (uint32_t)o;
     uint4* az = reinterpret_cast<uint4*>(base + o);
     o += 2 * (size_t)kVBytes;
@@ -542,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
     sm.scratch = reinterpret_cast<double*>(base + o); o += 32 * 8;
     sm.bar_wfull = al + (uint32_t)o; o += 8 * kRing;
     sm.bar_wfree = al + (uint32_t)o; o += 8 * kRing;
+    sm.bar_wpeer = al + (uint32_t)o; o += 8 * kRing;
     sm.bar_ready = al + (uint32_t)o; o += 8 * 2;
     sm.bar_acc = al + (uint32_t)o; o += 8 * 2;
     sm.illcond = reinterpret_cast<uint32_t*>(base + o); o += 16;
@@ -572,40 +585,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
     sm.coef[tid] = A::mul(h, (float)c);
   }
   if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_ready + 8 * i, 16); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
+    for (int i = 0; i < kRing; ++i) { ptx::mbar_init(sm.bar_wfull + 8 * i, 1); ptx::mbar_init(sm.bar_wfree + 8 * i, 1); ptx::mbar_init(sm.bar_wpeer + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(sm.bar_ready + 8 * i, 32); ptx::mbar_init(sm.bar_acc + 8 * i, 1); }
     ptx::fence_mbar_init();
   }
-  if (tid < 32) ptx::tmem_alloc(ptx::smem_u32(sm.tmem_slot), kTmemCols);
+  if (tid < 32) ptx::tmem_alloc_pair(ptx::smem_u32(sm.tmem_slot), kTmemCols);
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();            // both CTAs' barriers exist before anybody arrives through DSMEM
   ptx::tc_fence_after();
   const uint32_t tmem = *sm.tmem_slot;
 
-  // ---- schedule: unit u = 2*cta + v takes super-tiles u, u + 2*grid, ...
+  // ---- schedule: the pair p takes super-tiles 4p + 2v + cta + r * (2 * grid) for its two virtual slots v, rounds r. Both CTAs of
+  // a pair run the SAME job sequence (the MMAs are issued for the pair): a slot is active in a round when the LEADER's
+  // super-tile exists; a peer super-tile beyond the batch is computed on zeros and never stored.
   const int NST = (a.g.N + kImgs - 1) / kImgs;
   const int stride = gridDim.x * 2;
+  const int unit0 = ((int)blockIdx.x >> 1) * 4;
   Sched sc;
   sc.nevals = a.mode == MODE_STEP ? 6 : 1;
-  sc.lag = a.mode == MODE_STEP ? 3 : 0;
-  {
-    const int u0 = blockIdx.x * 2, u1 = u0 + 1;
-    sc.rounds = u0 < NST ? (NST - u0 + stride - 1) / stride : 0;
-    sc.rounds2 = u1 < NST ? (NST - u1 + stride - 1) / stride : 0;
+  sc.lag = 0;
+  sc.rounds = unit0 < NST ? (NST - unit0 + stride - 1) / stride : 0;
+  sc.rounds2 = unit0 + 2 < NST ? (NST - (unit0 + 2) + stride - 1) / stride : 0;
+  // De-phase the pairs: every CTA runs the same phase sequence, and in lockstep all 148 SMs would hit the L2-bound stage
+  // combination (and then the tensor-bound phases) at the same time. A start offset of a fraction of an iteration per pair
+  // group spreads the L2 bursts (a.nw >> 1 = offset unit in units of 256 ns; 0 = off).
+  if (a.mode == MODE_STEP && (a.nw >> 1) != 0) {
+    const unsigned grp = (blockIdx.x >> 1) & 3u;
+    for (unsigned i = 0; i < grp * (unsigned)(a.nw >> 1); ++i) __nanosleep(256);
   }
   const bool split = a.conv_mode == CONV_F16X3;
   bool timeout = false;
   double acc0 = 0.0, acc1 = 0.0;
   bool bad = false;
-  const bool prefetch_on = (a.nw & 1) == 0;          // tuning switch (NODE_B200_STEP8_PREFETCH=0 sets bit 0)
 
   if (tid >= kWorkers) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kAuxRegs));
     const int aw = __shfl_sync(0xffffffffu, (tid - kWorkers) >> 5, 0);
-    if (aw == 0) issuer_loop(sm, sc, tmem, split, timeout);
-    else if (aw == 1) producer_loop(sm, sc, w.w16, timeout);
-    else if (aw == 2 && prefetch_on) prefetch_loop(sm, sc, a, a.mode == MODE_STEP ? ctl->cur : 0, stride);
+    if (aw == 0) { if (cta == 0) issuer_loop(sm, sc, tmem, split, timeout); else relay_loop(sm, sc, timeout); }
+    else if (aw == 1) producer_loop(sm, sc, w.w16p, cta, timeout);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
     Pos me;
@@ -617,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
       me.pix = row * 8 + e;
       me.cls = (row == 0 ? 0 : (row == 7 ? 2 : 1)) * 3 + (e == 0 ? 0 : (e == 7 ? 2 : 1));
       me.arow = (uint32_t)(kLead + (2 + me.mt * 18 + s) * kSlotB + e * 16 + 4 * me.h * kLBO);
-      me.tcol = ((uint32_t)(me.wq * 32) << 16) + (uint32_t)(me.mt * 128 + 32 * me.h);
+      me.tcol = ((uint32_t)(me.wq * 32) << 16) + (uint32_t)(me.mt * 128);
     }
     Quad qd;
     qd.lane = me.lane; qd.mt = me.mt; qd.kc = 4 * me.h + me.wq;
@@ -635,12 +654,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
 #ifdef NODE_STEP8_DEBUG
     const bool rec_ph = blockIdx.x == 0 && tid == 0 && a.mode == MODE_STEP;
     long long last_ph = clock64();
+    long long* const ph_acc = s8_dbg_shared;
+    if (tid < 16) s8_dbg_shared[tid] = 0;
+    __syncwarp();
 #endif
+    const uint32_t ready0 = ptx::mapa(sm.bar_ready, 0);          // the LEADER's barrier (DSMEM address; also valid in the leader itself)
     auto publish = [&](int v) {
-      ptx::fence_proxy_async();          // my entries of the A image -> visible to the tensor core
+      ptx::fence_proxy_async();          // my entries of the A image -> visible to the tensor cores of the pair
       ptx::tc_fence_before();            // my tcgen05.ld of the previous accumulators are done
       __syncwarp();
-      if (me.lane == 0) ptx::mbar_arrive(sm.bar_ready + 8 * v);
+      if (me.lane == 0) ptx::mbar_arrive_cluster(ready0 + 8 * v);
     };
     auto wait_acc = [&](int v) {
       if (!timeout && !ptx::mbar_wait_relaxed(sm.bar_acc + 8 * v, nacc[v] & 1)) timeout = true;
@@ -648,6 +671,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
       ptx::tc_fence_after();
     };
 
+    // L2 prefetch by ONE worker thread, a phase or two ahead of the use: the k tensors of the ~1200 images in flight do
+    // not survive in the L2 from one stage of a step to the next (live set ~130 MB, reuse distance one iteration), so without
+    // it about half of the stage-combination loads are DRAM round trips inside a latency-bound phase.
+    auto prefetch_inputs = [&](int v, int k, bool for_error_norm) {      // inputs of slot v's k-th evaluation
+      if (a.mode != MODE_STEP || tid != 0 || k < 0 || (a.nw & 1)) return;      // a.nw bit 0: NODE_B200_STEP8_PREFETCH=0
+      const int r = k / sc.nevals, e = k - r * sc.nevals;
+      if (r >= (v == 0 ? sc.rounds : sc.rounds2)) return;
+      const int img0 = (unit0 + 2 * v + cta + r * stride) * kImgs;
+      int n = a.g.N - img0; n = n > kImgs ? kImgs : n;
+      if (n <= 0) return;
+      const size_t off = (size_t)img0 * kC * HW;
+      const uint32_t bytes = (uint32_t)n * kC * HW * 4;
+      ptx::bulk_prefetch_l2(Ycur + off, bytes);
+      ptx::bulk_prefetch_l2(Fcur + off, bytes);
+      if (for_error_norm) {
+        for (int j = 1; j < 5; ++j) ptx::bulk_prefetch_l2(w.K[j] + off, bytes);
+      } else {
+        for (int j = (e == 5 ? 1 : 0); j < e && j < 5; ++j) ptx::bulk_prefetch_l2(w.K[j] + off, bytes);
+      }
+    };
     const int n_iters = sc.iters();
     constexpr int nv = 2;
 #pragma unroll 1
@@ -659,10 +702,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
         for (int v = 0; v < nv; ++v) {
           if (!sc.active(it, v)) continue;
           const int kk_ = it - (v ? sc.lag : 0), r = kk_ / sc.nevals, ev = kk_ - r * sc.nevals;
-          const int st = blockIdx.x * 2 + v + r * stride;
+          const int st = unit0 + 2 * v + cta + r * stride;
           const int img = st * kImgs + qd.il;
           const bool valid = img < a.g.N;
           const size_t p0 = (valid ? (size_t)img * kC * HW : (size_t)0) + (size_t)(8 * qd.kc) * HW + qd.pix;
+          if (v == 0) prefetch_inputs(1, it - sc.lag, false);          // slot 1's stage combination comes right after this one
           float x[8][4];
           if (a.mode == MODE_F0 || a.mode == MODE_EVAL) {
 #pragma unroll
@@ -726,6 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
           S8_STAMP(15);
           wait_acc(v);
           S8_STAMP(3);
+          if (ev == 5) prefetch_inputs(v, kk_, true);                  // the error norm re-reads y, k1, k3..k6 two phases from now
           float x[32];
           conv_read_pos(sm, me, x, tmem, v, 0, w.scal[4], t, split);
           S8_STAMP(4);
@@ -749,6 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
           S8_STAMP(15);
           wait_acc(v);
           S8_STAMP(7);
+          if (v == 1 || !sc.active(it, 1)) prefetch_inputs(0, it + 1, false);      // slot 0's next stage combination
           const uint32_t vbase = sm.abase + (uint32_t)v * kVBytes;
           {
             float x[32];
@@ -762,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
           }
           S8_STAMP(8);
           group_sync(me.grp);
-          const int st = blockIdx.x * 2 + v + r * stride;
+          const int st = unit0 + 2 * v + cta + r * stride;
           const int img = st * kImgs + qd.il;
           const bool valid = img < a.g.N;
           float x[8][4];
@@ -823,12 +869,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
             const float* const Ynew = w.Y[cur ^ 1];
             const float* const srcs[7] = {Ycur, Ynew, Fcur, w.K[1], w.K[2], w.K[3], w.K[4]};
             float part = 0.f;
+            float4 ld[2][7];                     // two channels (14 x 128 bits) in flight per batch
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              float4 ld[1][7];
-              constexpr int b = 0;
+              const int b = c & 1;
+              if (b == 0) {
 #pragma unroll
-              for (int j = 0; j < 7; ++j) ld[0][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)c * HW);
+                for (int j = 0; j < 7; ++j) { ld[0][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)c * HW); ld[1][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)(c + 1) * HW); }
+              }
               float mid[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -856,6 +904,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
         }
       }
     }
+    S8_FLUSH(0);
   }
 
   if (a.mode != MODE_EVAL) {
@@ -870,17 +919,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   if (timeout) atomicOr(&ctl->status, NODE_ST_WATCHDOG);
   ptx::tc_fence_before();
   __syncthreads();
-  if (tid < 32) ptx::tmem_dealloc(tmem, kTmemCols);
+  ptx::cluster_sync_all();            // neither CTA's tensor memory / barriers go away while the pair still uses them
+  if (tid < 32) ptx::tmem_dealloc_pair(tmem, kTmemCols);
 }
 
 static int launch_step8(const FusedArgs& a_in, cudaStream_t st) {
   constexpr size_t smem = smem_bytes();
   FusedArgs a = a_in;
   static const char* pf = getenv("NODE_B200_STEP8_PREFETCH");
-  a.nw = (pf != nullptr && pf[0] == '0') ? 1 : 0;
+  static const char* ph = getenv("NODE_B200_STEP8_DEPHASE");      // start offset per pair group in units of 256 ns (default 0: measured no gain)
+  a.nw = ((pf != nullptr && pf[0] == '0') ? 1 : 0) | ((ph != nullptr ? atoi(ph) : 0) << 1);
   NODE_SET_SMEM_ONCE(k_step8, smem);
   const int NST = (a.g.N + kImgs - 1) / kImgs;
-  int grid = (NST + 1) / 2;
+  int grid = 2 * ((NST + 3) / 4);                  // CTA pairs: 16 images per pair and round
   if (grid > kMaxGrid) grid = kMaxGrid;
   k_step8<<<grid, kThreads, smem, st>>>(a);
   return (int)cudaGetLastError();

@@ -33,4 +33,5 @@ tot = sum(v[i] for i in names)
 print('ODE block %.3f ms, %d step launches; worker thread 0 of CTA 0: %.0f clocks per step launch' % (a.elapsed_time(b), nst, tot))
 for i in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 15):
     print('   %-28s %9.0f  %5.1f%%' % (names[i], v[i], 100 * v[i] / tot))
-print('issuer: between jobs %.0f  wait A ready %.0f  (tap loop) issue+other %.0f  wait weights %.0f' % (v[16], v[17], v[18], v[19]))
+print('issuer: between jobs %.0f  wait A ready %.0f  (tap loop) issue+other %.0f  wait own weights %.0f  wait peer weights %.0f' % (v[16], v[17], v[18], v[19], v[20]))
+print('producer (CTA 0): request+loop %.0f  wait ring slot free %.0f' % (v[24], v[25]))
