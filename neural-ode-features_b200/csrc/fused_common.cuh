@@ -109,6 +109,7 @@ struct VjpArgs {
   float* chan_part;              // [grid][6][64]: dgamma1, dbeta1, dgamma2, dbeta2, dgamma3, dbeta3
   double* t_part;                // [grid]: sum GC*Tmap over both convolutions
   const float* t_dev;            // device scalar: the time the solver evaluates at
+  unsigned* gc_max;              // [2] bit patterns of max |GC1|, |GC2| over the batch (zeroed before the launch): k_wgrad's scale
   float tsign, eps;
 };
 
@@ -116,6 +117,8 @@ struct WgradArgs {
   Geo g;
   const float* R[2]; const float* GC[2];         // [N,64,H,W] fp32 (written by k_vjp)
   float* part;                                   // [splits][2 conv][9 tap][64 co][kWgCols]
+  const unsigned* gc_max;                        // [2] written by k_vjp
+  const float* scal;                             // FusedWs::scal: [0..1] = activation scales of conv1 / conv2 inputs
   int nsplit;
 };
 

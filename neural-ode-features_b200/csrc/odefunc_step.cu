@@ -115,7 +115,7 @@ bool step_engine_supports(int H, int W) {
 int launch_step_engine(const FusedArgs& a, cudaStream_t st) {
   const int H = a.g.H, W = a.g.W;
   if (H == 8 && W == 8) {
-    static const char* dense = getenv("NODE_B200_STEP8");          // "0": the strip-tiled two-slot kernel (cross-check / tuning aid)
+    const char* dense = getenv("NODE_B200_STEP8");                 // "0": the strip-tiled two-slot kernel (cross-check / tuning aid)
     if (dense != nullptr && dense[0] == '0') return launch_step_8x8(a, st);
     return launch_step8_dense(a, st);
   }

@@ -3,6 +3,7 @@
 // fused VJP kernel (vjp_engine.cuh) and the weight-gradient GEMM (wgrad_engine.cuh), the deterministic fold of
 // their per-CTA partials into the flat parameter gradient, and the C entry points.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include "fused_common.cuh"
 
@@ -12,7 +13,7 @@ constexpr int kNParam = 2 * (kC * (kC + 1) * 9 + kC) + 6 * kC;   // 75,392 (misc
 
 struct VjpWs {
   float* R[2]; float* GC[2];
-  float* chan_part; double* t_part; float* wpart;
+  float* chan_part; double* t_part; float* wpart; unsigned* gc_max;
 };
 
 static int64_t vjp_ws_layout(void* base, int N, int C, int H, int W, VjpWs* out) {
@@ -24,18 +25,20 @@ static int64_t vjp_ws_layout(void* base, int N, int C, int H, int W, VjpWs* out)
   const int64_t o_chan = take((int64_t)kMaxGrid * 384 * 4);
   const int64_t o_tp = take((int64_t)kMaxGrid * 8);
   const int64_t o_wp = take((int64_t)kWgSplits * 2 * 9 * 64 * kWgCols * 4);
+  const int64_t o_gm = take(16);
   if (out != nullptr) {
     char* b = (char*)base;
     out->R[0] = (float*)(b + o_t[0]); out->R[1] = (float*)(b + o_t[1]);
     out->GC[0] = (float*)(b + o_t[2]); out->GC[1] = (float*)(b + o_t[3]);
     out->chan_part = (float*)(b + o_chan); out->t_part = (double*)(b + o_tp); out->wpart = (float*)(b + o_wp);
+    out->gc_max = (unsigned*)(b + o_gm);
   }
   return o;
 }
 
 // Data-gradient weight tiles (sets 2, 3 of w16): dL/dr[q, ci] = sum_tap' sum_co GC[q + off(tap'), co] * W[co, ci+1, 8 - tap'],
-// i.e. the forward implicit GEMM with "cout" = ci, "cin" = co and flipped taps. bf16 hi (rows 0..63) / lo (rows 64..127),
-// 64 K-values per 128-byte row, SWIZZLE_128B image - same geometry as the forward tiles.
+// i.e. the forward implicit GEMM with "cout" = ci, "cin" = co and flipped taps. fp16 hi (rows 0..63) / lo (rows 64..127) of
+// w * scal[2 + cv] (the forward tiles' power-of-two weight scale), 64 K-values per 128-byte row, SWIZZLE_128B image.
 __global__ void k_prepare_dgrad_tiles(FusedWs w, const float* c1w, const float* c2w) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const float* cw[2] = {c1w, c2w};
@@ -46,9 +49,9 @@ __global__ void k_prepare_dgrad_tiles(FusedWs w, const float* c1w, const float* 
     const int tap = r % 9; r /= 9;
     const int cv = r;
     const int ci = row & 63;
-    const float v = cw[cv][((int64_t)co * (kC + 1) + ci + 1) * 9 + (8 - tap)];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 val = row < 64 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    const float v = cw[cv][((int64_t)co * (kC + 1) + ci + 1) * 9 + (8 - tap)] * w.scal[2 + cv];
+    const __half hi = __float2half_rn(v);
+    const __half val = row < 64 ? hi : __float2half_rn(v - __half2float(hi));
     const int chunk = (co >> 3) ^ (row & 7);
     const int64_t dst = ((int64_t)((2 + cv) * 9 + tap) * 128 + row) * 64 + chunk * 8 + (co & 7);
     w.w16[dst] = *reinterpret_cast<const uint16_t*>(&val);
@@ -129,6 +132,9 @@ extern "C" void* node_b200_vjp_buffer(void* vjp_workspace, int which, int N, int
   }
 }
 
+// operand scales of the fused workspace the last node_b200_odefunc_vjp call ran on (node_b200_wgrad is always called from there)
+static const float* g_wgrad_scal = nullptr;
+
 extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float* gc1, const float* r2, const float* gc2,
                                int N, int C, int H, int W, void* stream) {
   WgradArgs a{};
@@ -136,6 +142,7 @@ extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float
   VjpWs v;
   vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
   a.R[0] = r1; a.R[1] = r2; a.GC[0] = gc1; a.GC[1] = gc2; a.part = v.wpart;
+  a.gc_max = v.gc_max; a.scal = g_wgrad_scal;
   cudaStream_t st = (cudaStream_t)stream;
   if (H == 8 && W == 8) return launch_wgrad_8x8(a, st);
   if (H == 7 && W == 7) return launch_wgrad_7x7(a, st);
@@ -156,7 +163,10 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   a.y = y; a.adj = adj_y; a.f_out = f_out; a.vy_out = vjp_y;
   a.R[0] = v.R[0]; a.R[1] = v.R[1]; a.GC[0] = v.GC[0]; a.GC[1] = v.GC[1];
   a.chan_part = v.chan_part; a.t_part = v.t_part; a.t_dev = t_dev; a.tsign = tsign < 0 ? -1.f : 1.f; a.eps = 1e-5f;
+  a.gc_max = v.gc_max;
   cudaStream_t st = (cudaStream_t)stream;
+  NODE_CUDA_OK(cudaMemsetAsync(v.gc_max, 0, 16, st));
+  g_wgrad_scal = a.w.scal;
   int rc;
   if (H == 8 && W == 8) rc = launch_vjp_8x8(a, st);
   else if (H == 7 && W == 7) rc = launch_vjp_7x7(a, st);

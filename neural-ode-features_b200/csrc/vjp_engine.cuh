@@ -105,26 +105,70 @@ __device__ __forceinline__ void act_to_A(const VjpSmem& sm, const Who& me, int h
   }
 }
 
-// 32 gradient values -> bf16 hi/lo rows of the A image.
+// Gradient operands of the two data-gradient convolutions. Gradients have no a-priori bound, so their fp16 hi/lo split
+// (2^-22 relative, like the forward operands; the bf16 split used before was 2^-16 and dominated the adjoint's end-to-end
+// error) needs a scale from the data: the 32 values of a half are first STAGED as fp32 in this position's own entries of
+// the A image (16 entries x 16 B = its 64 channels; chunk c <- channels 8c..8c+3 in the hi part, 8c+4..8c+7 in the lo part)
+// while every thread tracks max|g|; after both halves the CTA agrees on a power-of-two scale for the super-tile and every
+// thread converts ITS OWN entries in place, chunk by chunk.
 template <class T>
-__device__ __forceinline__ void grad_to_A(const VjpSmem& sm, const Who& me, int hb, const float (&g)[32], bool valid) {
+__device__ __forceinline__ void grad_stage(const VjpSmem& sm, const Who& me, int hb, const float (&g)[32], bool valid, float& gmax) {
   const uint32_t row = sm.s.abase + (T::HALO + me.wt) * 16 + 4 * hb * T::LBO;
 #pragma unroll
-  for (int kc = 0; kc < 4; ++kc) {
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gmax = fmaxf(gmax, fabsf(g[8 * j + i]));
+    if (valid) {
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + j * T::LBO), "f"(g[8 * j]), "f"(g[8 * j + 1]), "f"(g[8 * j + 2]), "f"(g[8 * j + 3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + j * T::LBO), "f"(g[8 * j + 4]), "f"(g[8 * j + 5]), "f"(g[8 * j + 6]), "f"(g[8 * j + 7]) : "memory");
+    }
+  }
+}
+
+// Power-of-two scale that brings max|g| of the super-tile just below 2^14; returns the scale, leaves 1/scale in inv.
+template <class T>
+__device__ __forceinline__ float grad_scale(const VjpSmem& sm, const Who& me, float gmax, float& inv) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  float* red = sm.part64;                       // [NWARP] (free between the GroupNorm reductions)
+  slot_sync(0, T::P);
+  if (me.lane == 0) red[me.warp] = gmax;
+  slot_sync(0, T::P);
+  float m = 0.f;
+#pragma unroll
+  for (int w = 0; w < T::NWARP; ++w) m = fmaxf(m, red[w]);
+  int e = 0;
+  if (m > 0.f && m < 3.0e38f) {
+    int ex;
+    (void)frexpf(m, &ex);                       // m = f * 2^ex, f in [0.5, 1)
+    e = 14 - ex;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  }
+  inv = exp2f((float)-e);
+  return exp2f((float)e);
+}
+
+template <class T>
+__device__ __forceinline__ void grad_finalize_A(const VjpSmem& sm, const Who& me, float scale, bool valid) {
+  if (!valid) return;
+  const uint32_t row = sm.s.abase + (T::HALO + me.wt) * 16;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a[8];
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]) : "r"(row + c * T::LBO));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(row + T::A_PART + c * T::LBO));
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v0 = g[kc * 8 + 2 * j], v1 = g[kc * 8 + 2 * j + 1];
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-      const float2 hf = __bfloat1622float2(h);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+      const float v0 = a[2 * j] * scale, v1 = a[2 * j + 1] * scale;
+      const __half2 h = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
       hi[j] = *reinterpret_cast<const uint32_t*>(&h);
       lo[j] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    if (valid) {
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + kc * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + kc * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-    }
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + c * T::LBO), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + T::A_PART + c * T::LBO), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
   }
 }
 
@@ -333,6 +377,8 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
   bool timeout = false;
   uint32_t njob = 0;
   float tacc = 0.f;
+  float gc_max[2] = {0.f, 0.f};                  // max |GC1|, |GC2| over this CTA's images (operand scale of k_wgrad)
+  const float inv_sw1 = 1.0f / w.scal[2], inv_sw2 = 1.0f / w.scal[3];
 
   Who me;
   me.slot = 0; me.wt = tid; me.warp = tid >> 5; me.lane = tid & 31;
@@ -378,6 +424,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
     }
     vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);
     // ---- c2 -> GN3 = f; backward of GN3 with cotangent -a (adjoint.py:43)
+    float gmax = 0.f, ginv = 1.f;
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
       const size_t p0 = goff + (size_t)(32 * hb) * HW;
@@ -406,14 +453,18 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       for (int c = 0; c < 32; ++c) {
         if (valid) { a.GC[1][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
       }
-      grad_to_A<T>(sm, me, hb, g, valid);
+      grad_stage<T>(sm, me, hb, g, valid, gmax);
     }
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr2 over c2's columns
+    gc_max[1] = fmaxf(gc_max[1], gmax);
+    grad_finalize_A<T>(sm, me, grad_scale<T>(sm, me, gmax, ginv), valid);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);      // dL/dr2 over c2's columns
+    const float mul2 = ginv * inv_sw2;
+    gmax = 0.f;
     // ---- ReLU mask of GN2's output, backward of GN2
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
       const size_t p0 = goff + (size_t)(32 * hb) * HW;
-      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, 1.f, 0.f, valid);
+      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, mul2, 0.f, valid);
       vjp_tmem_read<T>(sm, me, hb, x, tmem, kColC1, 0, w.scal[4], t, valid);
       {
         const float2* stt = st2.stat + min(me.img_l, T::G - 1) * 32 + 16 * hb;
@@ -434,14 +485,17 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       for (int c = 0; c < 32; ++c) {
         if (valid) { a.GC[0][p0 + (size_t)c * HW] = g[c]; tacc = fmaf(g[c], tm[c], tacc); }
       }
-      grad_to_A<T>(sm, me, hb, g, valid);
+      grad_stage<T>(sm, me, hb, g, valid, gmax);
     }
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdBF16N64, njob, timeout);     // dL/dr1
+    gc_max[0] = fmaxf(gc_max[0], gmax);
+    grad_finalize_A<T>(sm, me, grad_scale<T>(sm, me, gmax, ginv), valid);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);      // dL/dr1
+    const float mul1 = ginv * inv_sw1;
     // ---- ReLU mask of GN1's output, backward of GN1 -> vjp_y
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
       const size_t p0 = goff + (size_t)(32 * hb) * HW;
-      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, 1.f, 0.f, valid);
+      vjp_tmem_read<T>(sm, me, hb, g, tmem, kColC2, -1, mul1, 0.f, valid);
 #pragma unroll
       for (int c = 0; c < 32; ++c) { const float v = a.y[p0 + (size_t)c * HW]; x[c] = valid ? v : 0.f; }
       {
@@ -476,6 +530,13 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
   }
   const double tsum = block_sum((double)tacc, sm.s.scratch);
   if (tid == 0) a.t_part[blockIdx.x] = tsum;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {                  // non-negative floats order like their bit patterns
+    float m = gc_max[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0 && m > 0.f && m < 3.0e38f) atomicMax(a.gc_max + q, __float_as_uint(m));
+  }
   if (timeout) atomicOr(&w.ctl->status, NODE_ST_WATCHDOG);
   ptx::tc_fence_before();
   __syncthreads();

@@ -4,7 +4,7 @@
 // M = co (64), N = ci (64 + the ones plane), K = every position of every image.
 //
 // Mapping: the step engine's zero-padded position strips again, now as the K dimension. Both operands are
-// staged once per super-tile as bf16 hi/lo images [8-channel chunk][position][8 values] - which is exactly the
+// staged once per super-tile as fp16 hi/lo images (power-of-two scaled) [8-channel chunk][position][8 values] - which is exactly the
 // MN-major no-swizzle UMMA layout (8 K-rows x 16 bytes per core matrix) - so a convolution tap is nothing but a
 // row offset in the B descriptor, like in the forward engine. One tcgen05.mma has M = 128 = [GC_hi ; GC_lo]
 // (16 chunks), K = 16 positions; B = [IN_hi | ones | 0] (N = 80) and B = IN_lo (N = 64) accumulate into the same
@@ -15,14 +15,15 @@
 // Per-CTA results go to a partial buffer that k_vjp_finalize folds in a fixed order (deterministic).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "step_engine.cuh"
 
 namespace node {
 
 
-// kind::f16, bf16 x bf16 -> fp32, A and B MN-major, M = 128
+// kind::f16, fp16 x fp16 -> fp32, A and B MN-major, M = 128
 __host__ __device__ constexpr uint32_t wg_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 template <int H_, int W_>
@@ -76,6 +77,20 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
   constexpr uint32_t g_lbo = 128u, g_sbo = (uint32_t)WT::G_STRIDE;
   constexpr uint32_t r_lbo = 128u, r_sbo = (uint32_t)WT::R_STRIDE;
 
+  // Operand scales (powers of two, exact): the activations are bounded a priori (the forward engine's scale), the gradients by
+  // the batch maximum k_vjp has just measured; fp16 hi/lo of the scaled values = 2^-22 relative (the bf16 split was 2^-16).
+  const float s_r = a.scal[cv];
+  float s_g = 1.f;
+  {
+    const float m = __uint_as_float(a.gc_max[cv]);
+    if (m > 0.f && m < 3.0e38f) {
+      int ex;
+      (void)frexpf(m, &ex);
+      int e = 14 - ex;
+      e = e > 100 ? 100 : (e < -100 ? -100 : e);
+      s_g = exp2f((float)e);
+    }
+  }
   const int NST = (a.g.N + T::G - 1) / T::G;
   bool timeout = false;
   uint32_t it = 0;
@@ -102,6 +117,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
       const uint32_t row = half == 0 ? grow : rrow;
       const uint32_t cstride = half == 0 ? (uint32_t)WT::G_STRIDE : (uint32_t)WT::R_STRIDE;
       const uint32_t lo_chunk0 = half == 0 ? 8u : 10u;
+      const float sc = half == 0 ? s_g : s_r;
       // all 64 loads of this half in flight at once (the kernel has one CTA per SM and registers to spare; staging
       // is latency-bound and never overlaps the MMAs of the same super-tile)
       float v[64];
@@ -117,10 +133,10 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float v0 = valid ? v[kc * 8 + 2 * j] : 0.f, v1 = valid ? v[kc * 8 + 2 * j + 1] : 0.f;
-          const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          const float2 hf = __bfloat1622float2(h);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+          const float v0 = valid ? v[kc * 8 + 2 * j] * sc : 0.f, v1 = valid ? v[kc * 8 + 2 * j + 1] * sc : 0.f;
+          const __half2 h = __floats2half2_rn(v0, v1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
           hi[j] = *reinterpret_cast<const uint32_t*>(&h);
           lo[j] = *reinterpret_cast<const uint32_t*>(&l);
         }
@@ -128,8 +144,8 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row + (lo_chunk0 + kc) * cstride), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
       }
     }
-    {   // the ones plane: channel 0 of chunk 8 (bf16 1.0 = 0x3F80), zero elsewhere
-      const uint32_t one = valid ? 0x00003F80u : 0u;
+    {   // the ones plane: channel 0 of chunk 8 (fp16 1.0 = 0x3C00), zero elsewhere
+      const uint32_t one = valid ? 0x00003C00u : 0u;
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rrow + 8u * (uint32_t)WT::R_STRIDE), "r"(one), "r"(0u), "r"(0u), "r"(0u) : "memory");
     }
     ptx::fence_proxy_async();
@@ -162,6 +178,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
     ptx::tc_fence_after();
   }
 
+  const float inv_g = 1.0f / s_g, inv_gr = inv_g / s_r;
   // ---- drain: rows 0-63 = GC_hi^T * IN, rows 64-127 = GC_lo^T * IN; their sum is this CTA's partial
   float* stage = reinterpret_cast<float*>(base);          // [128][kWgCols + 1] fp32 over the (now free) operand images
   const int warp = tid >> 5, lane = tid & 31;
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
     float* dst = a.part + ((size_t)(split * 2 + cv) * 9 + (tap0 + tp)) * 64 * kWgCols;
     for (int i = tid; i < 64 * kWgCols; i += blockDim.x) {
       const int co = i / kWgCols, n = i % kWgCols;
-      dst[i] = stage[co * (kWgCols + 1) + n] + stage[(64 + co) * (kWgCols + 1) + n];
+      dst[i] = (stage[co * (kWgCols + 1) + n] + stage[(64 + co) * (kWgCols + 1) + n]) * (n < 64 ? inv_gr : inv_g);   // the ones column carries no activation scale
     }
   }
   (void)timeout;
