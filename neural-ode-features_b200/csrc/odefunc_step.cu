@@ -102,7 +102,8 @@ int launch_prepare16(const FusedWs& w, int H, int W, const float* c1w, const flo
 }
 
 int launch_step_8x8(const FusedArgs& a, cudaStream_t st);
-int launch_step8_dense(const FusedArgs& a, cudaStream_t st);      // step8.cu: dense 8x8 tiling, software-pipelined chain
+int launch_step8_dense(const FusedArgs& a, cudaStream_t st);
+constexpr int kStep8MinBatch = 445;      // up to 444 images the strip engine runs its one-slot variant, one super-tile per CTA      // step8.cu: dense 8x8 tiling, software-pipelined chain
 int launch_step_7x7(const FusedArgs& a, cudaStream_t st);
 int launch_step_6x6(const FusedArgs& a, cudaStream_t st);
 int launch_step_14x14(const FusedArgs& a, cudaStream_t st);
@@ -115,8 +116,12 @@ bool step_engine_supports(int H, int W) {
 int launch_step_engine(const FusedArgs& a, cudaStream_t st) {
   const int H = a.g.H, W = a.g.W;
   if (H == 8 && W == 8) {
-    const char* dense = getenv("NODE_B200_STEP8");                 // "0": the strip-tiled two-slot kernel (cross-check / tuning aid)
+    const char* dense = getenv("NODE_B200_STEP8");                 // "0" / "1": force the strip-tiled / the dense pair engine
     if (dense != nullptr && dense[0] == '0') return launch_step_8x8(a, st);
+    if (dense != nullptr && dense[0] == '1') return launch_step8_dense(a, st);
+    // Below kStep8MinBatch images a launch is one latency chain per CTA whatever the engine; the strip engine's chain is
+    // shorter there (3 images per CTA on more SMs, no pair handshakes; 1.08 vs 1.25 ms per solve at batch 128): tools/engine_sweep.py.
+    if (a.g.N < kStep8MinBatch) return launch_step_8x8(a, st);
     return launch_step8_dense(a, st);
   }
   if (H == 7 && W == 7) return launch_step_7x7(a, st);

@@ -3,6 +3,7 @@
 
 Used by `node_b200.models` for inference (no autograd graph); with gradients enabled the modules run their own
 PyTorch ops, exactly as in the reference. The module tree - and so the state_dict keys - is unchanged."""
+import os
 import weakref
 
 import torch
@@ -13,7 +14,14 @@ from . import native
 launches = 0        # kernels launched by this module (bench.py's gpu_launches)
 
 
+def enabled():
+    """NODE_B200_CALLERS=0: every caller kernel off - the modules run the reference's own PyTorch ops (bench.py's incumbent arm)."""
+    return os.environ.get('NODE_B200_CALLERS', '1') != '0'
+
+
 def _fusable(norm, x):
+    if not enabled():
+        return False
     if not isinstance(norm, nn.GroupNorm) or norm.weight is None or norm.bias is None:
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and norm.weight.is_cuda):
@@ -74,6 +82,8 @@ _resconv_ws = {}
 
 
 def _resconv_ok(norm, conv, x, shortcut):
+    if not enabled():
+        return False
     if not (isinstance(norm, nn.GroupNorm) and isinstance(conv, nn.Conv2d)) or norm.weight is None:
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and shortcut.shape == x.shape and shortcut.dtype == x.dtype):
@@ -140,6 +150,8 @@ def _is_conv(m, k, stride, pad):
 
 
 def _convs2_ok(norm, conv, down, a):
+    if not enabled():
+        return False
     if not (isinstance(norm, nn.GroupNorm) and norm.weight is not None and _is_conv(conv, 3, 2, 1) and _is_conv(down, 1, 2, 0)):
         return False
     if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 4 and a.shape[1] == 64 and norm.num_groups == 32):
@@ -185,6 +197,8 @@ def res_head(norm, conv, down, a):
 # ---- fused stem: relu(norm(conv(x))) for the first Conv2d(CIN, 64, 3, 1) of a downsampler (csrc/caller_ops.cu) -------------
 
 def _stem_ok(conv, norm, x):
+    if not enabled():
+        return False
     if not (isinstance(conv, nn.Conv2d) and isinstance(norm, nn.GroupNorm) and norm.weight is not None and conv.bias is not None):
         return False
     if (conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups) != (64, (3, 3), (1, 1), (0, 0), (1, 1), 1):
@@ -223,6 +237,7 @@ def head(seq, x):
     ok = (len(mods) == 5 and isinstance(mods[0], nn.GroupNorm) and isinstance(mods[1], nn.ReLU)
           and isinstance(mods[2], nn.AdaptiveAvgPool2d) and mods[2].output_size in (1, (1, 1)) and type(mods[3]).__name__ == 'Flatten'
           and (isinstance(mods[4], nn.Linear) or (type(mods[4]) is nn.Sequential and len(mods[4]) == 0)))
+    ok = ok and enabled()
     norm = mods[0] if ok else None
     if ok:
         lin = mods[4] if isinstance(mods[4], nn.Linear) else None

@@ -9,6 +9,13 @@ identical inputs - the accepted-step sequence is the same on every rank and equa
 single-GPU run at the same global batch.
 
 enable(group) switches the solver into sharded mode for this process; disable() switches back.
+
+Training (SURVEY 8e "training collective"): with the loss a mean over the LOCAL shard, the global gradient is the average
+of the ranks' gradients. The adjoint already integrates adj_params as a GLOBAL sum (its error norm needs the global value,
+adjoint.py:35-55 never reads it back), so after backward() the ODE-block parameters hold the SUM over ranks while every
+other parameter holds its local gradient. sync_gradients(model) brings both to the global average with ONE bucketed
+all-reduce of the non-ODE gradients (158,730 floats for the CIFAR `residual` net); do not wrap the model in
+DistributedDataParallel as well - it would average the already reduced ODE-block gradients a second time.
 """
 import torch
 
@@ -50,3 +57,45 @@ def global_numel(local_numel, device):
     v = torch.tensor([int(local_numel)], dtype=torch.int64, device=device)
     dist.all_reduce(v, op=dist.ReduceOp.SUM, group=_group)
     return int(v.item())
+
+
+def world_size():
+    import torch.distributed as dist
+    return dist.get_world_size(_group)
+
+
+def ode_parameters(model):
+    """Parameters whose gradient comes out of odeint_adjoint already summed over the ranks: those of every module the
+    fused / generic solver integrates (`ODEBlock.odefunc`, model.py:352-360)."""
+    seen = {}
+    for m in model.modules():
+        f = getattr(m, 'odefunc', None)
+        if f is not None:
+            for q in f.parameters():
+                seen[id(q)] = q
+    return seen
+
+
+def sync_gradients(model):
+    """Global-average gradients on every rank (call between backward() and optimizer.step()); returns the number of
+    floats that crossed the link. No-op when sharding is off."""
+    if _group is None:
+        return 0
+    world = world_size()
+    ode = ode_parameters(model)
+    rest = [q for q in model.parameters() if q.grad is not None and id(q) not in ode]
+    sent = 0
+    if rest:
+        flat = torch.cat([q.grad.reshape(-1) for q in rest])          # one bucket: < 1 MB for every net of the reference
+        all_reduce_sum(flat)
+        flat.div_(world)
+        sent = flat.numel()
+        o = 0
+        for q in rest:
+            n = q.grad.numel()
+            q.grad.copy_(flat[o:o + n].view_as(q.grad))
+            o += n
+    for q in ode.values():
+        if q.grad is not None:
+            q.grad.div_(world)                                        # already the sum over ranks (adjoint collective)
+    return sent

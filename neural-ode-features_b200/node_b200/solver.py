@@ -392,7 +392,8 @@ class _FusedGraph(object):
 
 
 def _fused_graph(ws, y, th, t_host, common, E, conv_mode, tsign, guess):
-    key = (id(ws), ws.shape, str(y.device), tuple(float(v) for v in t_host), common[2], common[3], conv_mode, tsign, guess)
+    key = (id(ws), ws.shape, str(y.device), tuple(float(v) for v in t_host), common[2], common[3], conv_mode, tsign, guess,
+           os.environ.get('NODE_B200_STEP8'))          # the captured launches are engine-specific
     g = _graph_cache.get(key)
     if g is not None or key in _graph_failed:
         return g
