@@ -83,7 +83,52 @@ def _needs_grad(func, y0, t):
         return True
     if isinstance(func, nn.Module):
         return any(p.requires_grad for p in func.parameters())
-    return False
+    return any(p.requires_grad for m in _closure_modules(func) for p in m.parameters())
+
+
+def _closure_modules(fn):
+    """nn.Modules a plain callable can reach: its closure cells, its default arguments, the object a bound method belongs to,
+    and the same one level down for functions found there (`lambda t, y: (f(t, y[0]), f(t, y[1]))` is the api_tests.py case)."""
+    found, seen = [], set()
+
+    def visit(obj, depth):
+        if id(obj) in seen:
+            return
+        seen.add(id(obj))
+        if isinstance(obj, nn.Module):
+            found.append(obj)
+            return
+        if depth > 2:
+            return
+        owner = getattr(obj, '__self__', None)
+        if owner is not None:
+            visit(owner, depth + 1)
+        for cell in getattr(obj, '__closure__', None) or ():
+            try:
+                visit(cell.cell_contents, depth + 1)
+            except ValueError:                       # empty cell
+                pass
+        for d in getattr(obj, '__defaults__', None) or ():
+            visit(d, depth + 1)
+        if isinstance(obj, (list, tuple)):
+            for o in obj:
+                visit(o, depth + 1)
+
+    visit(fn, 0)
+    return found
+
+
+class _CallableModule(nn.Module):
+    """A plain callable as an nn.Module, so that gradients requested through `odeint` can be served by the adjoint ODE
+    (which needs parameters to differentiate with respect to): the modules the callable closes over become sub-modules."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self._fn = fn
+        self.reached = nn.ModuleList(_closure_modules(fn))
+
+    def forward(self, t, y):
+        return self._fn(t, y)
 
 
 class _TensorFunc(nn.Module):
@@ -629,9 +674,9 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
         # solver runs in CUDA kernels that record no graph: gradients come from the adjoint ODE instead - the two
         # agree to the solver tolerance (the reference's own gradient_tests.py:98-116 checks exactly that).
         if not isinstance(func, nn.Module):
-            raise NotImplementedError(
-                'node_b200.odeint records no autograd graph through the solver and odeint_adjoint needs an nn.Module; '
-                'wrap the dynamics in an nn.Module or call under torch.no_grad().')
+            if not callable(func):
+                raise NotImplementedError('node_b200.odeint: gradients need a callable `func`')
+            func = _CallableModule(func)             # parameters of every module the callable closes over get their gradient
         global _warned_grad_bridge
         if not _warned_grad_bridge:
             warnings.warn('node_b200.odeint: gradients requested through the non-adjoint entry point - served by the '

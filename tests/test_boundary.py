@@ -76,10 +76,16 @@ def test_error_behaviour_matches_reference():
 
 
 def test_no_silent_autograd_through_odeint():
-    from node_b200 import odeint
+    """Gradients through `odeint` with a plain callable (api_tests.py:30-38, train.py without --adjoint) are served by the adjoint
+    ODE: the modules the callable closes over are found, so their parameters are differentiated too - never silently dropped.
+    (No GPU here: the request must get as far as the CUDA-only check, not return a graph-less tensor.)"""
+    from node_b200 import odeint, solver
     lin = nn.Linear(3, 3)
-    with pytest.raises(NotImplementedError, match='odeint_adjoint'):
-        odeint(lambda t, y: lin(y), torch.ones(3, requires_grad=True), torch.tensor([0., 1.]))
+    f = lambda t, y: lin(y)
+    assert solver._closure_modules(f) == [lin]
+    assert solver._needs_grad(f, (torch.ones(3),), torch.tensor([0., 1.]))        # lin's parameters require grad
+    with pytest.warns(UserWarning, match='adjoint'), pytest.raises(RuntimeError, match='CUDA-only'):
+        odeint(f, torch.ones(3, requires_grad=True), torch.tensor([0., 1.]))
 
 
 def test_recogniser_structure_checks():
