@@ -33,6 +33,7 @@ struct FusedWs {
   float* gn;      // [3][2][C] gamma, beta
   uint16_t* w16;  // f16 engine: [kW16Sets][9 tap][128 rows][64 halves], UMMA K-major SWIZZLE_128B image
   uint16_t* w16p; // CTA-pair engine (step8_engine.cuh): [2 conv][9 tap][2 cta][64 rows][64 halves] half tiles, SWIZZLE_128B image
+  uint16_t* w16q; // adjoint pair engine (vjp8_engine.cuh): [4 sets][9 tap][2 cta][32 hi rows + 32 lo rows][64 halves], SWIZZLE_128B image
   float* tmapc;   // [2][9 border classes][C]: the 9 distinct values of Tmap per channel
   float* scal;    // [16] power-of-two operand scales of the f16 engine (see odefunc_step.cu)
   float* Y[2]; float* F[2]; float* K[5]; float* YMID;
@@ -67,6 +68,7 @@ static int64_t ws_layout(void* base, int N, int C, int H, int W, FusedWs* out) {
   const int64_t o_gn = take((int64_t)6 * C * 4);
   const int64_t o_w16 = take((int64_t)kW16Sets * 9 * kW16TileBytes);
   const int64_t o_w16p = take((int64_t)2 * 9 * kW16TileBytes);
+  const int64_t o_w16q = take((int64_t)4 * 9 * kW16TileBytes);
   const int64_t o_tmapc = take((int64_t)2 * 9 * C * 4);
   const int64_t o_scal = take(16 * 4);
   int64_t o_state[10];
@@ -77,7 +79,7 @@ static int64_t ws_layout(void* base, int N, int C, int H, int W, FusedWs* out) {
     out->partials = (double*)(b + o_part); out->t_out = (double*)(b + o_tout);
     out->wtiles = (float*)(b + o_wt); out->wraw = (float*)(b + o_wraw); out->tmap = (float*)(b + o_tmap);
     out->bias = (float*)(b + o_bias); out->gn = (float*)(b + o_gn);
-    out->w16 = (uint16_t*)(b + o_w16); out->w16p = (uint16_t*)(b + o_w16p); out->tmapc = (float*)(b + o_tmapc); out->scal = (float*)(b + o_scal);
+    out->w16 = (uint16_t*)(b + o_w16); out->w16p = (uint16_t*)(b + o_w16p); out->w16q = (uint16_t*)(b + o_w16q); out->tmapc = (float*)(b + o_tmapc); out->scal = (float*)(b + o_scal);
     out->Y[0] = (float*)(b + o_state[0]); out->Y[1] = (float*)(b + o_state[1]);
     out->F[0] = (float*)(b + o_state[2]); out->F[1] = (float*)(b + o_state[3]);
     for (int i = 0; i < 5; ++i) out->K[i] = (float*)(b + o_state[4 + i]);

@@ -58,8 +58,34 @@ __global__ void k_prepare_dgrad_tiles(FusedWs w, const float* c1w, const float* 
   }
 }
 
+// CTA-pair half tiles of the adjoint pair engine (vjp8_engine.cuh): set 0, 1 = conv1, conv2 forward; set 2, 3 = their data
+// gradients. CTA c of a pair holds the output channels [32c, 32c+32): rows 0..31 their hi parts, rows 32..63 their lo parts, so that
+// the three products of the split (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo; N = 64 each) land in the same 64 accumulator columns.
+__global__ void k_prepare_pair3_tiles(FusedWs w, const float* c1w, const float* c2w) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const float* cw[2] = {c1w, c2w};
+  for (int i = tid; i < 4 * 9 * 2 * 64 * 64; i += nth) {
+    int r = i;
+    const int k = r % 64; r /= 64;
+    const int row = r % 64; r /= 64;
+    const int cta = r % 2; r /= 2;
+    const int tap = r % 9; r /= 9;
+    const int set = r, cv = set & 1;
+    const int n = 32 * cta + (row & 31);
+    const float v = (set < 2 ? cw[cv][((int64_t)n * (kC + 1) + k + 1) * 9 + tap]
+                             : cw[cv][((int64_t)k * (kC + 1) + n + 1) * 9 + (8 - tap)]) * w.scal[2 + cv];
+    const __half hi = __float2half_rn(v);
+    const __half val = row < 32 ? hi : __float2half_rn(v - __half2float(hi));
+    const int chunk = (k >> 3) ^ (row & 7);
+    const int64_t dst = (((int64_t)(set * 9 + tap) * 2 + cta) * 64 + row) * 64 + chunk * 8 + (k & 7);
+    w.w16q[dst] = *reinterpret_cast<const uint16_t*>(&val);
+  }
+}
+
 int launch_prepare_dgrad(const FusedWs& w, const float* c1w, const float* c2w, cudaStream_t st) {
   k_prepare_dgrad_tiles<<<148, 256, 0, st>>>(w, c1w, c2w);
+  NODE_CUDA_OK(cudaGetLastError());
+  k_prepare_pair3_tiles<<<148, 256, 0, st>>>(w, c1w, c2w);
   return (int)cudaGetLastError();
 }
 
@@ -98,6 +124,8 @@ __global__ void k_vjp_finalize(const float* __restrict__ wpart, int nsplit, cons
 
 // per-shape translation units (vjp_shape_HxW.cu)
 int launch_vjp_8x8(const VjpArgs& a, cudaStream_t st);
+int launch_vjp8_dense(const VjpArgs& a, cudaStream_t st, int* grid_out);      // vjp8.cu: dense 8x8 tiling on CTA pairs
+constexpr int kVjp8MinBatch = 445;        // below, the strip engine's one super-tile per CTA is the shorter chain (as for k_step8)
 int launch_vjp_7x7(const VjpArgs& a, cudaStream_t st);
 int launch_vjp_6x6(const VjpArgs& a, cudaStream_t st);
 int launch_vjp_14x14(const VjpArgs& a, cudaStream_t st);
@@ -167,8 +195,11 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   cudaStream_t st = (cudaStream_t)stream;
   NODE_CUDA_OK(cudaMemsetAsync(v.gc_max, 0, 16, st));
   g_wgrad_scal = a.w.scal;
-  int rc;
-  if (H == 8 && W == 8) rc = launch_vjp_8x8(a, st);
+  int rc, grid_dense = 0;
+  const char* dense = getenv("NODE_B200_VJP8");           // "0" / "1": force the strip-tiled / the dense pair engine
+  const bool use_dense = H == 8 && W == 8 && (dense != nullptr ? dense[0] != '0' : N >= kVjp8MinBatch);
+  if (use_dense) rc = launch_vjp8_dense(a, st, &grid_dense);
+  else if (H == 8 && W == 8) rc = launch_vjp_8x8(a, st);
   else if (H == 7 && W == 7) rc = launch_vjp_7x7(a, st);
   else if (H == 6 && W == 6) rc = launch_vjp_6x6(a, st);
   else if (H == 14 && W == 14) rc = launch_vjp_14x14(a, st);
@@ -179,7 +210,7 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   // grid sizes the two kernels used (same rules as their launchers)
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;
-  const int nst_vjp = NST < kMaxGrid ? NST : kMaxGrid;
+  const int nst_vjp = use_dense ? grid_dense : (NST < kMaxGrid ? NST : kMaxGrid);
   const int nsplit = NST < kWgSplits ? NST : kWgSplits;
   k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
                                                               vjp_t, vjp_params);

@@ -83,19 +83,20 @@ static_assert(smem_bytes() <= 227 * 1024, "shared memory budget");
 struct Sched {
   int rounds, rounds2;     // super-tiles of virtual slot 0 / of virtual slot 1 (rounds2 <= rounds)
   int nevals, lag;
-  __device__ __forceinline__ uint32_t jobs() const { return (uint32_t)(rounds + rounds2) * (uint32_t)nevals * 2u; }
+  int convs = 2;           // conv jobs per evaluation and slot (the adjoint engine, vjp8_engine.cuh, has 4)
+  __device__ __forceinline__ uint32_t jobs() const { return (uint32_t)(rounds + rounds2) * (uint32_t)nevals * (uint32_t)convs; }
   __device__ __forceinline__ int iters() const { const int a = rounds * nevals, b = rounds2 > 0 ? rounds2 * nevals + lag : 0; return a > b ? a : b; }
   __device__ __forceinline__ bool active(int it, int v) const {
     return v == 0 ? it < rounds * nevals : (it >= lag && it - lag < rounds2 * nevals);
   }
 };
 
-struct JobIter {        // conv jobs in issue order: for every iteration, conv1 of each active slot, then conv2 of each
+struct JobIter {        // conv jobs in issue order: for every iteration, conv1 of each active slot, then conv2 of each, ...
   int it = 0, cv = 0, v = 0;
   __device__ __forceinline__ void next(const Sched& s) {
     const int n = s.iters();
     do {
-      if (++v == 2) { v = 0; if (++cv == 2) { cv = 0; ++it; } }
+      if (++v == 2) { v = 0; if (++cv == s.convs) { cv = 0; ++it; } }
     } while (it < n && !s.active(it, v));
   }
 };
@@ -523,6 +524,7 @@ __device__ __forceinline__ void issuer_loop(const Smem& sm, const Sched& sc, uin
   S8_FLUSH(16);
 }
 
+#ifndef NODE_STEP8_HELPERS_ONLY      // vjp8_engine.cuh reuses the helpers above
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8(const FusedArgs a) {
   using A = Arith<float>;
   constexpr int HW = 64;
@@ -936,10 +938,11 @@ static int launch_step8(const FusedArgs& a_in, cudaStream_t st) {
   k_step8<<<grid, kThreads, smem, st>>>(a);
   return (int)cudaGetLastError();
 }
+#endif  // NODE_STEP8_HELPERS_ONLY
 
 }}  // namespace node::s8
 
-#ifdef NODE_STEP8_DEBUG
+#if defined(NODE_STEP8_DEBUG) && !defined(NODE_STEP8_HELPERS_ONLY)
 extern "C" int node_b200_step8_phase_read(long long* host, int clear) {
   int rc = (int)cudaMemcpyFromSymbol(host, node::s8::g_s8_phase, sizeof(long long) * 32);
   if (clear) { static long long z[32]; rc |= (int)cudaMemcpyToSymbol(node::s8::g_s8_phase, z, sizeof(z)); }

@@ -35,16 +35,26 @@ def pieces(flat):
 
 
 @pytest.mark.parametrize('tsign', [1.0, -1.0])
-@pytest.mark.parametrize('name,rep', [('cifar_res_n8', 1), ('mnist_res_n5', 1), ('mnist_conv_n9', 1), ('mnist_oneshot_n3', 1),
-                                      ('cifar_oneshot_n3', 1), ('cifar_res_n8', 80)])
-def test_native_vjp_matches_oracle(native_lib, golden, name, rep, tsign):
+@pytest.mark.parametrize('name,rep,n,engine', [
+    ('cifar_res_n8', 1, 8, '0'), ('mnist_res_n5', 1, 5, None), ('mnist_conv_n9', 1, 9, None), ('mnist_oneshot_n3', 1, 3, None),
+    ('cifar_oneshot_n3', 1, 3, None), ('cifar_res_n8', 80, 640, '0'),
+    # the dense pair engine (k_vjp8): default above 444 images; forced for the small / ragged cases (a pair with one active
+    # slot, a last super-tile of one image, a peer CTA without work)
+    ('cifar_res_n8', 80, 640, None), ('cifar_res_n8', 81, 645, None), ('cifar_res_n8', 1, 8, '1'), ('cifar_res_n8', 1, 5, '1'),
+    ('cifar_res_n8', 3, 21, '1'), ('cifar_res_n8', 320, 2560, None)])
+def test_native_vjp_matches_oracle(native_lib, golden, monkeypatch, name, rep, n, engine, tsign):
     from node_b200 import solver
+    if engine is not None:
+        monkeypatch.setenv('NODE_B200_VJP8', engine)
+    else:
+        monkeypatch.delenv('NODE_B200_VJP8', raising=False)
     g = golden(name)
     func = load_odefunc(g, DEV)
     p = odefunc_params(g)
     h0 = torch.from_numpy(g['h0'])
     if rep > 1:                                     # 640 images: > 148 super-tiles, ragged tail (640 = 213*3 + 1)
         h0 = torch.cat([h0 * (1 + 0.003 * i) for i in range(rep)], 0)
+    h0 = h0[:n].contiguous()
     gen = torch.Generator().manual_seed(7)
     adj = torch.randn(h0.shape, generator=gen) * 1e-2
     t = 0.37
