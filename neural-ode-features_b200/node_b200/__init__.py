@@ -4,6 +4,6 @@
 `models`: mirror of the reference's ODENet / ODEBlock / ODEfunc module surface;
 `native`: ctypes binding of the C ABI (include/node_b200.h); `distributed`: batch sharding.
 """
-from .solver import odeint, odeint_adjoint  # noqa: F401
+from .solver import invalidate_caches, odeint, odeint_adjoint  # noqa: F401
 
-__all__ = ['odeint', 'odeint_adjoint']
+__all__ = ['odeint', 'odeint_adjoint', 'invalidate_caches']

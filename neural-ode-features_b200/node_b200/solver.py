@@ -45,7 +45,10 @@ def _conv_mode():
 
 
 def _host_times(t):
-    """float64 host copy of `t` (one sync the first time a given tensor is seen)."""
+    """float64 host copy of `t` (one sync the first time a given tensor is seen). Freshness is judged by (identity, _version):
+    a tensor that requires grad is never cached (torch.autograd.gradcheck perturbs it through `.data`, which bumps no version)."""
+    if t.requires_grad:
+        return t.detach().to('cpu', torch.float64).numpy().copy()
     key = id(t)
     hit = _t_cache.get(key)
     if hit is not None and hit[0]() is t and hit[1] == t._version:
@@ -226,6 +229,21 @@ class FusedWorkspace(object):
         self.param_key = key
         self.param_refs = [weakref.ref(p) for p in params]
         self.param_key_fresh = True
+
+
+def invalidate_caches():
+    """Forget everything that is keyed by tensor identity and `_version`: host copies of time tensors, prepared weight tiles
+    (solver and caller kernels), captured CUDA graphs. In-place writes through `.data` (EMA / SWA swaps, `p.data.copy_()`, weight
+    clipping) bump no version: call this after them."""
+    _t_cache.clear()
+    _graph_cache.clear()
+    _graph_failed.clear()
+    for ws in _ws_cache.values():
+        ws.param_key = None
+        ws.param_refs = None
+    from . import caller_ops
+    caller_ops._resconv_ws.clear()
+    caller_ops._convs2_ws.clear()
 
 
 def fused_workspace(device, N, C, H, W):

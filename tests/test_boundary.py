@@ -146,3 +146,19 @@ def test_caller_modules_keep_the_reference_ops_off_the_gpu_or_with_gradients():
     h = net.downsample(x)
     net.classifier(h).sum().backward()
     assert x.grad is not None and net.downsample.module[1].conv1.weight.grad is not None
+
+
+def test_time_tensor_cache_and_invalidate():
+    """Host copies of time tensors are cached by (identity, _version); a tensor that requires grad is never cached (gradcheck
+    perturbs through `.data`, gradient_tests.py:33-37), and invalidate_caches() forgets the rest."""
+    from node_b200 import invalidate_caches, solver
+    t = torch.tensor([0., 1.])
+    assert solver._host_times(t)[1] == 1.0
+    t.data[1] = 2.0                                   # no version bump: the cached copy is stale by design ...
+    assert solver._host_times(t)[1] == 1.0
+    invalidate_caches()                               # ... until the caller says so
+    assert solver._host_times(t)[1] == 2.0
+    tg = torch.tensor([0., 1.], requires_grad=True)
+    assert solver._host_times(tg)[1] == 1.0
+    tg.data[1] = 3.0
+    assert solver._host_times(tg)[1] == 3.0

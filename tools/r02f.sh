@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02f_train_launches.csv python tools/train_profile.py 4736 > gpurun_out/r02f_train_profile.log 2>&1; tail -3 gpurun_out/r02f_train_profile.log
