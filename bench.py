@@ -524,6 +524,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=0, help='images per step of the reference arm / cpu_baseline (0 = the whole per-GPU batch)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='tuning runs: only the forward, e2e, ODE-block and step-kernel legs')
     ap.add_argument('--train-batch', type=int, default=4736, help='batch of the adjoint training-step measurement (0 = skip)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'native' else args.warmup
@@ -642,7 +643,7 @@ def main():
     t_ode = timed_loop(step_ode, args.steps)
 
     # legs every rank takes part in (collectives inside): cfg3 training step and the fixed-global-batch forwards
-    strong = strong_scaling(net, dev, world, rank)
+    strong = strong_scaling(net, dev, world, rank) if not args.quick else None
     train = train_step_rate(dev, args.train_batch, max(2, args.steps // 2), 2, world) if args.train_batch > 0 else None
 
     if rank != 0:
@@ -685,7 +686,7 @@ def main():
     line['strong_scaling'] = strong
     if train is not None:
         line['train_step'] = train
-    if world == 1:
+    if world == 1 and not args.quick:
         line['roofline_rk'] = rk_roofline(dev, pk)
         line['latency_b128'] = small_batch_latency(net, dev)
         line['other_configs'] = other_configs(dev)

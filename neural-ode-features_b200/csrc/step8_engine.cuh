@@ -271,7 +271,8 @@ struct Quad {
 // x[c][j] = y + sum_k (h*c_k) k_k for 8 channels x 4 pixels (rk_common.py:49-51), reference rounding and order.
 template <int NK>
 __device__ __forceinline__ void stage_in_quad(float (&x)[8][4], const float* __restrict__ y, const float* const (&src)[6],
-                                              const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid) {
+                                              const float (&hc)[6], float* __restrict__ ynew, size_t p0, bool valid, uint64_t pol_ld,
+                                              uint64_t pol_st) {
   using A = Arith<float>;
   constexpr int B = NK <= 1 ? 4 : 2;       // channels per batch (one or two GroupNorm groups): 8-12 128-bit loads in flight
 #pragma unroll
@@ -279,9 +280,9 @@ __device__ __forceinline__ void stage_in_quad(float (&x)[8][4], const float* __r
     float4 yv[B], kv[NK][B];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
-      yv[i] = ptx::ldg128_ordered(y + p0 + (size_t)(c0 + i) * 64);
+      yv[i] = ptx::ldg128_hint(y + p0 + (size_t)(c0 + i) * 64, pol_ld);
 #pragma unroll
-      for (int j = 0; j < NK; ++j) kv[j][i] = ptx::ldg128_ordered(src[j] + p0 + (size_t)(c0 + i) * 64);
+      for (int j = 0; j < NK; ++j) kv[j][i] = ptx::ldg128_hint(src[j] + p0 + (size_t)(c0 + i) * 64, pol_ld);
     }
 #pragma unroll
     for (int i = 0; i < B; ++i) {
@@ -298,7 +299,7 @@ __device__ __forceinline__ void stage_in_quad(float (&x)[8][4], const float* __r
         r[e] = A::add(ya[e], s);
         x[c0 + i][e] = valid ? r[e] : 0.f;
       }
-      if (ynew != nullptr && valid) *reinterpret_cast<float4*>(ynew + p0 + (size_t)(c0 + i) * 64) = make_float4(r[0], r[1], r[2], r[3]);
+      if (ynew != nullptr && valid) ptx::stg128_hint(ynew + p0 + (size_t)(c0 + i) * 64, make_float4(r[0], r[1], r[2], r[3]), pol_st);
     }
   }
 }
@@ -607,15 +608,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
   const int unit0 = ((int)blockIdx.x >> 1) * 4;
   Sched sc;
   sc.nevals = a.mode == MODE_STEP ? 6 : 1;
-  sc.lag = 0;
+  sc.lag = a.mode == MODE_STEP ? ((a.nw >> 24) & 7) : 0;      // NODE_B200_STEP8_LAG (tuning; default 0)
   sc.rounds = unit0 < NST ? (NST - unit0 + stride - 1) / stride : 0;
   sc.rounds2 = unit0 + 2 < NST ? (NST - (unit0 + 2) + stride - 1) / stride : 0;
   // De-phase the pairs: every CTA runs the same phase sequence, and in lockstep all 148 SMs would hit the L2-bound stage
   // combination (and then the tensor-bound phases) at the same time. A start offset of a fraction of an iteration per pair
   // group spreads the L2 bursts (a.nw >> 1 = offset unit in units of 256 ns; 0 = off).
-  if (a.mode == MODE_STEP && (a.nw >> 1) != 0) {
+  if (a.mode == MODE_STEP && ((a.nw >> 1) & 0xFFFFF) != 0) {
     const unsigned grp = (blockIdx.x >> 1) & 3u;
-    for (unsigned i = 0; i < grp * (unsigned)(a.nw >> 1); ++i) __nanosleep(256);
+    for (unsigned i = 0; i < grp * (unsigned)((a.nw >> 1) & 0xFFFFF); ++i) __nanosleep(256);
   }
   const bool split = a.conv_mode == CONV_F16X3;
   bool timeout = false;
@@ -650,6 +651,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
     }
     const int cur = a.mode == MODE_STEP ? ctl->cur : 0;
     const float rtol = (float)ctl->rtol[0], atol = (float)ctl->atol[0];
+    // L2 residency of the step's working set (a.nw bit 30 = NODE_B200_STEP8_L2HINT=0 switches the hints off): y, f and the k tensors
+    // of the images in flight are kept (evict_last) until the error norm has read them for the last time (evict_first), as are
+    // the outputs nothing reads again within this launch.
+    const bool hints = a.mode == MODE_STEP && !((a.nw >> 30) & 1);
+    const uint64_t pol_keep = hints ? ptx::policy_evict_last() : ptx::policy_evict_normal();
+    const uint64_t pol_drop = hints ? ptx::policy_evict_first() : ptx::policy_evict_normal();
     float* const Ycur = w.Y[cur];
     const float* const Fcur = w.F[cur];
     uint32_t nacc[2] = {0u, 0u};
@@ -727,31 +734,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
             if (a.mode == MODE_PROBE) {                               // y0 + h0*f0 (misc.py:133)
               const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
               const float hc[6] = {h, 0.f, 0.f, 0.f, 0.f, 0.f};
-              stage_in_quad<1>(x, Ycur, src, hc, nullptr, p0, valid);
+              stage_in_quad<1>(x, Ycur, src, hc, nullptr, p0, valid, pol_keep, pol_keep);
             } else if (ev == 0) {
               const float* src[6] = {Fcur, Fcur, Fcur, Fcur, Fcur, Fcur};
               const float hc[6] = {cf[0], 0.f, 0.f, 0.f, 0.f, 0.f};
-              stage_in_quad<1>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<1>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             } else if (ev == 1) {
               const float* src[6] = {Fcur, w.K[0], Fcur, Fcur, Fcur, Fcur};
               const float hc[6] = {cf[0], cf[1], 0.f, 0.f, 0.f, 0.f};
-              stage_in_quad<2>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<2>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             } else if (ev == 2) {
               const float* src[6] = {Fcur, w.K[0], w.K[1], Fcur, Fcur, Fcur};
               const float hc[6] = {cf[0], cf[1], cf[2], 0.f, 0.f, 0.f};
-              stage_in_quad<3>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<3>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             } else if (ev == 3) {
               const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], Fcur, Fcur};
               const float hc[6] = {cf[0], cf[1], cf[2], cf[3], 0.f, 0.f};
-              stage_in_quad<4>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<4>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             } else if (ev == 4) {
               const float* src[6] = {Fcur, w.K[0], w.K[1], w.K[2], w.K[3], Fcur};
               const float hc[6] = {cf[0], cf[1], cf[2], cf[3], cf[4], 0.f};
-              stage_in_quad<5>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<5>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             } else {
               const float* src[6] = {Fcur, w.K[1], w.K[2], w.K[3], w.K[4], Fcur};
               const float hc[6] = {cf[0], cf[2], cf[3], cf[4], cf[5], 0.f};
-              stage_in_quad<5>(x, Ycur, src, hc, ynew, p0, valid);
+              stage_in_quad<5>(x, Ycur, src, hc, ynew, p0, valid, pol_keep, pol_keep);
             }
           }
           S8_STAMP(0);
@@ -837,7 +844,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
             const float aa = (c & 1) ? p.y : p.x, bb = (c & 1) ? p.w : p.z;
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[c][e] = fmaf(x[c][e], aa, bb);
-            if (kdst != nullptr) *reinterpret_cast<float4*>(kdst + p0 + (size_t)c * HW) = make_float4(x[c][0], x[c][1], x[c][2], x[c][3]);
+            if (kdst != nullptr) ptx::stg128_hint(kdst + p0 + (size_t)c * HW, make_float4(x[c][0], x[c][1], x[c][2], x[c][3]), (a.mode == MODE_STEP && ev < 5) ? pol_keep : pol_drop);
           }
           S8_STAMP(10);
           if (a.mode == MODE_F0) {               // misc.py:121-126
@@ -877,7 +884,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
               const int b = c & 1;
               if (b == 0) {
 #pragma unroll
-                for (int j = 0; j < 7; ++j) { ld[0][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)c * HW); ld[1][j] = ptx::ldg128_ordered(srcs[j] + p0 + (size_t)(c + 1) * HW); }
+                for (int j = 0; j < 7; ++j) { ld[0][j] = ptx::ldg128_hint(srcs[j] + p0 + (size_t)c * HW, pol_drop); ld[1][j] = ptx::ldg128_hint(srcs[j] + p0 + (size_t)(c + 1) * HW, pol_drop); }
               }
               float mid[4];
 #pragma unroll
@@ -898,7 +905,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_step8
                 part += A::mul(qv, qv);
                 mid[e] = A::add(y0, md);
               }
-              *reinterpret_cast<float4*>(w.YMID + p0 + (size_t)c * HW) = make_float4(mid[0], mid[1], mid[2], mid[3]);
+              ptx::stg128_hint(w.YMID + p0 + (size_t)c * HW, make_float4(mid[0], mid[1], mid[2], mid[3]), pol_drop);
             }
             acc0 += (double)part;
             S8_STAMP(11);
@@ -930,7 +937,9 @@ static int launch_step8(const FusedArgs& a_in, cudaStream_t st) {
   FusedArgs a = a_in;
   static const char* pf = getenv("NODE_B200_STEP8_PREFETCH");
   static const char* ph = getenv("NODE_B200_STEP8_DEPHASE");      // start offset per pair group in units of 256 ns (default 0: measured no gain)
-  a.nw = ((pf != nullptr && pf[0] == '0') ? 1 : 0) | ((ph != nullptr ? atoi(ph) : 0) << 1);
+  const char* l2 = getenv("NODE_B200_STEP8_L2HINT");
+  const char* lg = getenv("NODE_B200_STEP8_LAG");
+  a.nw = ((pf != nullptr && pf[0] == '0') ? 1 : 0) | (((ph != nullptr ? atoi(ph) : 0) & 0xFFFFF) << 1) | ((l2 != nullptr && l2[0] == '0') ? (1 << 30) : 0) | (((lg != nullptr ? atoi(lg) : 0) & 7) << 24);
   NODE_SET_SMEM_ONCE(k_step8, smem);
   const int NST = (a.g.N + kImgs - 1) / kImgs;
   int grid = 2 * ((NST + 3) / 4);                  // CTA pairs: 16 images per pair and round
