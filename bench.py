@@ -487,6 +487,20 @@ def other_configs(dev):
         x = torch.rand(256, 3, 32, 32, device=dev)
         r = rate(lambda: net(x), 256, reps=3)
         out['n_filters_256'] = dict(images_per_s=r, batch=256, nfe=solver.last_stats.get('nfe'), route=solver.last_stats.get('route'))
+        # retrieval scoring of the 10,000-image test set (evaluate.py:326,339) on a device-resident feature plane
+        from node_b200 import retrieval
+        feats = torch.rand(10000, 64, device=dev)
+        t_cpu = None
+        fn = lambda: retrieval.retrieval_scores(retrieval.normalize_features(feats)[0], retrieval.normalize_features(feats)[0])
+        r = rate(fn, 1, reps=5)
+        f_np = feats.cpu().numpy()
+        t0 = time.perf_counter()
+        q = f_np / (np.linalg.norm(f_np, axis=-2, keepdims=True) + 1e-7)
+        q.dot(q.T)
+        t_cpu = time.perf_counter() - t0
+        out['retrieval_scores_10k'] = dict(gpu_ms=1e3 / r, cpu_numpy_ms=1e3 * t_cpu, scores_bytes=4 * 10000 * 10000,
+                                           write_gb_per_s=4e8 / (1.0 / r) / 1e9,
+                                           note='normalise (twice) + 10000x10000x64 fp32 scores; bound by the 400 MB write')
     return out
 
 

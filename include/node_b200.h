@@ -254,6 +254,16 @@ int node_b200_stem_gn_relu(const float* x, const float* conv_w, const float* con
 int node_b200_head(const float* x, const float* gn_w, const float* gn_b, const float* lin_w, const float* lin_b, float* out,
                    int64_t N, int C, int HW, int n_out, float eps, void* stream);
 
+/* SURVEY 8f-4 - the edges after the feature extractor, on device-resident buffers.
+ * feature_normalize: the reference's retrieval normalisation (evaluate.py:326)
+ *     out = features / (np.linalg.norm(features, axis=-2, keepdims=True) + 1e-7)
+ * for features [planes, N, D] fp32 (planes = tol x T of the HDF5 layout features[tol, T, N, D], evaluate.py:88-94): the norm
+ * runs over the N SAMPLES of a plane, one value per feature dimension (norms [planes, D], also returned). out may alias
+ * features.
+ * retrieval_scores: scores = queries . db^T (evaluate.py:339), queries [nq, D], db [ns, D], scores [nq, ns], fp32 FFMA. */
+int node_b200_feature_normalize(const float* features, float* out, float* norms, int64_t planes, int64_t N, int D, void* stream);
+int node_b200_retrieval_scores(const float* queries, const float* db, float* scores, int64_t nq, int64_t ns, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

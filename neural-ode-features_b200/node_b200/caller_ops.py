@@ -229,10 +229,11 @@ def stem_gn_relu(conv, norm, x):
 # ---- fused classifier head: GroupNorm -> ReLU -> global average pool (-> Linear) (csrc/caller_ops.cu k_head) ---------------
 
 @native.on_device_of(1)
-def head(seq, x):
+def head(seq, x, out=None):
     """FCClassifier.module (model.py:231-250) applied to x: one CUDA pass when the layer list is exactly
     [GroupNorm(32, 64), ReLU, AdaptiveAvgPool2d(1), (Dropout in eval mode,) Flatten, Linear(64, k) or an empty Sequential]
-    and no gradient is needed; run_sequential otherwise."""
+    and no gradient is needed; run_sequential otherwise. `out` (contiguous [N, n_out] fp32 on x's device, e.g. a slice of
+    the features[tol, T, N, 64] buffer of node_b200.retrieval.FeatureStore) receives the result in place."""
     mods = [m for m in seq.children() if not (isinstance(m, nn.Dropout) and not m.training)]
     ok = (len(mods) == 5 and isinstance(mods[0], nn.GroupNorm) and isinstance(mods[1], nn.ReLU)
           and isinstance(mods[2], nn.AdaptiveAvgPool2d) and mods[2].output_size in (1, (1, 1)) and type(mods[3]).__name__ == 'Flatten'
@@ -247,11 +248,18 @@ def head(seq, x):
               and not (torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad
                                                     or (lin is not None and lin.weight.requires_grad))))
     if not ok:
-        return run_sequential(seq, x)
+        res = run_sequential(seq, x)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
     x = x.contiguous()
     N, HW = int(x.shape[0]), int(x.shape[2] * x.shape[3])
     n_out = lin.out_features if lin is not None else 64
-    out = torch.empty((N, n_out), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty((N, n_out), dtype=x.dtype, device=x.device)
+    elif not (out.is_contiguous() and tuple(out.shape) == (N, n_out) and out.dtype == x.dtype and out.device == x.device):
+        raise ValueError('head: `out` must be a contiguous [%d, %d] %s tensor on %s' % (N, n_out, x.dtype, x.device))
     lw = native.ptr(lin.weight.contiguous()) if lin is not None else None
     lb = native.ptr(lin.bias) if lin is not None and lin.bias is not None else None
     native.check(native.lib().node_b200_head(native.ptr(x), native.ptr(norm.weight), native.ptr(norm.bias), lw, lb, native.ptr(out),

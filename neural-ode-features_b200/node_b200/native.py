@@ -34,7 +34,7 @@ EXPORTS = (
     'node_b200_fused_ctl', 'node_b200_vjp_workspace_bytes', 'node_b200_odefunc_vjp', 'node_b200_wgrad',
     'node_b200_vjp_buffer', 'node_b200_groupnorm_relu', 'node_b200_resconv_workspace_bytes', 'node_b200_resconv_prepare',
     'node_b200_resconv_forward', 'node_b200_convs2_workspace_bytes', 'node_b200_convs2_prepare', 'node_b200_convs2_forward',
-    'node_b200_stem_gn_relu', 'node_b200_head',
+    'node_b200_stem_gn_relu', 'node_b200_head', 'node_b200_feature_normalize', 'node_b200_retrieval_scores',
 )
 
 _lib = None
@@ -80,6 +80,8 @@ def _declare(lib):
     lib.node_b200_convs2_forward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
     lib.node_b200_stem_gn_relu.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
     lib.node_b200_head.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp]
+    lib.node_b200_feature_normalize.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _vp]
+    lib.node_b200_retrieval_scores.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _vp]
 
 
 def lib():
