@@ -264,6 +264,46 @@ int node_b200_head(const float* x, const float* gn_w, const float* gn_b, const f
 int node_b200_feature_normalize(const float* features, float* out, float* norms, int64_t planes, int64_t N, int D, void* stream);
 int node_b200_retrieval_scores(const float* queries, const float* db, float* scores, int64_t nq, int64_t ns, int D, void* stream);
 
+/* SURVEY 8f-3, backward of the callers (model.py:119-178 and 231-250 under autograd; train.py:40-58). All tensors contiguous
+ * NCHW fp32 on the device.
+ * groupnorm_relu_backward: y = relu?(GroupNorm(groups, C)(x)) with C = 2 * groups; given grad_out = dL/dy writes grad_in = dL/dx
+ *   (2 reads + 1 write), grad_gamma[C], grad_beta[C]; partials = scratch of 2 * N * C floats (per-image sums, folded in a fixed
+ *   order). Statistics are recomputed (two-pass) - nothing is saved by the forward.
+ * absmax: *out_bits = bit pattern of max |v| (the power-of-two operand scale of a gradient tensor in conv_wgrad).
+ * plane_split / plane_merge: planes[pr][pc][n][c][i][j] = a[n][c][2i+pr][2j+pc] (zero beyond the map), planes
+ *   [4][N][C][HO][WO] with HO = (HI-1)/2+1 - a stride-2 3x3 convolution is the sum of four stride-1 convolutions on them - and
+ *   the inverse scatter for the gradients.
+ * conv3x3_prepare / conv3x3_forward: out = conv2d(x, W, stride 1, padding 1) (+ addend) for a SIGNED x [N,64,H,W] and an
+ *   ordinary weight [64,64,3,3] on the tcgen05 engine of resconv_forward (fp16 operand split, the operand scale found per
+ *   super-tile in the kernel): the data gradient of a 3x3 convolution when W is its flipped, transposed kernel. Workspace of
+ *   resconv_workspace_bytes; maps 15x15, 8x8, 13x13, 7x7.
+ * conv_wgrad: dw[p][co][ci][tap] = sum_{n,pos} grads[p][n,co,pos] * inputs[p][n,ci,pos+tap] for npairs <= 6 (input, gradient)
+ *   pairs in one launch of the adjoint's weight-gradient GEMM; input_scales[p] / grad_max_bits[p] are DEVICE scalars (the
+ *   power-of-two scale of the input operand; the bit pattern of max |grad|, see absmax). Maps 15x15 and 8x8.
+ * stem_backward: gradients of out = relu(GroupNorm(32,64)(Conv2d(CIN,64,3,1)(x))) with respect to conv weight [64*CIN*9],
+ *   conv bias [64], gamma [64], beta [64] - written in that order to grads - without materialising the conv output
+ *   (recomputed per image). x itself receives no gradient. */
+int node_b200_groupnorm_relu_backward(const float* x, const float* grad_out, float* grad_in, const float* gamma, const float* beta,
+                                      float* partials, float* grad_gamma, float* grad_beta, int64_t N, int C, int groups, int HW,
+                                      float eps, int relu, void* stream);
+int node_b200_absmax(const float* v, int64_t n, unsigned* out_bits, void* stream);
+int node_b200_plane_split(const float* a, float* planes, int64_t N, int C, int HI, int WI, void* stream);
+int node_b200_plane_merge(const float* gplanes, float* ga, int64_t N, int C, int HI, int WI, void* stream);
+int node_b200_conv3x3_prepare(void* workspace, int C, int H, int W, const float* conv_w, void* stream);
+int node_b200_conv3x3_forward(void* workspace, const float* x, const float* addend, float* out, int N, int C, int H, int W,
+                              void* stream);
+int64_t node_b200_conv_wgrad_workspace_bytes(int npairs);
+int node_b200_conv_wgrad(void* workspace, int npairs, const float* const* inputs, const float* const* grads,
+                         const float* const* input_scales, const unsigned* const* grad_max_bits, float* dw, int N, int C, int H,
+                         int W, void* stream);
+int64_t node_b200_stem_backward_workspace_bytes(int CIN);
+int node_b200_stem_backward(const float* x, const float* conv_w, const float* conv_b, const float* gn_w, const float* gn_b,
+                            const float* grad_out, void* workspace, float* grads, int N, int CIN, int HIN, int WIN, float eps,
+                            void* stream);
+/* byte offset of the operand-scale block (float[8]; [0] = activation scale) inside a resconv / convs2 workspace */
+int64_t node_b200_resconv_scal_offset(void);
+int64_t node_b200_convs2_scal_offset(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,10 @@ int launch_resconv_15x15(const ResConvArgs& a, cudaStream_t st);
 int launch_resconv_8x8(const ResConvArgs& a, cudaStream_t st);
 int launch_resconv_13x13(const ResConvArgs& a, cudaStream_t st);
 int launch_resconv_7x7(const ResConvArgs& a, cudaStream_t st);
+int launch_resconv_raw_15x15(const ResConvArgs& a, cudaStream_t st);
+int launch_resconv_raw_8x8(const ResConvArgs& a, cudaStream_t st);
+int launch_resconv_raw_13x13(const ResConvArgs& a, cudaStream_t st);
+int launch_resconv_raw_7x7(const ResConvArgs& a, cudaStream_t st);
 
 struct ResConvWs { uint16_t* w16; float* scal; };
 
@@ -25,7 +29,8 @@ __global__ void k_resconv_scales(ResConvWs w, int HW, const float* cw, const flo
   const int tid = threadIdx.x;
   float mw = 0.f, mg = 0.f, mb = 0.f;
   for (int i = tid; i < kC * kC * 9; i += 256) mw = fmaxf(mw, fabsf(cw[i]));
-  for (int i = tid; i < kC; i += 256) { mg = fmaxf(mg, fabsf(gw[i])); mb = fmaxf(mb, fabsf(gb[i])); }
+  if (gw != nullptr)
+    for (int i = tid; i < kC; i += 256) { mg = fmaxf(mg, fabsf(gw[i])); mb = fmaxf(mb, fabsf(gb[i])); }
   red[0][tid] = mw; red[1][tid] = mg; red[2][tid] = mb;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -33,7 +38,7 @@ __global__ void k_resconv_scales(ResConvWs w, int HW, const float* cw, const flo
     __syncthreads();
   }
   if (tid == 0) {
-    const float bound_a = red[1][0] * sqrtf((float)(kCpg * HW)) + red[2][0];
+    const float bound_a = red[1][0] * sqrtf((float)(kCpg * HW)) + red[2][0];      // no GroupNorm given (raw operand): scale 1
     int ea = bound_a > 0.f ? (int)floorf(log2f(32768.0f / bound_a)) : 0;
     int ew = red[0][0] > 0.f ? (int)floorf(log2f(16384.0f / red[0][0])) : 0;
     ea = max(-24, min(24, ea)); ew = max(-24, min(24, ew));
@@ -177,3 +182,32 @@ extern "C" int node_b200_resconv_forward(void* workspace, const float* x, const 
   if (H == 13) return launch_resconv_13x13(a, st);
   return launch_resconv_7x7(a, st);
 }
+
+// Raw 3x3 stride-1 convolution of a signed tensor (the data gradients of the callers' convolutions, caller_ops.py):
+// out = conv(x, W) (+ addend). prepare() packs an ordinary [64,64,3,3] weight - the caller passes the flipped, transposed
+// kernel for a data gradient - and its power-of-two scale; the operand scale is found per super-tile inside the kernel.
+extern "C" int node_b200_conv3x3_prepare(void* workspace, int C, int H, int W, const float* conv_w, void* stream) {
+  if (node_b200_resconv_workspace_bytes(C, H, W) <= 0) return (int)cudaErrorInvalidValue;
+  ResConvWs w; resconv_layout(workspace, &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  k_resconv_scales<<<1, 256, 0, st>>>(w, H * W, conv_w, nullptr, nullptr);
+  NODE_CUDA_OK(cudaGetLastError());
+  k_resconv_tiles<<<148, 256, 0, st>>>(w, conv_w);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int node_b200_conv3x3_forward(void* workspace, const float* x, const float* addend, float* out, int N, int C, int H, int W,
+                                         void* stream) {
+  if (N < 1 || node_b200_resconv_workspace_bytes(C, H, W) <= 0) return (int)cudaErrorInvalidValue;
+  ResConvWs w; resconv_layout(workspace, &w);
+  ResConvArgs a{};
+  a.w16 = w.w16; a.scal = w.scal; a.x = x; a.shortcut = addend; a.out = out; a.N = N; a.eps = 0.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == 15) return launch_resconv_raw_15x15(a, st);
+  if (H == 8) return launch_resconv_raw_8x8(a, st);
+  if (H == 13) return launch_resconv_raw_13x13(a, st);
+  return launch_resconv_raw_7x7(a, st);
+}
+
+extern "C" int64_t node_b200_resconv_scal_offset(void) { return (int64_t)9 * kW16TileBytes; }
+extern "C" int64_t node_b200_convs2_scal_offset(void) { return (int64_t)kS2Tiles * kW16TileBytes; }

@@ -115,13 +115,21 @@ struct VjpArgs {
   float tsign, eps;
 };
 
+// CTAs of a weight-gradient launch = splits x 2 tap groups x pairs: whole waves of the 148 SMs (1 CTA per SM)
+static inline int wgrad_splits(int NST, int ncv) {
+  const int waves = (ncv + 2) / 3;
+  int n = 148 * waves / (2 * ncv);
+  if (ncv == 2) n = kWgSplits;
+  return NST < n ? NST : n;
+}
+constexpr int kWgMaxPairs = 6;                   // (input, output-gradient) pairs one k_wgrad launch serves (grid.z)
 struct WgradArgs {
   Geo g;
-  const float* R[2]; const float* GC[2];         // [N,64,H,W] fp32 (written by k_vjp)
-  float* part;                                   // [splits][2 conv][9 tap][64 co][kWgCols]
-  const unsigned* gc_max;                        // [2] written by k_vjp
-  const float* scal;                             // FusedWs::scal: [0..1] = activation scales of conv1 / conv2 inputs
-  int nsplit;
+  const float* R[kWgMaxPairs]; const float* GC[kWgMaxPairs];   // [N,64,H,W] fp32 (the adjoint's pairs are written by k_vjp)
+  float* part;                                   // [splits][ncv][9 tap][64 co][kWgCols]
+  const unsigned* gc_max[kWgMaxPairs];           // per pair: bit pattern of max |GC| over the batch (k_vjp / k_absmax)
+  const float* scal[kWgMaxPairs];                // per pair: the power-of-two scale of the input operand (device scalar)
+  int nsplit, ncv;
 };
 
 // images per super-tile of the position-strip tiling (Tile<H,W>::G in step_engine.cuh)

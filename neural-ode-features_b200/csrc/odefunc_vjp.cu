@@ -135,6 +135,7 @@ int launch_wgrad_7x7(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_6x6(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_14x14(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_16x16(const WgradArgs& a, cudaStream_t st);
+int launch_wgrad_15x15(const WgradArgs& a, cudaStream_t st);      // callers only (wgrad_shape_15x15.cu)
 
 }  // namespace node
 
@@ -170,7 +171,7 @@ extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float
   VjpWs v;
   vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
   a.R[0] = r1; a.R[1] = r2; a.GC[0] = gc1; a.GC[1] = gc2; a.part = v.wpart;
-  a.gc_max = v.gc_max; a.scal = g_wgrad_scal;
+  a.gc_max[0] = v.gc_max; a.gc_max[1] = v.gc_max + 1; a.scal[0] = g_wgrad_scal; a.scal[1] = g_wgrad_scal + 1; a.ncv = 2;
   cudaStream_t st = (cudaStream_t)stream;
   if (H == 8 && W == 8) return launch_wgrad_8x8(a, st);
   if (H == 7 && W == 7) return launch_wgrad_7x7(a, st);
@@ -214,5 +215,44 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   const int nsplit = NST < kWgSplits ? NST : kWgSplits;
   k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
                                                               vjp_t, vjp_params);
+  return (int)cudaGetLastError();
+}
+
+// ---- weight gradients of the callers' 3x3 stride-1 convolutions (model.py:119-178 under autograd) ------------------
+// dW[p][co][ci][tap] = sum_{n,pos} GC_p[n,co,pos] * R_p[n,ci,pos + tap] for up to kWgMaxPairs (input, output-gradient) pairs in one
+// k_wgrad launch (the stride-2 convolutions arrive as four stride-1 pairs on parity planes, caller_ops.py). Fixed-order fold.
+namespace node {
+__global__ void k_wgrad_fold(const float* __restrict__ wpart, int nsplit, int ncv, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncv * kC * kC * 9) return;
+  const int p = i / (kC * kC * 9), j = i % (kC * kC * 9);
+  const int co = j / (kC * 9), ci = (j / 9) % kC, tap = j % 9;
+  float v = 0.f;
+  for (int s = 0; s < nsplit; ++s) v += wpart[(((size_t)(s * ncv + p) * 9 + tap) * 64 + co) * kWgCols + ci];
+  dw[i] = v;
+}
+}  // namespace node
+
+extern "C" int64_t node_b200_conv_wgrad_workspace_bytes(int npairs) {
+  if (npairs < 1 || npairs > kWgMaxPairs) return 0;
+  return (int64_t)wgrad_splits(1 << 30, npairs) * npairs * 9 * 64 * kWgCols * 4;
+}
+
+extern "C" int node_b200_conv_wgrad(void* workspace, int npairs, const float* const* inputs, const float* const* grads,
+                                    const float* const* input_scales, const unsigned* const* grad_max_bits, float* dw,
+                                    int N, int C, int H, int W, void* stream) {
+  WgradArgs a{};
+  if (npairs < 1 || npairs > kWgMaxPairs || N < 1 || C != kC) return (int)cudaErrorInvalidValue;
+  if (!((H == 8 && W == 8) || (H == 15 && W == 15))) return (int)cudaErrorInvalidValue;
+  if (!make_geo(N, C, H, W, &a.g)) return (int)cudaErrorInvalidValue;
+  for (int p = 0; p < npairs; ++p) { a.R[p] = inputs[p]; a.GC[p] = grads[p]; a.scal[p] = input_scales[p]; a.gc_max[p] = grad_max_bits[p]; }
+  a.part = (float*)workspace; a.ncv = npairs;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rc = H == 8 ? launch_wgrad_8x8(a, st) : launch_wgrad_15x15(a, st);
+  if (rc != 0) return rc;
+  const int per = strip_images(H, W);
+  const int NST = (N + per - 1) / per;
+  const int nsplit = wgrad_splits(NST, npairs);
+  k_wgrad_fold<<<(npairs * kC * kC * 9 + 255) / 256, 256, 0, st>>>(a.part, nsplit, npairs, dw);
   return (int)cudaGetLastError();
 }

@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
 
   // Operand scales (powers of two, exact): the activations are bounded a priori (the forward engine's scale), the gradients by
   // the batch maximum k_vjp has just measured; fp16 hi/lo of the scaled values = 2^-22 relative (the bf16 split was 2^-16).
-  const float s_r = a.scal[cv];
+  const float s_r = *a.scal[cv];
   float s_g = 1.f;
   {
-    const float m = __uint_as_float(a.gc_max[cv]);
+    const float m = __uint_as_float(*a.gc_max[cv]);
     if (m > 0.f && m < 3.0e38f) {
       int ex;
       (void)frexpf(m, &ex);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
       }
     }
     __syncthreads();
-    float* dst = a.part + ((size_t)(split * 2 + cv) * 9 + (tap0 + tp)) * 64 * kWgCols;
+    float* dst = a.part + ((size_t)(split * a.ncv + cv) * 9 + (tap0 + tp)) * 64 * kWgCols;
     for (int i = tid; i < 64 * kWgCols; i += blockDim.x) {
       const int co = i / kWgCols, n = i % kWgCols;
       dst[i] = (stage[co * (kWgCols + 1) + n] + stage[(64 + co) * (kWgCols + 1) + n]) * (n < 64 ? inv_gr : inv_g);   // the ones column carries no activation scale
@@ -217,8 +217,8 @@ static int launch_wgrad_shape(WgradArgs a, cudaStream_t st) {
   static_assert(128 * (kWgCols + 1) * 4 <= WT::GCH * WT::G_STRIDE + WT::RCH * WT::R_STRIDE, "drain staging");
   NODE_SET_SMEM_ONCE((k_wgrad<H_, W_>), WT::smem);
   const int NST = (a.g.N + T::G - 1) / T::G;
-  a.nsplit = NST < kWgSplits ? NST : kWgSplits;
-  k_wgrad<H_, W_><<<dim3(a.nsplit, 2, 2), T::P, WT::smem, st>>>(a);
+  a.nsplit = wgrad_splits(NST, a.ncv);
+  k_wgrad<H_, W_><<<dim3(a.nsplit, 2, a.ncv), T::P, WT::smem, st>>>(a);
   return (int)cudaGetLastError();
 }
 
@@ -229,3 +229,7 @@ static int launch_wgrad_shape(WgradArgs a, cudaStream_t st) {
   namespace node { \
   int launch_vjp_##H##x##W(const VjpArgs& a, cudaStream_t st) { return launch_vjp_shape<H, W>(a, st); } \
   int launch_wgrad_##H##x##W(const WgradArgs& a, cudaStream_t st) { return launch_wgrad_shape<H, W>(a, st); } }
+
+// weight gradients only (the callers' convolutions): wgrad_shape_HxW.cu
+#define NODE_WGRAD_SHAPE_TU(H, W) \
+  namespace node { int launch_wgrad_##H##x##W(const WgradArgs& a, cudaStream_t st) { return launch_wgrad_shape<H, W>(a, st); } }

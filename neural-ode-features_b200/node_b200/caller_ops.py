@@ -9,7 +9,7 @@ import weakref
 import torch
 import torch.nn as nn
 
-from . import native
+from . import caller_grad, native
 
 launches = 0        # kernels launched by this module (bench.py's gpu_launches)
 
@@ -26,10 +26,15 @@ def _fusable(norm, x):
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 3 and norm.weight.is_cuda):
         return False
-    if torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad or norm.bias.requires_grad):
-        return False
     cell = (x.shape[1] // norm.num_groups) * (x.numel() // (x.shape[0] * x.shape[1]))
+    if _needs_grad(x, norm.weight, norm.bias):       # training: the native backward serves GroupNorm(g, 2g) cells of <= 2048 floats
+        if not (caller_grad.enabled() and x.shape[1] == 2 * norm.num_groups and cell <= 2048):
+            return False
     return x.shape[1] == norm.num_channels and 0 < cell <= 4096 and x.shape[0] > 0
+
+
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 @native.on_device_of(1)
@@ -38,6 +43,8 @@ def group_norm_relu(norm, x, relu=True):
     if not _fusable(norm, x):
         y = norm(x)
         return torch.relu(y) if relu else y
+    if _needs_grad(x, norm.weight, norm.bias):
+        return caller_grad.GnRelu.apply(x, norm.weight, norm.bias, int(norm.num_groups), float(norm.eps), bool(relu))
     x = x.contiguous()
     y = torch.empty_like(x)
     N, C = int(x.shape[0]), int(x.shape[1])
@@ -88,7 +95,7 @@ def _resconv_ok(norm, conv, x, shortcut):
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and shortcut.shape == x.shape and shortcut.dtype == x.dtype):
         return False
-    if torch.is_grad_enabled() and (x.requires_grad or shortcut.requires_grad or conv.weight.requires_grad or norm.weight.requires_grad):
+    if _needs_grad(x, shortcut, conv.weight, norm.weight, norm.bias) and not (caller_grad.enabled() and x.shape[2:] in ((15, 15), (8, 8))):
         return False
     if (conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups) != \
             (64, 64, (3, 3), (1, 1), (1, 1), (1, 1), 1) or conv.bias is not None or conv.padding_mode != 'zeros':
@@ -103,10 +110,11 @@ def res_conv(norm, conv, x, shortcut, next_norm=None):
     """conv(relu(norm(x))) + shortcut for the ResBlock tail; one tcgen05 kernel when the shape is served and no gradient
     is needed, the modules' own ops otherwise. With `next_norm` (the following block's norm1) the result is
     relu(next_norm(.)) of that - fused into the same kernel when next_norm is a GroupNorm(32, 64) with the same eps."""
+    training = _needs_grad(x, shortcut, conv.weight, norm.weight, norm.bias if isinstance(norm, nn.GroupNorm) else None,
+                           next_norm.weight if isinstance(next_norm, nn.GroupNorm) else None)
     fuse_next = (next_norm is not None and isinstance(next_norm, nn.GroupNorm) and next_norm.weight is not None
                  and next_norm.num_groups == 32 and next_norm.num_channels == 64 and isinstance(norm, nn.GroupNorm)
-                 and next_norm.eps == norm.eps
-                 and not (torch.is_grad_enabled() and (next_norm.weight.requires_grad or next_norm.bias.requires_grad)))
+                 and next_norm.eps == norm.eps and not training)       # training: the block output itself is needed by the backward
     if not _resconv_ok(norm, conv, x, shortcut):
         out = conv(torch.relu(norm(x))) + shortcut
         return out if next_norm is None else group_norm_relu(next_norm, out)
@@ -126,6 +134,9 @@ def res_conv(norm, conv, x, shortcut, next_norm=None):
         native.check(lib.node_b200_resconv_prepare(native.ptr(buf), C, H, W, native.ptr(conv.weight), native.ptr(norm.weight),
                                                    native.ptr(norm.bias), native.stream_ptr()), 'resconv_prepare')
         ent = _resconv_ws[key] = (buf, ver, [weakref.ref(p) for p in live])
+    if training:
+        out = caller_grad.ResTail.apply(x, shortcut, norm.weight, norm.bias, conv.weight, float(norm.eps), ent[0])
+        return out if next_norm is None else group_norm_relu(next_norm, out)
     out = torch.empty_like(x)
     nw = native.ptr(next_norm.weight) if fuse_next else None
     nb = native.ptr(next_norm.bias) if fuse_next else None
@@ -156,7 +167,7 @@ def _convs2_ok(norm, conv, down, a):
         return False
     if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 4 and a.shape[1] == 64 and norm.num_groups == 32):
         return False
-    if torch.is_grad_enabled() and (a.requires_grad or conv.weight.requires_grad or down.weight.requires_grad):
+    if _needs_grad(a, conv.weight, down.weight) and not (caller_grad.enabled() and a.shape[2:] in ((30, 30), (15, 15))):
         return False
     return native.lib().node_b200_convs2_workspace_bytes(64, int(a.shape[2]), int(a.shape[3])) > 0
 
@@ -185,6 +196,8 @@ def res_head(norm, conv, down, a):
         native.check(lib.node_b200_convs2_prepare(native.ptr(buf), C, HI, WI, native.ptr(conv.weight), native.ptr(down.weight),
                                                   native.ptr(norm.weight), native.ptr(norm.bias), native.stream_ptr()), 'convs2_prepare')
         ent = _convs2_ws[key] = (buf, ver, [weakref.ref(p) for p in live])
+    if _needs_grad(a, conv.weight, down.weight):
+        return caller_grad.ResHead.apply(a, conv.weight, down.weight, ent[0])
     c = torch.empty((N, C, HO, WO), dtype=a.dtype, device=a.device)
     sc = torch.empty_like(c)
     native.check(lib.node_b200_convs2_forward(native.ptr(ent[0]), native.ptr(a), native.ptr(c), native.ptr(sc), N, C, HI, WI,
@@ -205,7 +218,9 @@ def _stem_ok(conv, norm, x):
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and norm.num_groups == 32 and norm.num_channels == 64):
         return False
-    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad or norm.weight.requires_grad):
+    if torch.is_grad_enabled() and x.requires_grad:          # dL/dx wanted (PGD attack): the modules' own ops
+        return False
+    if _needs_grad(conv.weight, conv.bias, norm.weight, norm.bias) and not caller_grad.enabled():
         return False
     return (int(x.shape[1]), int(x.shape[2]), int(x.shape[3])) in ((3, 32, 32), (1, 28, 28)) and conv.in_channels == x.shape[1]
 
@@ -215,6 +230,8 @@ def stem_gn_relu(conv, norm, x):
     """relu(norm(conv(x))): one CUDA pass when served and no gradient is needed, the modules' own ops otherwise."""
     if not _stem_ok(conv, norm, x):
         return group_norm_relu(norm, conv(x))
+    if _needs_grad(conv.weight, conv.bias, norm.weight, norm.bias):
+        return caller_grad.Stem.apply(x, conv.weight, conv.bias, norm.weight, norm.bias, float(norm.eps))
     x = x.contiguous()
     N, CIN, HIN, WIN = (int(v) for v in x.shape)
     out = torch.empty((N, 64, HIN - 2, WIN - 2), dtype=x.dtype, device=x.device)

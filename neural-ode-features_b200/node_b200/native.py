@@ -35,6 +35,10 @@ EXPORTS = (
     'node_b200_vjp_buffer', 'node_b200_groupnorm_relu', 'node_b200_resconv_workspace_bytes', 'node_b200_resconv_prepare',
     'node_b200_resconv_forward', 'node_b200_convs2_workspace_bytes', 'node_b200_convs2_prepare', 'node_b200_convs2_forward',
     'node_b200_stem_gn_relu', 'node_b200_head', 'node_b200_feature_normalize', 'node_b200_retrieval_scores',
+    'node_b200_groupnorm_relu_backward', 'node_b200_absmax', 'node_b200_plane_split', 'node_b200_plane_merge',
+    'node_b200_conv3x3_prepare', 'node_b200_conv3x3_forward', 'node_b200_conv_wgrad_workspace_bytes', 'node_b200_conv_wgrad',
+    'node_b200_stem_backward_workspace_bytes', 'node_b200_stem_backward', 'node_b200_resconv_scal_offset',
+    'node_b200_convs2_scal_offset',
 )
 
 _lib = None
@@ -82,6 +86,20 @@ def _declare(lib):
     lib.node_b200_head.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _vp]
     lib.node_b200_feature_normalize.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _vp]
     lib.node_b200_retrieval_scores.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, _vp]
+    lib.node_b200_groupnorm_relu_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp]
+    lib.node_b200_absmax.argtypes = [_vp, _i64, _vp, _vp]
+    lib.node_b200_plane_split.argtypes = [_vp, _vp, _i64, _i, _i, _i, _vp]
+    lib.node_b200_plane_merge.argtypes = [_vp, _vp, _i64, _i, _i, _i, _vp]
+    lib.node_b200_conv3x3_prepare.argtypes = [_vp, _i, _i, _i, _vp, _vp]
+    lib.node_b200_conv3x3_forward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_conv_wgrad_workspace_bytes.argtypes = [_i]
+    lib.node_b200_conv_wgrad_workspace_bytes.restype = _i64
+    lib.node_b200_conv_wgrad.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_stem_backward_workspace_bytes.argtypes = [_i]
+    lib.node_b200_stem_backward_workspace_bytes.restype = _i64
+    lib.node_b200_stem_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
+    lib.node_b200_resconv_scal_offset.restype = _i64
+    lib.node_b200_convs2_scal_offset.restype = _i64
 
 
 def lib():
