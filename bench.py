@@ -93,10 +93,10 @@ class ClockSampler(object):
         return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), samples_total=n_all)
 
 
-def build_model(device, adjoint=False):
+def build_model(device, adjoint=False, dropout=0):
     from node_b200 import models
     torch.manual_seed(0)
-    net = models.ODENet(3, n_filters=64, downsample='residual', tol=TOL, adjoint=adjoint).eval()
+    net = models.ODENet(3, n_filters=64, downsample='residual', tol=TOL, adjoint=adjoint, dropout=dropout).eval()
     return net.to(device)
 
 
@@ -270,9 +270,10 @@ def train_step_rate(dev, batch, steps, warmup, world=1):
     gradients, node_b200.distributed.sync_gradients), SGD step (reproduce.sh:3-6 hyper-parameters). Every rank runs it on
     its own shard of `batch` images; returns the dict for the JSON line (aggregate images/s, max over ranks)."""
     import torch.distributed as dist
-    from node_b200 import solver, distributed as nd
+    from node_b200 import solver, caller_grad, distributed as nd
+    cg0 = caller_grad.launches
     torch.manual_seed(0)
-    net = build_model(dev, adjoint=True).train()
+    net = build_model(dev, adjoint=True, dropout=0.5).train()          # cfg3: reproduce.sh:3-6 (lr 0.1, dropout 0.5, wd 1e-4)
     opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
     rank = int(os.environ.get('RANK', '0'))
     g = torch.Generator().manual_seed(99 + rank)
@@ -311,8 +312,11 @@ def train_step_rate(dev, batch, steps, warmup, world=1):
     return dict(images_per_s=world * batch * steps / dt, ms_per_step=1e3 * dt / steps, per_gpu_batch=batch, global_batch=world * batch,
                 n_gpus=world, steps=steps, nfe_forward=nfe[0], nfe_backward=nfe[1], adjoint_vjp=solver.last_stats.get('adjoint_vjp'),
                 loss=float(loss.detach()), non_ode_gradient_floats_allreduced=sent[0],
+                callers_backward='native' if caller_grad.launches > cg0 else 'pytorch',
                 note='forward + CE loss + odeint_adjoint backward (native VJP kernels, tol 1e-3) + gradient sync + SGD step; '
-                     'downsampler / classifier autograd in PyTorch fp32; weak scaling (per-GPU batch fixed), device time, max over ranks')
+                     'downsampler forward AND backward on this repo\'s kernels (node_b200.caller_grad: GroupNorm/ReLU backward, tcgen05 '
+                     'data / weight gradients, fused stem backward), pooling / dropout / linear / loss in PyTorch; weak scaling '
+                     '(per-GPU batch fixed), device time, max over ranks')
 
 
 def strong_scaling(net, dev, world, rank):
