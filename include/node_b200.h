@@ -304,6 +304,18 @@ int node_b200_stem_backward(const float* x, const float* conv_w, const float* co
 int64_t node_b200_resconv_scal_offset(void);
 int64_t node_b200_convs2_scal_offset(void);
 
+/* all-reduce of the solver's float64 sums over NVLink peer memory, fused into the kernel that folds the per-CTA
+ * partials (csrc/peer_reduce.cu) - no host-launched collective between an attempted step and its controller. One process per
+ * GPU: peer_alloc returns the 64-byte CUDA IPC handle of this process' exchange buffer; the host side gathers the handles of
+ * all ranks (torch.distributed) and passes them, rank-major, to peer_open; from then on every node_b200_fused_phase /
+ * node_b200_fused_solve call reduces its sums over the peers (all ranks must issue the same call sequence). peer_close returns
+ * to single-GPU behaviour. fold_reduce is the building block itself: sums[row] = sum_b partials[row][b], then summed over ranks. */
+int node_b200_peer_alloc(void* handle_out_64_bytes);
+int node_b200_peer_open(int world, int rank, const void* handles);
+int node_b200_peer_close(void);
+int node_b200_peer_world(void);
+int node_b200_fold_reduce(const double* partials, int nblocks, double* sums, int nrows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 //     added with the conv bias in the TMEM->shared epilogue.
 // conv_mode 2 swaps the tensor-core engine for a plain fp32 FFMA engine (same kernel family).
 #include "fused_common.cuh"
+#include "peer_reduce.cuh"
 
 namespace node {
 
@@ -732,6 +733,8 @@ extern "C" node_ctl_t* node_b200_fused_ctl(void* workspace) {
 
 constexpr int kTimesByValue = 32;
 struct TimesArg { double t[kTimesByValue]; };
+__global__ void k_put_double(double* dst, double v) { *dst = v; }
+__global__ void k_set_numel(node_ctl_t* c, const double* global_numel) { c->seg_numel[0] = (int64_t)llrint(*global_numel); }
 __global__ void k_set_times(double* t_out, TimesArg ta, int T) {
   if (threadIdx.x < T) t_out[threadIdx.x] = ta.t[threadIdx.x];
 }
@@ -765,23 +768,28 @@ extern "C" int node_b200_fused_phase(void* workspace, int phase, const float* y0
       NODE_CUDA_OK(cudaMemsetAsync(a.w.nonfinite, 0, sizeof(int), st));
       a.mode = MODE_F0; a.y_in = y0; a.out0 = out; a.t_explicit = (float)t_host[0];
       NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
-      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
-      return (int)cudaGetLastError();
+      if (peer_ctx().world > 1) {
+        // sharded over peer memory: the GLOBAL element count of the error-norm mean travels as a third row of the first
+        // reduction (the host would otherwise need a collective plus a read-back before it could enqueue the solve)
+        k_put_double<<<1, 1, 0, st>>>(a.w.partials + 2 * kPartialBlocksF, (double)E);
+        NODE_CUDA_OK((cudaError_t)launch_fold_reduce(a.w.partials, kPartialBlocksF, a.w.sums, 3, (int*)&a.w.ctl->status, st));
+        k_set_numel<<<1, 1, 0, st>>>(a.w.ctl, a.w.sums + 2);
+        return (int)cudaGetLastError();
+      }
+      return launch_fold_reduce(a.w.partials, kPartialBlocksF, a.w.sums, nrows, (int*)&a.w.ctl->status, st);
     }
     case 1: {
       NODE_CUDA_OK((cudaError_t)node_b200_controller(a.w.ctl, 0, a.w.sums, nullptr, a.w.t_out, stream));
       a.mode = MODE_PROBE;
       NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
-      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
-      return (int)cudaGetLastError();
+      return launch_fold_reduce(a.w.partials, kPartialBlocksF, a.w.sums, nrows, (int*)&a.w.ctl->status, st);
     }
     case 2:
       return node_b200_controller(a.w.ctl, 1, a.w.sums, nullptr, a.w.t_out, stream);
     case 3: {
       a.mode = MODE_STEP;
       NODE_CUDA_OK((cudaError_t)launch_fused(a, st));
-      k_fold_partials<<<nrows, 32, 0, st>>>(a.w.partials, a.w.sums, nullptr);
-      return (int)cudaGetLastError();
+      return launch_fold_reduce(a.w.partials, kPartialBlocksF, a.w.sums, nrows, (int*)&a.w.ctl->status, st);
     }
     case 4: {
       NODE_CUDA_OK((cudaError_t)node_b200_controller(a.w.ctl, 2, a.w.sums, a.w.nonfinite, a.w.t_out, stream));

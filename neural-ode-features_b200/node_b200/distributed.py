@@ -22,17 +22,66 @@ import torch
 _group = None
 
 
-def enable(process_group=None):
+_peer = False
+
+
+def enable(process_group=None, peer_reduce=None):
+    """Switch the solver into sharded mode. With `peer_reduce` (default: on for CUDA ranks of one box, NODE_B200_PEER_REDUCE=0
+    switches it off) the fused route's sums are all-reduced over NVLink peer memory INSIDE the kernel that folds them
+    (csrc/peer_reduce.cu) instead of a host-launched ncclAllReduce per attempted step: the ranks exchange the CUDA IPC handles
+    of their exchange buffers once, here."""
+    import os
     import torch.distributed as dist
-    global _group
+    global _group, _peer
     if not dist.is_initialized():
         raise RuntimeError('torch.distributed is not initialised')
     _group = process_group if process_group is not None else dist.group.WORLD
+    _peer = False
+    if peer_reduce is None:
+        peer_reduce = os.environ.get('NODE_B200_PEER_REDUCE', '1') != '0'
+    world = dist.get_world_size(_group)
+    if peer_reduce and torch.cuda.is_available() and dist.get_backend(_group) == 'nccl' and 1 < world <= 8:
+        _peer = _setup_peers(world, dist.get_rank(_group))
+
+
+def _setup_peers(world, rank):
+    """Exchange the IPC handles of the ranks' exchange buffers; every rank reports whether it could map all peers and the
+    mode is used only if ALL could (the decision must be identical everywhere: it changes the collective sequence)."""
+    import ctypes
+    import torch.distributed as dist
+    from . import native
+    lib = native.lib()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    handle = (ctypes.c_ubyte * 64)()
+    ok = lib.node_b200_peer_alloc(ctypes.cast(handle, ctypes.c_void_p)) == 0
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=_group)
+    if ok:
+        blob = torch.cat(gathered).cpu().numpy().tobytes()
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        ok = lib.node_b200_peer_open(world, rank, ctypes.cast(buf, ctypes.c_void_p)) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=_group)
+    if int(flag.item()) != 1:
+        lib.node_b200_peer_close()
+        return False
+    dist.barrier(group=_group)              # every rank has zeroed and mapped the buffers before anybody writes
+    return True
+
+
+def peer_active():
+    """True when the fused route reduces its sums over peer memory (no NCCL call per attempted step)."""
+    return _group is not None and _peer
 
 
 def disable():
-    global _group
+    global _group, _peer
+    if _peer:
+        from . import native
+        native.lib().node_b200_peer_close()
     _group = None
+    _peer = False
 
 
 def group():

@@ -38,7 +38,8 @@ EXPORTS = (
     'node_b200_groupnorm_relu_backward', 'node_b200_absmax', 'node_b200_plane_split', 'node_b200_plane_merge',
     'node_b200_conv3x3_prepare', 'node_b200_conv3x3_forward', 'node_b200_conv_wgrad_workspace_bytes', 'node_b200_conv_wgrad',
     'node_b200_stem_backward_workspace_bytes', 'node_b200_stem_backward', 'node_b200_resconv_scal_offset',
-    'node_b200_convs2_scal_offset',
+    'node_b200_convs2_scal_offset', 'node_b200_peer_alloc', 'node_b200_peer_open', 'node_b200_peer_close', 'node_b200_peer_world',
+    'node_b200_fold_reduce',
 )
 
 _lib = None
@@ -100,6 +101,9 @@ def _declare(lib):
     lib.node_b200_stem_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]
     lib.node_b200_resconv_scal_offset.restype = _i64
     lib.node_b200_convs2_scal_offset.restype = _i64
+    lib.node_b200_peer_alloc.argtypes = [_vp]
+    lib.node_b200_peer_open.argtypes = [_i, _i, _vp]
+    lib.node_b200_fold_reduce.argtypes = [_vp, _i, _vp, _i, _vp]
 
 
 def lib():

@@ -357,10 +357,11 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     launches = 7 + (1 if ws.param_key_fresh else 0)
     ws.param_key_fresh = False
     events = PROFILE_STEP_EVENTS
-    if group is None and events is None:
+    peer = group is not None and dist_state.peer_active()          # sums all-reduced inside the fold kernel (peer memory)
+    if (group is None or peer) and events is None:
         guess = _step_guess.get(id(_unwrap(func)))
         graph = None
-        if guess is not None and _graph_wanted(N, T):
+        if guess is not None and _graph_wanted(N, T) and not peer:
             # Launch-bound sizes: the whole enqueue sequence (f0, probe, `guess` attempted steps with their controllers
             # and dense output) is captured ONCE per (shape, times, tolerances, step count) and replayed.
             graph = _fused_graph(ws, y, th, t_host, common, E, conv_mode, int(tsign), guess)
@@ -390,14 +391,15 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
             out.copy_(graph.out)
     else:
         sharded = group is not None
-        E_glob = dist_state.global_numel(E, y.device) if sharded else E
+        # peer mode: the global element count is reduced on the device with the first norms (no collective, no read-back here)
+        E_glob = dist_state.global_numel(E, y.device) if (sharded and not peer) else E
 
         def phase(ph):
             native.check(lib.node_b200_fused_phase(native.ptr(ws.buf), ph, native.ptr(y), *common, E_glob, native.ptr(out),
                                                    conv_mode, int(tsign), native.stream_ptr()), 'fused_phase %d' % ph)
 
         def reduce():
-            if sharded:
+            if sharded and not peer:                                # peer mode: phases 0, 1, 3 end with the reduced sums
                 dist_state.all_reduce_sum(ws.sums)
 
         phase(0); reduce()
@@ -561,7 +563,10 @@ class _GenericSolve(object):
         if dist_state.group() is not None:
             if self.rep_from < len(self.lens) and dist_state.rank() != 0:
                 self.sums[2 * self.rep_from:].zero_()        # replicated members: counted once (rank 0's copy)
-            dist_state.all_reduce_sum(self.sums)
+            if dist_state.peer_active():                     # in-kernel all-reduce over NVLink peer memory (csrc/peer_reduce.cu)
+                native.check(lib.node_b200_fold_reduce(native.ptr(self.sums), 1, native.ptr(self.sums), len(self.sums), sp), 'fold_reduce')
+            else:
+                dist_state.all_reduce_sum(self.sums)
         native.check(lib.node_b200_controller(native.ptr(self.ctl), mode, native.ptr(self.sums),
                                               native.ptr(self.flag) if mode == 2 else native._vp(0),
                                               native.ptr(self.t_dev), sp), 'controller')
