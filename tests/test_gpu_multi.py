@@ -1,0 +1,29 @@
+"""GPU, >= 2 devices (skipped on a one-GPU box): the sharded solve and training step over NCCL + the peer-memory all-reduce of
+csrc/peer_reduce.cu against the single-GPU run of the same global batch - tools/sharded_check.py under torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('peer', ['1', '0'])
+def test_sharded_forward_and_training_step_two_gpus(native_lib, peer):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    env = dict(os.environ, NODE_B200_PEER_REDUCE=peer)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29541' if peer == '1' else '29543', os.path.join(ROOT, 'tools', 'sharded_check.py'), '192', '--train']
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [json.loads(l) for l in res.stdout.splitlines() if l.startswith('{')]
+    fwd, train = lines[0], lines[1]
+    assert fwd['identical_step_sequence_on_all_ranks'] and fwd['max_rel_output_deviation'] <= 1e-6
+    assert train['identical_nfe_and_backward_sequence_on_all_ranks']
+    assert train['max_rel_dev_classifier_grads'] <= 1e-5
+    assert train['max_rel_dev_odeblock_grads'] <= 1e-2 and train['max_rel_dev_downsample_grads'] <= 1e-2
