@@ -122,6 +122,12 @@ static inline int wgrad_splits(int NST, int ncv) {
   if (ncv == 2) n = kWgSplits;
   return NST < n ? NST : n;
 }
+// the dense 8x8 weight-gradient kernel (wgrad8_engine.cuh): stages of two images
+static inline int wgrad8_splits(int N, int ncv) {
+  const int NST = (N + 1) / 2, waves = (ncv + 2) / 3;
+  const int n = 148 * waves / (2 * ncv);
+  return NST < n ? NST : n;
+}
 constexpr int kWgMaxPairs = 6;                   // (input, output-gradient) pairs one k_wgrad launch serves (grid.z)
 struct WgradArgs {
   Geo g;

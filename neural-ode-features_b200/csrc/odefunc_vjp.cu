@@ -136,6 +136,9 @@ int launch_wgrad_6x6(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_14x14(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_16x16(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_15x15(const WgradArgs& a, cudaStream_t st);      // callers only (wgrad_shape_15x15.cu)
+int launch_wgrad8_dense(const WgradArgs& a, bool ones, cudaStream_t st);      // wgrad8.cu
+// NODE_B200_WGRAD8=0: the strip-tiled k_wgrad<8,8> instead of the dense 8x8 kernel (kept as the second implementation the tests compare)
+static bool wgrad8_enabled() { const char* e = getenv("NODE_B200_WGRAD8"); return !(e != nullptr && e[0] == '0'); }
 
 }  // namespace node
 
@@ -173,7 +176,7 @@ extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float
   a.R[0] = r1; a.R[1] = r2; a.GC[0] = gc1; a.GC[1] = gc2; a.part = v.wpart;
   a.gc_max[0] = v.gc_max; a.gc_max[1] = v.gc_max + 1; a.scal[0] = g_wgrad_scal; a.scal[1] = g_wgrad_scal + 1; a.ncv = 2;
   cudaStream_t st = (cudaStream_t)stream;
-  if (H == 8 && W == 8) return launch_wgrad_8x8(a, st);
+  if (H == 8 && W == 8) return wgrad8_enabled() ? launch_wgrad8_dense(a, true, st) : launch_wgrad_8x8(a, st);
   if (H == 7 && W == 7) return launch_wgrad_7x7(a, st);
   if (H == 6 && W == 6) return launch_wgrad_6x6(a, st);
   if (H == 14 && W == 14) return launch_wgrad_14x14(a, st);
@@ -212,7 +215,7 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;
   const int nst_vjp = use_dense ? grid_dense : (NST < kMaxGrid ? NST : kMaxGrid);
-  const int nsplit = NST < kWgSplits ? NST : kWgSplits;
+  const int nsplit = (H == 8 && W == 8 && wgrad8_enabled()) ? wgrad8_splits(N, 2) : (NST < kWgSplits ? NST : kWgSplits);
   k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
                                                               vjp_t, vjp_params);
   return (int)cudaGetLastError();
@@ -248,11 +251,12 @@ extern "C" int node_b200_conv_wgrad(void* workspace, int npairs, const float* co
   for (int p = 0; p < npairs; ++p) { a.R[p] = inputs[p]; a.GC[p] = grads[p]; a.scal[p] = input_scales[p]; a.gc_max[p] = grad_max_bits[p]; }
   a.part = (float*)workspace; a.ncv = npairs;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = H == 8 ? launch_wgrad_8x8(a, st) : launch_wgrad_15x15(a, st);
+  const bool dense = H == 8 && wgrad8_enabled();
+  const int rc = dense ? launch_wgrad8_dense(a, false, st) : (H == 8 ? launch_wgrad_8x8(a, st) : launch_wgrad_15x15(a, st));
   if (rc != 0) return rc;
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;
-  const int nsplit = wgrad_splits(NST, npairs);
+  const int nsplit = dense ? wgrad8_splits(N, npairs) : wgrad_splits(NST, npairs);
   k_wgrad_fold<<<(npairs * kC * kC * 9 + 255) / 256, 256, 0, st>>>(a.part, nsplit, npairs, dw);
   return (int)cudaGetLastError();
 }

@@ -153,18 +153,24 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_wgrad(const WgradArgs a)
     if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {      // first warp, warp-uniform; one elected lane issues
       const bool lead = ptx::elect_one();
       ptx::tc_fence_after();
+      // only the start-address field (bytes >> 4, the low 14 bits) of a descriptor changes from MMA to MMA: one 32-bit add on
+      // the low word instead of three descriptor constructions per K-step (the issuing thread is instruction-latency bound)
+      const uint64_t da = ptx::make_desc_nosw(gimg, g_lbo, g_sbo);
+      const uint64_t dh = ptx::make_desc_nosw(rimg + (uint32_t)T::HALO * 16, r_lbo, r_sbo);
+      const uint64_t dl = ptx::make_desc_nosw(rimg + (uint32_t)T::HALO * 16 + 10u * (uint32_t)WT::R_STRIDE, r_lbo, r_sbo);
+      const uint32_t a_hiw = (uint32_t)(da >> 32), b_hiw = (uint32_t)(dh >> 32);
+      auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
 #pragma unroll 1
       for (int tp = 0; tp < ntap; ++tp) {
         const int tap = tap0 + tp;
-        const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);
+        const int off = (tap / 3 - 1) * T::Wp + (tap % 3 - 1);       // rows = 16-byte units of the address field
         const uint32_t d = tmem + (uint32_t)(tp * kWgCols);
-#pragma unroll 1
-        for (int k0 = 0; k0 < P; k0 += 16) {
-          const uint64_t adesc = ptx::make_desc_nosw(gimg + (uint32_t)k0 * 16, g_lbo, g_sbo);
-          const uint32_t brow = rimg + (uint32_t)(T::HALO + k0 + off) * 16;
-          const uint64_t b_hi = ptx::make_desc_nosw(brow, r_lbo, r_sbo);
-          const uint64_t b_lo = ptx::make_desc_nosw(brow + 10u * (uint32_t)WT::R_STRIDE, r_lbo, r_sbo);
-          if (lead) {
+        if (lead) {
+#pragma unroll 4
+          for (int k0 = 0; k0 < P; k0 += 16) {
+            const uint64_t adesc = pack((uint32_t)da + (uint32_t)k0, a_hiw);
+            const uint64_t b_hi = pack((uint32_t)dh + (uint32_t)(k0 + off), b_hiw);
+            const uint64_t b_lo = pack((uint32_t)dl + (uint32_t)(k0 + off), b_hiw);
             ptx::mma_f16_ss(d, adesc, b_hi, wg_idesc(kWgCols), (it == 0 && k0 == 0) ? 0u : 1u);
             ptx::mma_f16_ss(d, adesc, b_lo, wg_idesc(64), 1u);
           }
