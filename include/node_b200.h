@@ -279,7 +279,7 @@ int node_b200_retrieval_scores(const float* queries, const float* db, float* sco
  *   resconv_workspace_bytes; maps 15x15, 8x8, 13x13, 7x7.
  * conv_wgrad: dw[p][co][ci][tap] = sum_{n,pos} grads[p][n,co,pos] * inputs[p][n,ci,pos+tap] for npairs <= 6 (input, gradient)
  *   pairs in one launch of the adjoint's weight-gradient GEMM; input_scales[p] / grad_max_bits[p] are DEVICE scalars (the
- *   power-of-two scale of the input operand; the bit pattern of max |grad|, see absmax). Maps 15x15 and 8x8.
+ *   power-of-two scale of the input operand; the bit pattern of max |grad|, see absmax). Maps 15x15, 8x8 (CIFAR), 13x13, 7x7 (MNIST).
  * stem_backward: gradients of out = relu(GroupNorm(32,64)(Conv2d(CIN,64,3,1)(x))) with respect to conv weight [64*CIN*9],
  *   conv bias [64], gamma [64], beta [64] - written in that order to grads - without materialising the conv output
  *   (recomputed per image). x itself receives no gradient. */

@@ -136,6 +136,7 @@ int launch_wgrad_6x6(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_14x14(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_16x16(const WgradArgs& a, cudaStream_t st);
 int launch_wgrad_15x15(const WgradArgs& a, cudaStream_t st);      // callers only (wgrad_shape_15x15.cu)
+int launch_wgrad_13x13(const WgradArgs& a, cudaStream_t st);      // callers only, MNIST (wgrad_shape_13x13.cu)
 int launch_wgrad8_dense(const WgradArgs& a, bool ones, cudaStream_t st);      // wgrad8.cu
 // NODE_B200_WGRAD8=0: the strip-tiled k_wgrad<8,8> instead of the dense 8x8 kernel (kept as the second implementation the tests compare)
 static bool wgrad8_enabled() { const char* e = getenv("NODE_B200_WGRAD8"); return !(e != nullptr && e[0] == '0'); }
@@ -246,13 +247,14 @@ extern "C" int node_b200_conv_wgrad(void* workspace, int npairs, const float* co
                                     int N, int C, int H, int W, void* stream) {
   WgradArgs a{};
   if (npairs < 1 || npairs > kWgMaxPairs || N < 1 || C != kC) return (int)cudaErrorInvalidValue;
-  if (!((H == 8 && W == 8) || (H == 15 && W == 15))) return (int)cudaErrorInvalidValue;
+  if (!((H == 8 && W == 8) || (H == 15 && W == 15) || (H == 13 && W == 13) || (H == 7 && W == 7))) return (int)cudaErrorInvalidValue;
   if (!make_geo(N, C, H, W, &a.g)) return (int)cudaErrorInvalidValue;
   for (int p = 0; p < npairs; ++p) { a.R[p] = inputs[p]; a.GC[p] = grads[p]; a.scal[p] = input_scales[p]; a.gc_max[p] = grad_max_bits[p]; }
   a.part = (float*)workspace; a.ncv = npairs;
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = H == 8 && wgrad8_enabled();
-  const int rc = dense ? launch_wgrad8_dense(a, false, st) : (H == 8 ? launch_wgrad_8x8(a, st) : launch_wgrad_15x15(a, st));
+  const int rc = dense ? launch_wgrad8_dense(a, false, st)
+                       : (H == 8 ? launch_wgrad_8x8(a, st) : (H == 15 ? launch_wgrad_15x15(a, st) : (H == 13 ? launch_wgrad_13x13(a, st) : launch_wgrad_7x7(a, st))));
   if (rc != 0) return rc;
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;

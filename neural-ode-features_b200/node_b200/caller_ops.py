@@ -95,7 +95,7 @@ def _resconv_ok(norm, conv, x, shortcut):
         return False
     if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and shortcut.shape == x.shape and shortcut.dtype == x.dtype):
         return False
-    if _needs_grad(x, shortcut, conv.weight, norm.weight, norm.bias) and not (caller_grad.enabled() and x.shape[2:] in ((15, 15), (8, 8))):
+    if _needs_grad(x, shortcut, conv.weight, norm.weight, norm.bias) and not (caller_grad.enabled() and x.shape[2:] in ((15, 15), (8, 8), (13, 13), (7, 7))):
         return False
     if (conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups) != \
             (64, 64, (3, 3), (1, 1), (1, 1), (1, 1), 1) or conv.bias is not None or conv.padding_mode != 'zeros':
@@ -167,7 +167,7 @@ def _convs2_ok(norm, conv, down, a):
         return False
     if not (a.is_cuda and a.dtype == torch.float32 and a.dim() == 4 and a.shape[1] == 64 and norm.num_groups == 32):
         return False
-    if _needs_grad(a, conv.weight, down.weight) and not (caller_grad.enabled() and a.shape[2:] in ((30, 30), (15, 15))):
+    if _needs_grad(a, conv.weight, down.weight) and not (caller_grad.enabled() and a.shape[2:] in ((30, 30), (15, 15), (26, 26), (13, 13))):
         return False
     return native.lib().node_b200_convs2_workspace_bytes(64, int(a.shape[2]), int(a.shape[3])) > 0
 

@@ -162,6 +162,25 @@ def test_stem_backward_matches_float64(native_lib, n):
     assert all(e <= max(2e-5, 3.0 * a) for e, a in zip(errs, errs_aten)), (errs, errs_aten)
 
 
+def test_mnist_residual_downsampler_gradients(native_lib):
+    """MNIST shapes (28 -> 26 -> 13 -> 7): the same native backward through the 13x13 / 7x7 engines, against float64."""
+    import copy
+    from node_b200 import caller_grad, models
+    torch.manual_seed(3)
+    net = models.ODENet(1, n_filters=64, downsample='residual', tol=1e-3, adjoint=True).to(DEV).train()
+    x = torch.rand(40, 1, 28, 28, device=DEV)
+    y = (0.5 + torch.rand(40, 64, 7, 7, device=DEV)) * 1e-2
+    before = caller_grad.launches
+    out_n, g_n = _grads(net, x, y, True)
+    assert caller_grad.launches - before > 40, 'the native training path did not run on every block'
+    out_r, g_r = _grads(net, x, y, False)
+    out_t, g_t = _grads(copy.deepcopy(net).double(), x.double(), y.double(), False)
+    worst = {k: rel(g_n[k].double(), g_t[k]) for k in g_t}
+    aten = {k: rel(g_r[k].double(), g_t[k]) for k in g_t}
+    bad = {k: (worst[k], aten[k]) for k in worst if worst[k] > max(1e-4, 3.0 * aten[k])}
+    assert not bad, bad
+
+
 def test_training_step_gradients_whole_model(native_lib):
     """cfg3: forward + CE loss + adjoint backward; all parameter gradients with the native caller backward vs PyTorch's."""
     net = _blocks(1)
