@@ -316,6 +316,17 @@ int node_b200_peer_close(void);
 int node_b200_peer_world(void);
 int node_b200_fold_reduce(const double* partials, int nblocks, double* sums, int nrows, void* stream);
 
+/* One attempted step of odeint_adjoint's backward integration (adjoint.py:23-102 via dopri5.py:94-122) for the fused ODE-Net
+ * dynamics, enqueued by ONE call: 6 x (stage combination of the 4-member augmented state, augmented dynamics through the native
+ * VJP kernels), error norm, fold, controller. `bufs` are the generic route's 11 state rows of row_elems floats (Y0 Y1 F0 F1
+ * K2..K6 YMID YI), members (y, adj_y, adj_t, adj_params) at seg_off; `cur` = index of the current y/f pair; ts32_offset_bytes =
+ * offset of the controller's fp32 stage times inside *ctl (node_b200_ctl_layout). The caller reads the controller block back
+ * once per attempt, as before. */
+int node_b200_adjoint_step(void* ctl, float* bufs, int64_t row_elems, int cur, const int64_t* host_seg_off,
+                           const int64_t* host_seg_len, int n_seg, void* workspace, void* vjp_workspace, float tsign,
+                           int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums,
+                           int* nonfinite_flag, const double* t_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

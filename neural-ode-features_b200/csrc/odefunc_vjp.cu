@@ -262,3 +262,36 @@ extern "C" int node_b200_conv_wgrad(void* workspace, int npairs, const float* co
   k_wgrad_fold<<<(npairs * kC * kC * 9 + 255) / 256, 256, 0, st>>>(a.part, nsplit, npairs, dw);
   return (int)cudaGetLastError();
 }
+
+// ---- one attempted step of the adjoint's backward integration as ONE call (SURVEY 8b `node_dopri5_adjoint_backward`, the
+// per-step half of it; reference adjoint.py:23-102 through dopri5.py:94-122) ------------------------------------------------------
+// The augmented state (y, adj_y, adj_t, adj_params) lives in the generic route's flat buffers (rows of `row_elems` floats:
+// Y0 Y1 F0 F1 K2..K6 YMID YI, members at seg_off). The host loop issued 6 x (stage combination, augmented dynamics) + error norm
+// + fold + controller as ~20 Python -> C calls per attempt; at the reference's batch of 128 those calls, not the kernels, were
+// the step. Same kernels, same order, same arithmetic - enqueued from here.
+extern "C" int node_b200_adjoint_step(void* ctl_v, float* bufs, int64_t row_elems, int cur, const int64_t* seg_off,
+                                      const int64_t* seg_len, int n_seg, void* workspace, void* vjp_workspace, float tsign,
+                                      int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums,
+                                      int* nonfinite_flag, const double* t_out, void* stream) {
+  if (n_seg != 4) return (int)cudaErrorInvalidValue;
+  node_ctl_t* ctl = (node_ctl_t*)ctl_v;
+  enum { Y0 = 0, F0 = 2, K2 = 4, YI = 10 };
+  auto row = [&](int i) { return bufs + (size_t)i * row_elems; };
+  const int y = Y0 + cur, f = F0 + cur, yn = Y0 + (cur ^ 1), fn = F0 + (cur ^ 1);
+  const int ks[7] = {f, K2, K2 + 1, K2 + 2, K2 + 3, K2 + 4, fn};
+  const void* kp[7];
+  for (int i = 0; i < 7; ++i) kp[i] = row(ks[i]);
+  const float* ts32 = (const float*)((const char*)ctl_v + ts32_offset_bytes);
+  for (int i = 0; i < 6; ++i) {
+    float* dst = row(i < 5 ? YI : yn);
+    NODE_CUDA_OK((cudaError_t)node_b200_rk_stage_combine(ctl, NODE_F32, i, dst, row(y), kp, i + 1, row_elems, stream));
+    float* out = row(ks[i + 1]);
+    NODE_CUDA_OK((cudaError_t)node_b200_odefunc_vjp(workspace, vjp_workspace, dst + seg_off[0], dst + seg_off[1], ts32 + (i + 1), tsign,
+                                                    out + seg_off[0], out + seg_off[1], out + seg_off[2], out + seg_off[3], N, C, H, W,
+                                                    stream));
+  }
+  NODE_CUDA_OK((cudaError_t)node_b200_rk_error_norm(ctl, NODE_F32, row(y), row(yn), kp, seg_off, seg_len, n_seg, partials,
+                                                    nonfinite_flag, stream));
+  NODE_CUDA_OK((cudaError_t)node_b200_reduce_partials(partials, 2 * n_seg, sums, stream));
+  return node_b200_controller(ctl, 2, sums, nonfinite_flag, t_out, stream);
+}

@@ -39,7 +39,7 @@ EXPORTS = (
     'node_b200_conv3x3_prepare', 'node_b200_conv3x3_forward', 'node_b200_conv_wgrad_workspace_bytes', 'node_b200_conv_wgrad',
     'node_b200_stem_backward_workspace_bytes', 'node_b200_stem_backward', 'node_b200_resconv_scal_offset',
     'node_b200_convs2_scal_offset', 'node_b200_peer_alloc', 'node_b200_peer_open', 'node_b200_peer_close', 'node_b200_peer_world',
-    'node_b200_fold_reduce',
+    'node_b200_fold_reduce', 'node_b200_adjoint_step',
 )
 
 _lib = None
@@ -104,6 +104,7 @@ def _declare(lib):
     lib.node_b200_peer_alloc.argtypes = [_vp]
     lib.node_b200_peer_open.argtypes = [_i, _i, _vp]
     lib.node_b200_fold_reduce.argtypes = [_vp, _i, _vp, _i, _vp]
+    lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
 
 
 def lib():

@@ -597,19 +597,37 @@ class _GenericSolve(object):
         self.out[0].copy_(self.bufs[Y0])
         cur = 0
         view = native.CtlView(self.ctl)
+        # The adjoint of the fused ODE-Net dynamics on one GPU: a whole attempted step is ONE C call (node_b200_adjoint_step) -
+        # the same kernels in the same order as the loop below, without ~20 Python -> C round trips per attempt.
+        fast = None
+        if (isinstance(self.func, _FusedAugmented) and dist_state.group() is None and self.code == native.F32 and nseg == 4
+                and os.environ.get('NODE_B200_ADJOINT_STEP', '1') != '0'):
+            N, C, H, W = self.shapes[0]
+            fws = fused_workspace(self.device, N, C, H, W)
+            fws.prepare(recognise_odefunc(self.func.func))
+            fast = (fws.buf, _vjp_workspace(self.device, N, C, H, W), N, C, H, W)
         while not view.i32('done'):
             y, f, yn, fn = Y0 + cur, F0 + cur, Y0 + (cur ^ 1), F0 + (cur ^ 1)
             ks = [f, K2, K2 + 1, K2 + 2, K2 + 3, K2 + 4, fn]
-            for i in range(6):
-                dst = YI if i < 5 else yn
-                native.check(lib.node_b200_rk_stage_combine(ctl, self.code, i, native.ptr(self.bufs[dst]),
-                                                            native.ptr(self.bufs[y]), self._kptrs(ks[:i + 1]), i + 1,
-                                                            self.L, sp), 'stage_combine')
-                self._eval(self.ts[i + 1], dst, ks[i + 1])
-            native.check(lib.node_b200_rk_error_norm(ctl, self.code, native.ptr(self.bufs[y]), native.ptr(self.bufs[yn]),
-                                                     self._kptrs(ks), *segs, native.ptr(self.partials),
-                                                     native.ptr(self.flag), sp), 'error_norm')
-            self._reduce_and_control(2)
+            if fast is not None:
+                native.check(lib.node_b200_adjoint_step(ctl, native.ptr(self.bufs), self.L, cur, self.seg_off, self.seg_len, nseg,
+                                                        native.ptr(fast[0]), native.ptr(fast[1]), float(self.tsign),
+                                                        native.layout()['ts32'], fast[2], fast[3], fast[4], fast[5],
+                                                        native.ptr(self.partials), native.ptr(self.sums), native.ptr(self.flag),
+                                                        native.ptr(self.t_dev), sp), 'adjoint_step')
+                if hasattr(self.func.target, 'nfe'):
+                    self.func.target.nfe += 6             # model.py:340 counts every evaluation
+            else:
+                for i in range(6):
+                    dst = YI if i < 5 else yn
+                    native.check(lib.node_b200_rk_stage_combine(ctl, self.code, i, native.ptr(self.bufs[dst]),
+                                                                native.ptr(self.bufs[y]), self._kptrs(ks[:i + 1]), i + 1,
+                                                                self.L, sp), 'stage_combine')
+                    self._eval(self.ts[i + 1], dst, ks[i + 1])
+                native.check(lib.node_b200_rk_error_norm(ctl, self.code, native.ptr(self.bufs[y]), native.ptr(self.bufs[yn]),
+                                                         self._kptrs(ks), *segs, native.ptr(self.partials),
+                                                         native.ptr(self.flag), sp), 'error_norm')
+                self._reduce_and_control(2)
             view = native.CtlView(self.ctl)                                   # the one host read per attempt
             if view.i32('accepted_last'):
                 if view.i32('out_hi') > view.i32('out_lo'):
