@@ -327,6 +327,28 @@ int node_b200_adjoint_step(void* ctl, float* bufs, int64_t row_elems, int cur, c
                            int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums,
                            int* nonfinite_flag, const double* t_out, void* stream);
 
+/* Wide dynamics (n_filters = 128, 192, 256: the paper's CIFAR setting, reproduce.sh:21): ODEfunc.forward (model.py:339-348) as
+ * 64-channel blocks on the tcgen05 engine instead of cuDNN.
+ * conv3x3_forward_strided = conv3x3_forward on a 64-channel block of a wider tensor: x / (addend, out) point at the block's
+ *   first channel and in_image_stride / out_image_stride are the element distances between images (C_total * H * W);
+ *   addend == out accumulates the input-channel blocks of one output block.
+ * groupnorm_relu_ex: y = post * relu?(GroupNorm(x + add_bias[c] + tsign * t * add_tmap[c][pix])) - the GroupNorm after a
+ *   ConcatConv2d whose time channel is folded into b + t * Tmap (t: device scalar). L = (C / groups) * HW must be a multiple
+ *   of 4 and <= 4096. */
+int node_b200_conv3x3_forward_strided(void* workspace, const float* x, const float* addend, float* out, int N, int C, int H, int W,
+                                      int64_t in_image_stride, int64_t out_image_stride, void* stream);
+int node_b200_groupnorm_relu_ex(const float* x, float* y, const float* gamma, const float* beta, const float* add_bias,
+                                const float* add_tmap, const float* t_dev, float tsign, float post, int64_t N, int C, int groups,
+                                int HW, float eps, int relu, void* stream);
+
+/* wide_odefunc: one evaluation out = s * ODEfunc(s * t, y) of a C = 64 * nb model by ONE call (the sequence above); block_ws =
+ * [2 convs][nb][nb] conv3x3 workspaces (conv3x3_prepare on W[64co:64co+64, 1+64ci:1+64ci+64]) block_ws_stride bytes apart,
+ * bias / tmap = the convolutions' biases [C] and folded time maps [C,H,W], tmp_a / tmp_c = [N,C,H,W] scratch. */
+int node_b200_wide_odefunc(void* block_ws, int64_t block_ws_stride, const float* y, float* out, float* tmp_a, float* tmp_c,
+                           const float* g1w, const float* g1b, const float* g2w, const float* g2b, const float* g3w, const float* g3b,
+                           const float* bias1, const float* tmap1, const float* bias2, const float* tmap2, const float* t_dev,
+                           float tsign, int N, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,9 +198,15 @@ extern "C" int node_b200_conv3x3_prepare(void* workspace, int C, int H, int W, c
 
 extern "C" int node_b200_conv3x3_forward(void* workspace, const float* x, const float* addend, float* out, int N, int C, int H, int W,
                                          void* stream) {
+  return node_b200_conv3x3_forward_strided(workspace, x, addend, out, N, C, H, W, 0, 0, stream);
+}
+
+extern "C" int node_b200_conv3x3_forward_strided(void* workspace, const float* x, const float* addend, float* out, int N, int C, int H,
+                                                 int W, int64_t in_image_stride, int64_t out_image_stride, void* stream) {
   if (N < 1 || node_b200_resconv_workspace_bytes(C, H, W) <= 0) return (int)cudaErrorInvalidValue;
   ResConvWs w; resconv_layout(workspace, &w);
   ResConvArgs a{};
+  a.in_stride = in_image_stride; a.out_stride = out_image_stride;
   a.w16 = w.w16; a.scal = w.scal; a.x = x; a.shortcut = addend; a.out = out; a.N = N; a.eps = 0.f;
   cudaStream_t st = (cudaStream_t)stream;
   if (H == 15) return launch_resconv_raw_15x15(a, st);
@@ -211,3 +217,30 @@ extern "C" int node_b200_conv3x3_forward(void* workspace, const float* x, const 
 
 extern "C" int64_t node_b200_resconv_scal_offset(void) { return (int64_t)9 * kW16TileBytes; }
 extern "C" int64_t node_b200_convs2_scal_offset(void) { return (int64_t)kS2Tiles * kW16TileBytes; }
+
+// One evaluation of a wide ODEfunc (C = 64 * nb; node_b200/wide.py, model.py:339-348) enqueued by ONE call: GN1 -> ReLU,
+// nb x nb block convolutions, GN2 (+ folded time channel) -> ReLU, nb x nb block convolutions, GN3 (+ folded time channel).
+// block_ws = [2 layers][nb co][nb ci] prepared conv3x3 workspaces, block_ws_stride bytes apart; tmp_a / tmp_c = [N,C,H,W] scratch.
+extern "C" int node_b200_wide_odefunc(void* block_ws, int64_t block_ws_stride, const float* y, float* out, float* tmp_a, float* tmp_c,
+                                      const float* g1w, const float* g1b, const float* g2w, const float* g2b, const float* g3w,
+                                      const float* g3b, const float* bias1, const float* tmap1, const float* bias2,
+                                      const float* tmap2, const float* t_dev, float tsign, int N, int C, int H, int W, void* stream) {
+  if (C % kC != 0 || C <= kC || N < 1) return (int)cudaErrorInvalidValue;
+  const int nb = C / kC, HW = H * W;
+  const int64_t stride = (int64_t)C * HW;
+  auto convs = [&](int layer, const float* a, float* c) -> int {
+    for (int co = 0; co < nb; ++co)
+      for (int ci = 0; ci < nb; ++ci) {
+        char* ws = (char*)block_ws + ((int64_t)(layer * nb + co) * nb + ci) * block_ws_stride;
+        float* dst = c + (int64_t)co * kC * HW;
+        const int rc = node_b200_conv3x3_forward_strided(ws, a + (int64_t)ci * kC * HW, ci ? dst : nullptr, dst, N, kC, H, W, stride, stride, stream);
+        if (rc != 0) return rc;
+      }
+    return 0;
+  };
+  NODE_CUDA_OK((cudaError_t)node_b200_groupnorm_relu(y, tmp_a, g1w, g1b, N, C, 32, HW, 1e-5f, 1, stream));
+  NODE_CUDA_OK((cudaError_t)convs(0, tmp_a, tmp_c));
+  NODE_CUDA_OK((cudaError_t)node_b200_groupnorm_relu_ex(tmp_c, tmp_a, g2w, g2b, bias1, tmap1, t_dev, tsign, 1.0f, N, C, 32, HW, 1e-5f, 1, stream));
+  NODE_CUDA_OK((cudaError_t)convs(1, tmp_a, tmp_c));
+  return node_b200_groupnorm_relu_ex(tmp_c, out, g3w, g3b, bias2, tmap2, t_dev, tsign, tsign < 0 ? -1.0f : 1.0f, N, C, 32, HW, 1e-5f, 0, stream);
+}

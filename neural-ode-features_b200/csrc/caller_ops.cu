@@ -82,6 +82,76 @@ __global__ void __launch_bounds__(kGnThreads) k_groupnorm_relu(const float* __re
   }
 }
 
+// y = post * relu?(GN(x + bias[c] + t * tmap[c][pix])): the GroupNorm that follows a ConcatConv2d whose time channel has been
+// folded into a position-dependent bias (model.py:320-323; conv(cat([t*1, x])) = conv(x, W[:,1:]) + b + t*Tmap) - used by the
+// wide (C = 128, 256, ...) dynamics, whose convolutions run as 64-channel blocks and carry no bias of their own.
+template <int VPT, int VEC>
+__global__ void __launch_bounds__(kGnThreads) k_groupnorm_relu_ex(const float* __restrict__ x, float* __restrict__ y,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   const float* __restrict__ add_bias, const float* __restrict__ add_tmap,
+                                                                   const float* __restrict__ t_dev, float tsign, float post,
+                                                                   int groups, int cpg, int HW, float eps, int relu) {
+  __shared__ float scratch[kGnThreads / 32];
+  const int L = cpg * HW;
+  const size_t base = (size_t)blockIdx.x * L;
+  const int g = blockIdx.x % groups;
+  const float t = add_tmap != nullptr ? tsign * __ldg(t_dev) : 0.f;
+  float v[VPT][VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int e = (i * kGnThreads + threadIdx.x) * VEC;
+    if (e < L) {
+      if (VEC == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(x + base + e));
+        v[i][0] = q.x; v[i][1 % VEC] = q.y; v[i][2 % VEC] = q.z; v[i][3 % VEC] = q.w;
+      } else {
+        v[i][0] = __ldg(x + base + e);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int c = g * cpg + (e + j) / HW, pix = (e + j) % HW;
+        if (add_bias != nullptr) v[i][j] += __ldg(add_bias + c);
+        if (add_tmap != nullptr) v[i][j] = fmaf(t, __ldg(add_tmap + (size_t)c * HW + pix), v[i][j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s += v[i][j];
+  }
+  const float inv_n = 1.0f / (float)L;
+  const float mean = block_sum_f(s, scratch) * inv_n;
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int e = (i * kGnThreads + threadIdx.x) * VEC;
+    if (e < L) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { const float d = v[i][j] - mean; q2 = fmaf(d, d, q2); }
+    }
+  }
+  const float rstd = 1.0f / sqrtf(block_sum_f(q2, scratch) * inv_n + eps);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int e = (i * kGnThreads + threadIdx.x) * VEC;
+    if (e < L) {
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int c = g * cpg + (e + j) / HW;
+        const float a = rstd * __ldg(gamma + c);
+        float r = fmaf(v[i][j] - mean, a, __ldg(beta + c));
+        if (relu) r = fmaxf(r, 0.f);
+        o[j] = r * post;
+      }
+      if (VEC == 4) *reinterpret_cast<float4*>(y + base + e) = make_float4(o[0], o[1 % VEC], o[2 % VEC], o[3 % VEC]);
+      else y[base + e] = o[0];
+    }
+  }
+}
+
 template <int VPT, int VEC>
 static int launch_gn(const float* x, float* y, const float* gamma, const float* beta, int64_t cells, int groups, int cpg, int HW,
                      float eps, int relu, cudaStream_t st) {
@@ -113,6 +183,25 @@ extern "C" int node_b200_groupnorm_relu(const float* x, float* y, const float* g
   if (L <= 16 * kGnThreads) return launch_gn<16, 1>(x, y, gamma, beta, cells, groups, cpg, HW, eps, relu, st);
   if (L <= 32 * kGnThreads) return launch_gn<32, 1>(x, y, gamma, beta, cells, groups, cpg, HW, eps, relu, st);
   return (int)cudaErrorInvalidValue;
+}
+
+extern "C" int node_b200_groupnorm_relu_ex(const float* x, float* y, const float* gamma, const float* beta, const float* add_bias,
+                                           const float* add_tmap, const float* t_dev, float tsign, float post, int64_t N, int C,
+                                           int groups, int HW, float eps, int relu, void* stream) {
+  using namespace node;
+  if (N < 1 || C < 1 || groups < 1 || C % groups != 0 || HW < 1 || (add_tmap != nullptr && t_dev == nullptr)) return (int)cudaErrorInvalidValue;
+  const int cpg = C / groups;
+  const int64_t L = (int64_t)cpg * HW, cells = N * groups;
+  if (cells > 0x7fffffffLL || L % 4 != 0 || L > 8 * 4 * kGnThreads || ((uintptr_t)x % 16) || ((uintptr_t)y % 16)) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nv = L / 4;
+#define NODE_GN_EX(VPT) k_groupnorm_relu_ex<VPT, 4><<<(unsigned)cells, kGnThreads, 0, st>>>(x, y, gamma, beta, add_bias, add_tmap, t_dev, tsign, post, groups, cpg, HW, eps, relu)
+  if (nv <= kGnThreads) NODE_GN_EX(1);
+  else if (nv <= 2 * kGnThreads) NODE_GN_EX(2);
+  else if (nv <= 4 * kGnThreads) NODE_GN_EX(4);
+  else NODE_GN_EX(8);
+#undef NODE_GN_EX
+  return (int)cudaGetLastError();
 }
 
 // ---- stem: conv0 (Conv2d(CIN, 64, 3, 1), bias) -> GroupNorm(32, 64) -> ReLU in one pass ------------------------------------

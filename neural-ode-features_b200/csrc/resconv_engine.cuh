@@ -17,6 +17,7 @@ struct ResConvArgs {
   const float* gamma_next; const float* beta_next;   // optional: the NEXT block's norm1 - out = relu(norm1_next(conv + shortcut))
   const float* x; const float* shortcut; float* out;
   int N; float eps;
+  int64_t in_stride, out_stride;   // elements between images of x / of shortcut and out (0 = 64 * H * W): channel blocks of wider tensors
 };
 
 __host__ __device__ constexpr size_t resconv_smem_bytes(int A_PART, int NSLOT, int NWARP, int G) {
@@ -131,12 +132,14 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
     me.isB = me.img_l != ia;
   }
   const float sa = a.scal[0], inv = a.scal[2];
+  const size_t istr = a.in_stride > 0 ? (size_t)a.in_stride : (size_t)kC * HW, ostr = a.out_stride > 0 ? (size_t)a.out_stride : (size_t)kC * HW;
   uint32_t njob = 0;
 #pragma unroll 1
   for (int st = blockIdx.x * NSLOT + me.slot; st < NST; st += stride) {
     const int img = st * T::G + me.img_l;
     const bool valid = me.inimg && img < a.N;
-    const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+    const size_t goff = valid ? (size_t)img * istr + me.pix : (size_t)(me.inimg ? me.pix : 0);
+    const size_t ooff = valid ? (size_t)img * ostr + me.pix : (size_t)(me.inimg ? me.pix : 0);
     float x[32];
     float inv_job = inv;
     if constexpr (RAW) {
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_resconv(const Re
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
       conv_read<T, false>(sm, me, hb, x, tmem, 0, inv_job, true, valid);
-      const size_t p0 = goff + (size_t)(32 * hb) * HW;
+      const size_t p0 = ooff + (size_t)(32 * hb) * HW;
       if (!RAW || a.shortcut != nullptr) {
         float sc[32];
 #pragma unroll

@@ -39,7 +39,8 @@ EXPORTS = (
     'node_b200_conv3x3_prepare', 'node_b200_conv3x3_forward', 'node_b200_conv_wgrad_workspace_bytes', 'node_b200_conv_wgrad',
     'node_b200_stem_backward_workspace_bytes', 'node_b200_stem_backward', 'node_b200_resconv_scal_offset',
     'node_b200_convs2_scal_offset', 'node_b200_peer_alloc', 'node_b200_peer_open', 'node_b200_peer_close', 'node_b200_peer_world',
-    'node_b200_fold_reduce', 'node_b200_adjoint_step',
+    'node_b200_fold_reduce', 'node_b200_adjoint_step', 'node_b200_conv3x3_forward_strided', 'node_b200_groupnorm_relu_ex',
+    'node_b200_wide_odefunc',
 )
 
 _lib = None
@@ -104,6 +105,9 @@ def _declare(lib):
     lib.node_b200_peer_alloc.argtypes = [_vp]
     lib.node_b200_peer_open.argtypes = [_i, _i, _vp]
     lib.node_b200_fold_reduce.argtypes = [_vp, _i, _vp, _i, _vp]
+    lib.node_b200_conv3x3_forward_strided.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp]
+    lib.node_b200_wide_odefunc.argtypes = [_vp, _i64] + [_vp] * 15 + [_f, _i, _i, _i, _i, _vp]
+    lib.node_b200_groupnorm_relu_ex.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i64, _i, _i, _i, _f, _i, _vp]
     lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
 
 

@@ -684,6 +684,15 @@ def _solve(func, y0, t, rtol, atol, options):
         plain = not options and not _is_iterable(rtol) and not _is_iterable(atol)
         if params is not None and plain and _fusable_state(params, y0) and len(t_host) <= 1024:
             return (_solve_fused(func, params, y0[0], t_host, tsign, rtol, atol),)
+        from . import wide
+        base_mod = _unwrap(func)
+        if (plain and os.environ.get('NODE_B200_WIDE', '1') != '0' and os.environ.get('NODE_B200_FUSED', '1') != '0'
+                and wide.serves(base_mod, y0)):
+            # n_filters = 128 / 192 / 256 (the paper's CIFAR setting): the dynamics as 64-channel blocks on the tcgen05 engine,
+            # K2-K6 from the generic route
+            out = _GenericSolve(wide.WideDynamics.of(base_mod), y0, t_host, rtol, atol, options, tsign=tsign).run()
+            last_stats['route'] = 'native-wide'
+            return out
         if tsign < 0 and not hasattr(func, 'eval_into'):
             base = func
             call = lambda tt, yy: tuple(-v for v in base(-tt, yy))

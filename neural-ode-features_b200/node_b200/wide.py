@@ -1,0 +1,127 @@
+"""Wide ODE-Net dynamics (n_filters = 128, 192, 256 - the paper's CIFAR setting, reference reproduce.sh:21, model.py:326-348)
+on this repo's kernels instead of cuDNN.
+
+The fused step engines are built for C = 64 (one accumulator tile = all output channels). For wider models the dynamics run
+per evaluation as 64-channel blocks on the same tcgen05 machinery:
+
+    a1 = relu(GN1(y))                                   node_b200_groupnorm_relu      (cells of C/32 channels)
+    c1[co] = sum_ci conv3x3(a1[ci], W1[co, 1+ci])       node_b200_conv3x3_forward_strided, (C/64)^2 launches, `addend == out`
+    a2 = relu(GN2(c1 + b1 + t * Tmap1))                 node_b200_groupnorm_relu_ex   (the time channel folded: model.py:320-323)
+    c2[co] = sum_ci conv3x3(a2[ci], W2[co, 1+ci])
+    k  = s * GN3(c2 + b2 + t * Tmap2)                   node_b200_groupnorm_relu_ex
+
+(fp32 contract by fp16 operand splitting; the operand scale is found per super-tile inside the convolution kernel, so no
+a-priori bound on the activations is needed). The Runge-Kutta stage combinations, error norm, controller and dense output
+are the generic route's kernels - at C = 256 an evaluation is 16x the FLOPs of C = 64 for 4x the bytes, so leaving them
+un-fused costs a few per cent. Served maps: 8x8 (CIFAR residual), 7x7 (MNIST residual), 15x15, 13x13.
+"""
+import weakref
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import native
+
+_SERVED_HW = ((8, 8), (7, 7), (15, 15), (13, 13))
+
+
+def recognise(func):
+    """The reference's ODEfunc (model.py:326-348) with C = 128, 192, 256, ... fp32 CUDA parameters; returns C or None."""
+    if not isinstance(func, nn.Module) or (type(func).__name__ != 'ODEfunc' and not getattr(func, '_node_b200_fusable', False)):
+        return None
+    try:
+        convs = [func.conv1._layer, func.conv2._layer]
+        norms = [func.norm1, func.norm2, func.norm3]
+    except AttributeError:
+        return None
+    if not isinstance(getattr(func, 'relu', None), nn.ReLU):
+        return None
+    C = convs[0].out_channels
+    if C <= 64 or C % 64 != 0:
+        return None
+    for c in convs:
+        if type(c) is not nn.Conv2d or (c.in_channels, c.out_channels, c.kernel_size, c.stride, c.padding, c.dilation, c.groups) != \
+                (C + 1, C, (3, 3), (1, 1), (1, 1), (1, 1), 1) or c.bias is None or c.padding_mode != 'zeros':
+            return None
+        if c.weight.dtype != torch.float32 or not c.weight.is_cuda:
+            return None
+    for n in norms:
+        if type(n) is not nn.GroupNorm or n.num_groups != 32 or n.num_channels != C or not n.affine or abs(n.eps - 1e-5) > 1e-12:
+            return None
+    return C
+
+
+def serves(func, y0):
+    C = recognise(func)
+    if C is None or len(y0) != 1:
+        return False
+    y = y0[0]
+    return (y.dtype == torch.float32 and y.is_cuda and y.dim() == 4 and y.shape[1] == C and tuple(y.shape[2:]) in _SERVED_HW
+            and y.device == func.conv1._layer.weight.device and ((C // 32) * y.shape[2] * y.shape[3]) % 4 == 0)
+
+
+class WideDynamics(object):
+    """eval_into-style dynamics for the generic route (solver._GenericSolve): f(t, y) of a wide ODEfunc, block by block."""
+
+    _cache = weakref.WeakKeyDictionary()
+
+    def __init__(self, func):
+        self.func = func
+        self.C = recognise(func)
+        self.nb = self.C // 64
+
+    @classmethod
+    def of(cls, func):
+        inst = cls._cache.get(func)
+        if inst is None:
+            inst = cls._cache[func] = cls(func)
+        return inst
+
+    # ---- per parameter version: 64x64 weight blocks packed for the engine, time maps ------------------------------------
+    def _prepare(self, H, W):
+        convs = [self.func.conv1._layer, self.func.conv2._layer]
+        key = (H, W) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
+        if getattr(self, '_key', None) == key:
+            return
+        lib = native.lib()
+        dev = convs[0].weight.device
+        nbytes = lib.node_b200_resconv_workspace_bytes(64, H, W)
+        if not hasattr(self, '_ws') or self._ws.shape[-1] != nbytes or self._ws.device != dev:
+            self._ws = torch.zeros((2, self.nb, self.nb, nbytes), dtype=torch.uint8, device=dev)
+        self._tmap = []
+        ones = torch.ones(1, 1, H, W, device=dev)
+        for li, c in enumerate(convs):
+            w = c.weight.detach()
+            self._tmap.append(F.conv2d(ones, w[:, :1], padding=1)[0].contiguous())      # [C, H, W]: sum of the time-plane taps inside the map
+            for co in range(self.nb):
+                for ci in range(self.nb):
+                    blk = w[64 * co:64 * co + 64, 1 + 64 * ci:1 + 64 * ci + 64].contiguous()
+                    native.check(lib.node_b200_conv3x3_prepare(native.ptr(self._ws[li, co, ci]), 64, H, W, native.ptr(blk),
+                                                               native.stream_ptr()), 'conv3x3_prepare')
+        self._key = key
+
+    def eval_into(self, t_dev, src, dst, tsign):
+        """dst[0] = tsign * f(tsign * t, src[0]) (misc.py:184-187 for reversed time)."""
+        y, out = src[0], dst[0]
+        N, C, H, W = (int(v) for v in y.shape)
+        self._prepare(H, W)
+        f, lib, sp = self.func, native.lib(), native.stream_ptr
+        if not hasattr(self, '_tmp') or self._tmp.shape[1:] != y.shape or self._tmp.device != y.device:
+            self._tmp = torch.empty((2,) + tuple(y.shape), dtype=y.dtype, device=y.device)
+        a, c = self._tmp[0], self._tmp[1]
+        t32 = t_dev if t_dev.dtype == torch.float32 else t_dev.float()
+        native.check(lib.node_b200_wide_odefunc(
+            native.ptr(self._ws), int(self._ws.shape[-1]), native.ptr(y), native.ptr(out), native.ptr(a), native.ptr(c),
+            native.ptr(f.norm1.weight), native.ptr(f.norm1.bias), native.ptr(f.norm2.weight), native.ptr(f.norm2.bias),
+            native.ptr(f.norm3.weight), native.ptr(f.norm3.bias), native.ptr(f.conv1._layer.bias), native.ptr(self._tmap[0]),
+            native.ptr(f.conv2._layer.bias), native.ptr(self._tmap[1]), native.ptr(t32), float(tsign), N, C, H, W, sp()), 'wide_odefunc')
+        if hasattr(f, 'nfe'):
+            f.nfe += 1                                       # model.py:340 counts every evaluation
+
+    def __call__(self, t, y):
+        """f(t, y) as a plain function (tests): y a tensor, t a python float or 0-d tensor."""
+        t_dev = t if torch.is_tensor(t) else torch.tensor(float(t), dtype=torch.float32, device=y.device)
+        out = torch.empty_like(y)
+        self.eval_into(t_dev.to(y.device), (y.contiguous(),), (out,), 1.0)
+        return out
