@@ -349,6 +349,27 @@ int node_b200_wide_odefunc(void* block_ws, int64_t block_ws_stride, const float*
                            const float* bias1, const float* tmap1, const float* bias2, const float* tmap2, const float* t_dev,
                            float tsign, int N, int C, int H, int W, void* stream);
 
+/* wide8: the wide dynamics on 8x8 maps (C = 128 / 256) as ONE TMA-fed tcgen05 implicit GEMM over all channels per convolution
+ * (csrc/wide8_engine.cu) instead of (C/64)^2 block launches. ODEfunc.forward (model.py:339-348) =
+ *   gn_operand(0, y) -> conv(0) -> gn_operand(1, c1 + b1 + t*Tmap1) -> conv(1) -> groupnorm_relu_ex(c2 + b2 + t*Tmap2).
+ * prepare: packs W1[:, 1:], W2[:, 1:] ([C, C+1, 3, 3] ConcatConv2d weights, model.py:313-323) as fp16 hi/lo weight tiles at a
+ *   power-of-two scale, the folded time maps and the operand scales (from |gamma|, |beta| of norm1 / norm2).
+ * operand = node_b200_wide8_operand_bytes(N, C) bytes, ZERO-FILLED ONCE by the caller (the kernels never write the halo entries).
+ * gn_operand(which): operand <- scale * relu(GroupNorm_32(x (+ add_bias + tsign * t * Tmap1 when which == 1))) as fp16 hi + lo.
+ * conv(which): out[N, C, 8, 8] <- conv3x3(operand, W_which[:, 1:]) (no bias, no time channel).
+ * odefunc: the five launches above; out = tsign * f(tsign * t, y). watchdog: 1 if a bounded barrier wait expired (synchronises). */
+int64_t node_b200_wide8_workspace_bytes(int C, int H, int W);
+int64_t node_b200_wide8_operand_bytes(int64_t N, int C);
+int node_b200_wide8_prepare(void* workspace, int C, int H, int W, const float* conv1_w, const float* conv2_w, const float* g1w,
+                            const float* g1b, const float* g2w, const float* g2b, void* stream);
+int node_b200_wide8_gn_operand(void* workspace, int which, const float* x, void* operand, const float* gamma, const float* beta,
+                               const float* add_bias, const float* t_dev, float tsign, int N, int C, void* stream);
+int node_b200_wide8_conv(void* workspace, int which, const void* operand, float* out, int N, int C, void* stream);
+int node_b200_wide8_watchdog(void* workspace, int C, void* stream);
+int node_b200_wide8_odefunc(void* workspace, const float* y, float* out, void* operand, float* tmp_c, const float* g1w,
+                            const float* g1b, const float* g2w, const float* g2b, const float* g3w, const float* g3b,
+                            const float* bias1, const float* bias2, const float* t_dev, float tsign, int N, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

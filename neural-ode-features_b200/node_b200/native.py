@@ -40,7 +40,8 @@ EXPORTS = (
     'node_b200_stem_backward_workspace_bytes', 'node_b200_stem_backward', 'node_b200_resconv_scal_offset',
     'node_b200_convs2_scal_offset', 'node_b200_peer_alloc', 'node_b200_peer_open', 'node_b200_peer_close', 'node_b200_peer_world',
     'node_b200_fold_reduce', 'node_b200_adjoint_step', 'node_b200_conv3x3_forward_strided', 'node_b200_groupnorm_relu_ex',
-    'node_b200_wide_odefunc',
+    'node_b200_wide_odefunc', 'node_b200_wide8_workspace_bytes', 'node_b200_wide8_operand_bytes', 'node_b200_wide8_prepare',
+    'node_b200_wide8_gn_operand', 'node_b200_wide8_conv', 'node_b200_wide8_watchdog', 'node_b200_wide8_odefunc',
 )
 
 _lib = None
@@ -108,6 +109,15 @@ def _declare(lib):
     lib.node_b200_conv3x3_forward_strided.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp]
     lib.node_b200_wide_odefunc.argtypes = [_vp, _i64] + [_vp] * 15 + [_f, _i, _i, _i, _i, _vp]
     lib.node_b200_groupnorm_relu_ex.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i64, _i, _i, _i, _f, _i, _vp]
+    lib.node_b200_wide8_workspace_bytes.argtypes = [_i, _i, _i]
+    lib.node_b200_wide8_workspace_bytes.restype = _i64
+    lib.node_b200_wide8_operand_bytes.argtypes = [_i64, _i]
+    lib.node_b200_wide8_operand_bytes.restype = _i64
+    lib.node_b200_wide8_prepare.argtypes = [_vp, _i, _i, _i] + [_vp] * 7
+    lib.node_b200_wide8_gn_operand.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _vp]
+    lib.node_b200_wide8_conv.argtypes = [_vp, _i, _vp, _vp, _i, _i, _vp]
+    lib.node_b200_wide8_watchdog.argtypes = [_vp, _i, _vp]
+    lib.node_b200_wide8_odefunc.argtypes = [_vp] * 14 + [_f, _i, _i, _vp]
     lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
 
 

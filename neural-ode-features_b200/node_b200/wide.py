@@ -14,7 +14,13 @@ per evaluation as 64-channel blocks on the same tcgen05 machinery:
 a-priori bound on the activations is needed). The Runge-Kutta stage combinations, error norm, controller and dense output
 are the generic route's kernels - at C = 256 an evaluation is 16x the FLOPs of C = 64 for 4x the bytes, so leaving them
 un-fused costs a few per cent. Served maps: 8x8 (CIFAR residual), 7x7 (MNIST residual), 15x15, 13x13.
+
+8x8 maps with C = 128 / 256 (the CIFAR `residual` model) run on the wide8 engine instead (csrc/wide8_engine.cu): the GroupNorm pass
+writes the activation once as the fp16 hi/lo operand image of the dense 8x8 tiling and each convolution is ONE TMA-fed tcgen05
+implicit GEMM over all C channels (N = C accumulator columns, a weight tile read once per 4 images). `NODE_B200_WIDE8=0` keeps the
+block path.
 """
+import os
 import weakref
 
 import torch
@@ -101,10 +107,53 @@ class WideDynamics(object):
                                                                native.stream_ptr()), 'conv3x3_prepare')
         self._key = key
 
+    # ---- wide8 engine: 8x8 maps, C = 128 / 256 ---------------------------------------------------------------------------
+    def _wide8(self, H, W):
+        return (H, W) == (8, 8) and self.C in (128, 256) and os.environ.get('NODE_B200_WIDE8', '1') != '0'
+
+    def _prepare8(self):
+        f = self.func
+        ps = [f.conv1._layer.weight, f.conv2._layer.weight, f.norm1.weight, f.norm1.bias, f.norm2.weight, f.norm2.bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, '_key8', None) == key:
+            return
+        lib = native.lib()
+        dev = ps[0].device
+        nbytes = lib.node_b200_wide8_workspace_bytes(self.C, 8, 8)
+        if not hasattr(self, '_ws8') or self._ws8.device != dev:
+            self._ws8 = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        native.check(lib.node_b200_wide8_prepare(native.ptr(self._ws8), self.C, 8, 8, *[native.ptr(p.detach()) for p in ps],
+                                                 native.stream_ptr()), 'wide8_prepare')
+        self._key8 = key
+
+    def _eval8(self, t_dev, y, out, tsign):
+        N, C = int(y.shape[0]), self.C
+        self._prepare8()
+        f, lib = self.func, native.lib()
+        nop = lib.node_b200_wide8_operand_bytes(N, C)
+        if not hasattr(self, '_op8') or self._op8.numel() != nop or self._op8.device != y.device:
+            self._op8 = torch.zeros(nop, dtype=torch.uint8, device=y.device)      # halo entries stay zero: the kernels never write them
+            self._c8 = torch.empty_like(y)
+        t32 = t_dev if t_dev.dtype == torch.float32 else t_dev.float()
+        native.check(lib.node_b200_wide8_odefunc(
+            native.ptr(self._ws8), native.ptr(y), native.ptr(out), native.ptr(self._op8), native.ptr(self._c8),
+            native.ptr(f.norm1.weight), native.ptr(f.norm1.bias), native.ptr(f.norm2.weight), native.ptr(f.norm2.bias),
+            native.ptr(f.norm3.weight), native.ptr(f.norm3.bias), native.ptr(f.conv1._layer.bias), native.ptr(f.conv2._layer.bias),
+            native.ptr(t32), float(tsign), N, C, native.stream_ptr()), 'wide8_odefunc')
+
+    def watchdog(self):
+        """1 if a bounded barrier wait of the wide8 convolution kernel expired since the last prepare (synchronises)."""
+        return int(native.lib().node_b200_wide8_watchdog(native.ptr(self._ws8), self.C, native.stream_ptr())) if hasattr(self, '_ws8') else 0
+
     def eval_into(self, t_dev, src, dst, tsign):
         """dst[0] = tsign * f(tsign * t, src[0]) (misc.py:184-187 for reversed time)."""
         y, out = src[0], dst[0]
         N, C, H, W = (int(v) for v in y.shape)
+        if self._wide8(H, W):
+            self._eval8(t_dev, y, out, tsign)
+            if hasattr(self.func, 'nfe'):
+                self.func.nfe += 1
+            return
         self._prepare(H, W)
         f, lib, sp = self.func, native.lib(), native.stream_ptr
         if not hasattr(self, '_tmp') or self._tmp.shape[1:] != y.shape or self._tmp.device != y.device:

@@ -37,6 +37,54 @@ def test_wide_dynamics_match_module(native_lib, C, hw, n):
     assert f.nfe == 6
 
 
+@pytest.mark.parametrize('C,n', [(256, 1), (256, 5), (256, 8), (128, 3), (256, 601), (128, 594)])
+def test_wide8_conv_pieces(native_lib, C, n):
+    """wide8 engine, piece by piece: operand image + implicit GEMM against GroupNorm -> ReLU -> cuDNN fp32 convolution."""
+    import torch.nn.functional as F
+    from node_b200 import models, wide, native
+    torch.manual_seed(C + n)
+    f = models.ODEfunc(C).to(DEV)
+    with torch.no_grad():
+        for norm in (f.norm1, f.norm2, f.norm3):
+            norm.weight.uniform_(0.5, 1.5)
+            norm.bias.uniform_(-0.5, 0.5)
+        y = torch.randn(n, C, 8, 8, device=DEV) * 1.5 + 0.2
+        wd = wide.WideDynamics.of(f)
+        wd._prepare8()
+        lib = native_lib
+        op = torch.zeros(lib.node_b200_wide8_operand_bytes(n, C), dtype=torch.uint8, device=DEV)
+        out = torch.empty_like(y)
+        t = torch.tensor(0.4, device=DEV)
+        for which, (norm, conv) in enumerate(((f.norm1, f.conv1._layer), (f.norm2, f.conv2._layer))):
+            bias = f.conv1._layer.bias if which == 1 else None
+            native.check(lib.node_b200_wide8_gn_operand(native.ptr(wd._ws8), which, native.ptr(y), native.ptr(op), native.ptr(norm.weight),
+                                                        native.ptr(norm.bias), native.ptr(bias) if bias is not None else None, native.ptr(t),
+                                                        1.0, n, C, native.stream_ptr()), 'gn_operand')
+            native.check(lib.node_b200_wide8_conv(native.ptr(wd._ws8), which, native.ptr(op), native.ptr(out), n, C, native.stream_ptr()), 'conv')
+            x = y
+            if which == 1:
+                tmap = F.conv2d(torch.ones(1, 1, 8, 8, device=DEV), f.conv1._layer.weight[:, :1], padding=1)
+                x = y + bias.view(1, C, 1, 1) + t * tmap
+            ref = F.conv2d(torch.relu(norm(x)), conv.weight[:, 1:], padding=1)
+            assert rel(out, ref) <= 2e-5, (which, rel(out, ref))
+        assert wd.watchdog() == 0
+
+
+def test_wide8_matches_block_path(native_lib):
+    from node_b200 import models, wide
+    torch.manual_seed(9)
+    f = models.ODEfunc(256).to(DEV)
+    y = torch.randn(7, 256, 8, 8, device=DEV)
+    with torch.no_grad():
+        got = wide.WideDynamics.of(f)(0.3, y)
+        os.environ['NODE_B200_WIDE8'] = '0'
+        try:
+            ref = wide.WideDynamics.of(f)(0.3, y)
+        finally:
+            os.environ.pop('NODE_B200_WIDE8', None)
+    assert rel(got, ref) <= 2e-5, rel(got, ref)
+
+
 @pytest.mark.parametrize('times', [[0.0, 1.0], [0.0, 0.3, 1.0], [1.0, 0.0]])
 def test_wide_solve_matches_module_route(native_lib, times):
     from node_b200 import models, solver
