@@ -491,6 +491,22 @@ def other_configs(dev):
         x = torch.rand(256, 3, 32, 32, device=dev)
         r = rate(lambda: net(x), 256, reps=3)
         out['n_filters_256'] = dict(images_per_s=r, batch=256, nfe=solver.last_stats.get('nfe'), route=solver.last_stats.get('route'))
+        # the paper's CIFAR setting (reproduce.sh:21) at a batch of whole rounds of the wide8 convolution kernel (148 CTAs x 4 images x 4)
+        x = torch.rand(2368, 3, 32, 32, device=dev)
+        r = rate(lambda: net(x), 2368, reps=3)
+        h0 = net.downsample(x)
+        rb = rate(lambda: net.odeblock(h0), 2368, reps=3)
+        nfe = solver.last_stats.get('nfe')
+        out['n_filters_256_b2368'] = dict(images_per_s=r, batch=2368, nfe=nfe, route=solver.last_stats.get('route'), odeblock_ms=2368e3 / rb,
+                                          odeblock_algorithmic_tflops=2368 * nfe * 2 * 2 * 9 * 256 * 256 * 64 / (2368.0 / rb) / 1e12,
+                                          note='dynamics: wide8 engine (one tcgen05 implicit GEMM per convolution, f16x3); RK stages / error norm: generic route kernels')
+        os.environ['NODE_B200_WIDE'] = '0'
+        try:
+            r0 = rate(lambda: net(x), 2368, reps=2)
+            out['n_filters_256_b2368']['cudnn_dynamics_images_per_s'] = r0
+        finally:
+            os.environ.pop('NODE_B200_WIDE', None)
+        del x, h0
         # retrieval scoring of the 10,000-image test set (evaluate.py:326,339) on a device-resident feature plane
         from node_b200 import retrieval
         feats = torch.rand(10000, 64, device=dev)

@@ -1,11 +1,11 @@
 // Wide dynamics on 8x8 maps (n_filters = 128 / 256: the paper's CIFAR setting, reference reproduce.sh:21, model.py:326-348) as a
 // TMA-fed tcgen05 implicit GEMM over ALL channels: one evaluation of ODEfunc.forward (model.py:339-348) is
 //
-//     k_wide_gn_operand   a1 = relu(GN1(y))                        -> operand image (fp16 hi + lo)
+//     k_wide_gn<operand>  a1 = relu(GN1(y))                        -> operand image (fp16 hi + lo)
 //     k_wide_conv         c1 = conv3x3(a1, W1[:, 1:])              N = C accumulator columns, K = 9 * C
-//     k_wide_gn_operand   a2 = relu(GN2(c1 + b1 + t * Tmap1))      (time channel of ConcatConv2d folded, model.py:320-323)
+//     k_wide_gn<operand>  a2 = relu(GN2(c1 + b1 + t * Tmap1))      (time channel of ConcatConv2d folded, model.py:320-323)
 //     k_wide_conv         c2 = conv3x3(a2, W2[:, 1:])
-//     k_groupnorm_relu_ex k  = s * GN3(c2 + b2 + t * Tmap2)        (caller_ops.cu)
+//     k_wide_gn<fp32>     k  = s * GN3(c2 + b2 + t * Tmap2)
 //
 // The block path of caller_conv.cu (node_b200_wide_odefunc) ran a convolution as (C/64)^2 launches of the 64-channel engine,
 // each converting its input block again and read-modify-writing its output block. Here the GroupNorm pass writes the activation
@@ -130,62 +130,174 @@ __device__ __forceinline__ size_t operand_entry(int img, int S, int kc, int part
   return ((size_t)st * S + (kc >> 2)) * kStageB + kLead + (size_t)part * kPartB + (size_t)(kc & 3) * kLBO + (size_t)slot * kSlotB + (size_t)(pix & 7) * 16;
 }
 
-template <int CPG>
-__global__ void __launch_bounds__(128) k_wide_gn_operand(const float* __restrict__ x, uint8_t* __restrict__ a16, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, const float* __restrict__ add_bias,
-                                                          const float* __restrict__ add_tmap, const float* __restrict__ t_dev, float tsign,
-                                                          const float* __restrict__ scale, int C, float eps) {
+// One block per (image, stage of 4 k-chunks = 32 channels): thread = (channel c of each chunk, pixel quad q), 4 independent
+// 128-bit loads in flight per thread. OPERAND: write scale * relu(GN(.)) as fp16 hi / lo entries of the operand image; otherwise
+// write post * GN(.) as fp32 [N, C, 8, 8] (norm3).
+template <int CPG, bool OPERAND>
+__global__ void __launch_bounds__(128) k_wide_gn(const float* __restrict__ x, uint8_t* __restrict__ a16, float* __restrict__ y,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ add_bias, const float* __restrict__ add_tmap,
+                                                  const float* __restrict__ t_dev, float tsign, const float* __restrict__ scale, float post,
+                                                  int C, float eps) {
   constexpr int WPG = CPG / 2;                    // warps per GroupNorm group
-  __shared__ float red[2][4];
-  __shared__ __align__(16) __half tile[2][64][8];
+  __shared__ float red[2][4][4];
+  __shared__ __align__(16) __half tile[OPERAND ? 4 : 1][2][64][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkc = C >> 3;
-  const int img = blockIdx.x / nkc, kc = blockIdx.x % nkc;
-  const int c = tid >> 4, q = tid & 15, ch = 8 * kc + c;
-  float4 v4 = __ldg(reinterpret_cast<const float4*>(x + ((size_t)img * C + ch) * 64 + 4 * q));
-  float v[4] = {v4.x, v4.y, v4.z, v4.w};
-  if (add_bias != nullptr) {
-    const float b = __ldg(add_bias + ch);
+  const int S = C >> 5;
+  const int img = blockIdx.x / S, stg = blockIdx.x % S;
+  const int c = tid >> 4, q = tid & 15;
+  float v[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] += b;
+  for (int j = 0; j < 4; ++j) {
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + ((size_t)img * C + 32 * stg + 8 * j + c) * 64 + 4 * q));
+    v[j][0] = v4.x; v[j][1] = v4.y; v[j][2] = v4.z; v[j][3] = v4.w;
+  }
+  if (add_bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float b = __ldg(add_bias + 32 * stg + 8 * j + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[j][e] += b;
+    }
   }
   if (add_tmap != nullptr) {
     const float t = tsign * __ldg(t_dev);
-    const float4 m = __ldg(reinterpret_cast<const float4*>(add_tmap + (size_t)ch * 64 + 4 * q));
-    v[0] = fmaf(t, m.x, v[0]); v[1] = fmaf(t, m.y, v[1]); v[2] = fmaf(t, m.z, v[2]); v[3] = fmaf(t, m.w, v[3]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(add_tmap + (size_t)(32 * stg + 8 * j + c) * 64 + 4 * q));
+      v[j][0] = fmaf(t, m.x, v[j][0]); v[j][1] = fmaf(t, m.y, v[j][1]); v[j][2] = fmaf(t, m.z, v[j][2]); v[j][3] = fmaf(t, m.w, v[j][3]);
+    }
   }
   const int wg0 = (warp / WPG) * WPG;
   constexpr float inv_n = 1.0f / (float)(CPG * 64);
-  float s = warp_sum((v[0] + v[1]) + (v[2] + v[3]));
-  if (lane == 0) red[0][warp] = s;
-  __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < WPG; ++i) tot += red[0][wg0 + i];
-  const float mean = tot * inv_n;
-  float d[4], q2 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { d[j] = v[j] - mean; q2 = fmaf(d[j], d[j], q2); }
-  q2 = warp_sum(q2);
-  if (lane == 0) red[1][warp] = q2;
-  __syncthreads();
-  tot = 0.f;
-#pragma unroll
-  for (int i = 0; i < WPG; ++i) tot += red[1][wg0 + i];
-  const float rstd = 1.0f / sqrtf(tot * inv_n + eps);
-  const float sa = __ldg(scale);
-  const float ga = rstd * __ldg(gamma + ch), be = __ldg(beta + ch);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float r = fmaxf(fmaf(d[j], ga, be), 0.f) * sa;
-    const __half hi = __float2half_rn(r);
-    tile[0][4 * q + j][c] = hi;
-    tile[1][4 * q + j][c] = __float2half_rn(r - __half2float(hi));
+    const float s = warp_sum((v[j][0] + v[j][1]) + (v[j][2] + v[j][3]));
+    if (lane == 0) red[0][j][warp] = s;
   }
   __syncthreads();
-  const int part = tid >> 6, pix = tid & 63;
-  const uint4 e = *reinterpret_cast<const uint4*>(&tile[part][pix][0]);
-  *reinterpret_cast<uint4*>(a16 + operand_entry(img, C >> 5, kc, part, pix)) = e;
+  float mean[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPG; ++i) tot += red[0][j][wg0 + i];
+    mean[j] = tot * inv_n;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float q2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[j][e] -= mean[j]; q2 = fmaf(v[j][e], v[j][e], q2); }
+    q2 = warp_sum(q2);
+    if (lane == 0) red[1][j][warp] = q2;
+  }
+  __syncthreads();
+  const float sa = OPERAND ? __ldg(scale) : post;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPG; ++i) tot += red[1][j][wg0 + i];
+    const float rstd = 1.0f / sqrtf(tot * inv_n + eps);
+    const int ch = 32 * stg + 8 * j + c;
+    const float ga = rstd * __ldg(gamma + ch), be = __ldg(beta + ch);
+    if constexpr (OPERAND) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float r = fmaxf(fmaf(v[j][e], ga, be), 0.f) * sa;
+        const __half hi = __float2half_rn(r);
+        tile[j][0][4 * q + e][c] = hi;
+        tile[j][1][4 * q + e][c] = __float2half_rn(r - __half2float(hi));
+      }
+    } else {
+      float4 o;
+      o.x = fmaf(v[j][0], ga, be) * sa; o.y = fmaf(v[j][1], ga, be) * sa; o.z = fmaf(v[j][2], ga, be) * sa; o.w = fmaf(v[j][3], ga, be) * sa;
+      *reinterpret_cast<float4*>(y + ((size_t)img * C + ch) * 64 + 4 * q) = o;
+    }
+  }
+  if constexpr (OPERAND) {
+    __syncthreads();
+    const int part = tid >> 6, pix = tid & 63;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 e = *reinterpret_cast<const uint4*>(&tile[j][part][pix][0]);
+      *reinterpret_cast<uint4*>(a16 + operand_entry(img, S, 4 * stg + j, part, pix)) = e;
+    }
+  }
+}
+
+// Operand mode without a transposition: thread = (pixel, half of the stage's 32 channels) owns 16 channels of ONE pixel = two
+// complete 16-byte operand entries (hi and lo): 16 warp-coalesced scalar loads in flight, statistics by warp sums + one exchange
+// between the two warps of a half, four 16-byte stores.
+template <int CPG>
+__global__ void __launch_bounds__(128) k_wide_gn_op(const float* __restrict__ x, uint8_t* __restrict__ a16, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, const float* __restrict__ add_bias,
+                                                     const float* __restrict__ add_tmap, const float* __restrict__ t_dev, float tsign,
+                                                     const float* __restrict__ scale, int C, float eps) {
+  constexpr int NG = 16 / CPG;                    // GroupNorm groups per thread
+  __shared__ float red[2][4][NG];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = C >> 5;
+  const int img = blockIdx.x / S, stg = blockIdx.x % S;
+  const int px = tid & 63, h = tid >> 6, ch0 = 32 * stg + 16 * h;
+  const float* xp = x + ((size_t)img * C + ch0) * 64 + px;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __ldg(xp + i * 64);
+  if (add_bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(add_bias + ch0 + i);
+  }
+  if (add_tmap != nullptr) {
+    const float t = tsign * __ldg(t_dev);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaf(t, __ldg(add_tmap + (size_t)(ch0 + i) * 64 + px), v[i]);
+  }
+  constexpr float inv_n = 1.0f / (float)(CPG * 64);
+  float mean[NG], rstd[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) s += v[g * CPG + i];
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp][g] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    mean[g] = (red[0][2 * h][g] + red[0][2 * h + 1][g]) * inv_n;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) { v[g * CPG + i] -= mean[g]; q2 = fmaf(v[g * CPG + i], v[g * CPG + i], q2); }
+    q2 = warp_sum(q2);
+    if (lane == 0) red[1][warp][g] = q2;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < NG; ++g) rstd[g] = 1.0f / sqrtf((red[1][2 * h][g] + red[1][2 * h + 1][g]) * inv_n + eps);
+  const float sa = __ldg(scale);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = 8 * k + 2 * e + u;
+        r[u] = fmaxf(fmaf(v[i], rstd[i / CPG] * __ldg(gamma + ch0 + i), __ldg(beta + ch0 + i)), 0.f) * sa;
+      }
+      const __half2 hh = __floats2half2_rn(r[0], r[1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(r[0] - hf.x, r[1] - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(a16 + operand_entry(img, S, 4 * stg + 2 * h + k, 0, px)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a16 + operand_entry(img, S, 4 * stg + 2 * h + k, 1, px)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 // ---- the convolution ----------------------------------------------------------------------------------------------------------
@@ -349,11 +461,16 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
-static int launch_gn_operand(const float* x, uint8_t* a16, const float* gamma, const float* beta, const float* add_bias, const float* add_tmap,
-                             const float* t_dev, float tsign, const float* scale, int N, int C, cudaStream_t st) {
-  const unsigned grid = (unsigned)((int64_t)N * (C / 8));
-  if (C == 256) k_wide_gn_operand<8><<<grid, 128, 0, st>>>(x, a16, gamma, beta, add_bias, add_tmap, t_dev, tsign, scale, C, 1e-5f);
-  else k_wide_gn_operand<4><<<grid, 128, 0, st>>>(x, a16, gamma, beta, add_bias, add_tmap, t_dev, tsign, scale, C, 1e-5f);
+static int launch_gn(const float* x, uint8_t* a16, float* y, const float* gamma, const float* beta, const float* add_bias, const float* add_tmap,
+                     const float* t_dev, float tsign, const float* scale, float post, int N, int C, cudaStream_t st) {
+  const unsigned grid = (unsigned)((int64_t)N * (C / 32));
+  if (a16 != nullptr) {
+    if (C == 256) k_wide_gn_op<8><<<grid, 128, 0, st>>>(x, a16, gamma, beta, add_bias, add_tmap, t_dev, tsign, scale, C, 1e-5f);
+    else k_wide_gn_op<4><<<grid, 128, 0, st>>>(x, a16, gamma, beta, add_bias, add_tmap, t_dev, tsign, scale, C, 1e-5f);
+  } else {
+    if (C == 256) k_wide_gn<8, false><<<grid, 128, 0, st>>>(x, nullptr, y, gamma, beta, add_bias, add_tmap, t_dev, tsign, nullptr, post, C, 1e-5f);
+    else k_wide_gn<4, false><<<grid, 128, 0, st>>>(x, nullptr, y, gamma, beta, add_bias, add_tmap, t_dev, tsign, nullptr, post, C, 1e-5f);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -391,7 +508,7 @@ extern "C" int node_b200_wide8_gn_operand(void* workspace, int which, const floa
   if (N < 1 || (C != 128 && C != 256) || which < 0 || which > 1) return (int)cudaErrorInvalidValue;
   w8::Ws w; w8::ws_layout(workspace, C, &w);
   const float* tmap = (add_bias != nullptr && which == 1) ? w.tmap : nullptr;           // GN2 follows conv1 (Tmap1)
-  return w8::launch_gn_operand(x, (uint8_t*)operand, gamma, beta, add_bias, tmap, t_dev, tsign, w.scal + 3 * which, N, C, (cudaStream_t)stream);
+  return w8::launch_gn(x, (uint8_t*)operand, nullptr, gamma, beta, add_bias, tmap, t_dev, tsign, w.scal + 3 * which, 1.f, N, C, (cudaStream_t)stream);
 }
 
 extern "C" int node_b200_wide8_conv(void* workspace, int which, const void* operand, float* out, int N, int C, void* stream) {
@@ -420,6 +537,6 @@ extern "C" int node_b200_wide8_odefunc(void* workspace, const float* y, float* o
   NODE_CUDA_OK((cudaError_t)node_b200_wide8_conv(workspace, 0, operand, tmp_c, N, C, stream));
   NODE_CUDA_OK((cudaError_t)node_b200_wide8_gn_operand(workspace, 1, tmp_c, operand, g2w, g2b, bias1, t_dev, tsign, N, C, stream));
   NODE_CUDA_OK((cudaError_t)node_b200_wide8_conv(workspace, 1, operand, tmp_c, N, C, stream));
-  return node_b200_groupnorm_relu_ex(tmp_c, out, g3w, g3b, bias2, w.tmap + (size_t)C * 64, t_dev, tsign, tsign < 0 ? -1.0f : 1.0f, N, C, 32, 64,
-                                     1e-5f, 0, stream);
+  return w8::launch_gn(tmp_c, nullptr, out, g3w, g3b, bias2, w.tmap + (size_t)C * 64, t_dev, tsign, nullptr, tsign < 0 ? -1.0f : 1.0f, N, C,
+                       (cudaStream_t)stream);
 }

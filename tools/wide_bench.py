@@ -8,7 +8,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 dev = 'cuda'
 torch.manual_seed(0)
 net = models.ODENet(3, n_filters=256, downsample='residual', tol=1e-3).eval().to(dev)
-for B in (256, 1024, 2048):
+for B in (256, 1024, 2048, 2368):
     x = torch.rand(B, 3, 32, 32, device=dev)
     for mode in ('1', '0'):
         os.environ['NODE_B200_WIDE'] = mode
