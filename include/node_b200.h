@@ -327,6 +327,22 @@ int node_b200_adjoint_step(void* ctl, float* bufs, int64_t row_elems, int cur, c
                            int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums,
                            int* nonfinite_flag, const double* t_out, void* stream);
 
+/* One INTERVAL of odeint_adjoint's backward integration (adjoint.py:77-97: odeint of the augmented system over [t_i, t_{i-1}];
+ * SURVEY 8b `node_dopri5_adjoint_backward`) as ONE call without a host read: f0 (dopri5.py:78), the initial-step probe and
+ * norms (misc.py:84-143) - or the fixed first step when first_step_given != 0, sums[0] holding the constant - and then the loop
+ * `while next_t > t1: step` (dopri5.py:88) as a CUDA graph WHILE node whose condition the device-resident controller sets
+ * (csrc/adjoint_solve.cu). Arguments as node_b200_adjoint_step; the start state is in row 0 of `bufs`, ctl is initialised by
+ * node_b200_ctl_init, t_out = device float64 [n_out] (sign-flipped for reversed spans), out = [n_out][row_elems] floats: out[0] =
+ * the start state, out[j] = the dense output at t_out[j]. The attempt always runs rows (Y0, F0) -> (Y1, F1) and a commit kernel
+ * copies the accepted pair back, so ctl.cur is not used. The loop graphs are cached per argument set (the caller keeps the
+ * buffers alive and at the same addresses to reuse them); adjoint_solve_reset drops them. The caller reads ctl back ONCE,
+ * after the call, for status / counters / trace. */
+int node_b200_adjoint_solve(void* ctl, float* bufs, int64_t row_elems, const int64_t* host_seg_off, const int64_t* host_seg_len,
+                            int n_seg, void* workspace, void* vjp_workspace, float tsign, int64_t ts32_offset_bytes, int N, int C,
+                            int H, int W, double* partials, double* sums, int* nonfinite_flag, const double* t_out, float* out,
+                            int first_step_given, void* stream);
+int node_b200_adjoint_solve_reset(void);
+
 /* Wide dynamics (n_filters = 128, 192, 256: the paper's CIFAR setting, reproduce.sh:21): ODEfunc.forward (model.py:339-348) as
  * 64-channel blocks on the tcgen05 engine instead of cuDNN.
  * conv3x3_forward_strided = conv3x3_forward on a 64-channel block of a wider tensor: x / (addend, out) point at the block's

@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(kThreads) k_stage_combine(const node_ctl_t* __
   using A = Arith<T>;
   constexpr int V = Vec<T>::n;
   constexpr int U = 2;                      // vectors per thread per iteration
+  // the mid-point only feeds the dense output: nothing to do unless the controller scheduled outputs for the accepted step
+  // (callers that decide on the host launch row 6 only then; node_b200_adjoint_solve launches it every attempt)
+  if (ROW == 6 && ctl->out_hi <= ctl->out_lo) return;
   // row 7: probe step h0; row 6 (dense-output mid-point) runs AFTER the controller accepted the step, when
   // ctl->h* already hold the next attempt's size, so it takes the accepted step's h saved in it_h*.
   const T h = ROW == 7 ? (sizeof(T) == 4 ? (T)ctl->h0_32 : (T)ctl->h0)

@@ -42,6 +42,7 @@ EXPORTS = (
     'node_b200_fold_reduce', 'node_b200_adjoint_step', 'node_b200_conv3x3_forward_strided', 'node_b200_groupnorm_relu_ex',
     'node_b200_wide_odefunc', 'node_b200_wide8_workspace_bytes', 'node_b200_wide8_operand_bytes', 'node_b200_wide8_prepare',
     'node_b200_wide8_gn_operand', 'node_b200_wide8_conv', 'node_b200_wide8_watchdog', 'node_b200_wide8_odefunc',
+    'node_b200_adjoint_solve', 'node_b200_adjoint_solve_reset',
 )
 
 _lib = None
@@ -119,6 +120,8 @@ def _declare(lib):
     lib.node_b200_wide8_watchdog.argtypes = [_vp, _i, _vp]
     lib.node_b200_wide8_odefunc.argtypes = [_vp] * 14 + [_f, _i, _i, _vp]
     lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+    lib.node_b200_adjoint_solve.argtypes = [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+    lib.node_b200_adjoint_solve_reset.argtypes = []
 
 
 def lib():

@@ -277,6 +277,8 @@ def odefunc_forward(func, t, y, tsign=1.0, conv_mode=None):
 
 
 _vjp_ws_cache = {}
+_adjoint_bufs = {}              # (device, row length, T) -> state rows / controller / sums of node_b200_adjoint_solve
+_adjoint_solve_failed = False
 N_PARAMS_64 = 2 * (64 * 65 * 9 + 64) + 6 * 64
 
 
@@ -508,13 +510,28 @@ class _GenericSolve(object):
         self.T = len(t_host)
         self.t_host = native.host_f64(t_host)
         L = native.layout()
-        self.bufs = torch.zeros(self.NBUF, self.L, dtype=self.dtype, device=self.device)
-        self.ctl = torch.zeros(L['sizeof'], dtype=torch.uint8, device=self.device)
-        self.partials = torch.zeros(2 * L['max_seg'] * L['partial_blocks'], dtype=torch.float64, device=self.device)
-        self.sums = torch.zeros(2 * L['max_seg'], dtype=torch.float64, device=self.device)
-        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.t_dev = torch.tensor([float(v) for v in t_host], dtype=torch.float64, device=self.device)
-        self.out = torch.empty(self.T, self.L, dtype=self.dtype, device=self.device)
+        # The adjoint of the fused ODE-Net dynamics on one GPU runs as ONE C call per interval (node_b200_adjoint_solve): its
+        # loop graph points at these buffers, so they are kept (and reused) per state shape instead of allocated per solve.
+        self.one_call = (isinstance(func, _FusedAugmented) and dist_state.group() is None and self.code == native.F32
+                         and len(y0) == 4 and len(self.shapes[0]) == 4 and os.environ.get('NODE_B200_ADJOINT_SOLVE', '1') != '0'
+                         and not _adjoint_solve_failed)
+        kept = _adjoint_bufs.get((str(self.device), self.L, self.T)) if self.one_call else None
+        if kept is not None:
+            self.bufs, self.ctl, self.partials, self.sums, self.flag, self.t_dev, self.out = kept
+            self.t_dev.copy_(torch.tensor([float(v) for v in t_host], dtype=torch.float64))
+        else:
+            self.bufs = torch.zeros(self.NBUF, self.L, dtype=self.dtype, device=self.device)
+            self.ctl = torch.zeros(L['sizeof'], dtype=torch.uint8, device=self.device)
+            self.partials = torch.zeros(2 * L['max_seg'] * L['partial_blocks'], dtype=torch.float64, device=self.device)
+            self.sums = torch.zeros(2 * L['max_seg'], dtype=torch.float64, device=self.device)
+            self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.t_dev = torch.tensor([float(v) for v in t_host], dtype=torch.float64, device=self.device)
+            self.out = torch.empty(self.T, self.L, dtype=self.dtype, device=self.device)
+            if self.one_call:
+                if len(_adjoint_bufs) > 4:
+                    _adjoint_bufs.clear()
+                _adjoint_bufs[(str(self.device), self.L, self.T)] = (self.bufs, self.ctl, self.partials, self.sums, self.flag,
+                                                                     self.t_dev, self.out)
         self.seg_off = native.host_i64(self.offs)
         self.seg_len = native.host_i64(self.lens)
         nseg = len(y0)
@@ -523,12 +540,11 @@ class _GenericSolve(object):
         sharded = dist_state.group() is not None
         numel = native.host_i64([dist_state.global_numel(n, self.device) if (sharded and i < self.rep_from) else n
                                  for i, n in enumerate(self.lens)])
-        err = native.lib().node_b200_ctl_init(
-            native.ptr(self.ctl), self.code, nseg, native.host_f64(rt), native.host_f64(at),
-            numel, _dflt(opts.get('safety', 0.9)), _dflt(opts.get('ifactor', 10.0)),
-            _dflt(opts.get('dfactor', 0.2)), _dflt(1 / 5), int(opts.get('max_num_steps', 2 ** 31 - 1)), self.T, 1,
-            native.stream_ptr())
-        native.check(err, 'ctl_init')
+        self.ctl_args = (native.ptr(self.ctl), self.code, nseg, native.host_f64(rt), native.host_f64(at),
+                         numel, _dflt(opts.get('safety', 0.9)), _dflt(opts.get('ifactor', 10.0)),
+                         _dflt(opts.get('dfactor', 0.2)), _dflt(1 / 5), int(opts.get('max_num_steps', 2 ** 31 - 1)), self.T, 1)
+        native.check(native.lib().node_b200_ctl_init(*self.ctl_args, native.stream_ptr()), 'ctl_init')
+        self.y0_kept = y0 if self.one_call else None
         self.first_step = opts.get('first_step')
         key = 'ts32' if self.code == native.F32 else 'ts64'
         isz = 4 if self.code == native.F32 else 8
@@ -571,7 +587,46 @@ class _GenericSolve(object):
                                               native.ptr(self.flag) if mode == 2 else native._vp(0),
                                               native.ptr(self.t_dev), sp), 'controller')
 
+    def _run_one_call(self):
+        """The whole interval by node_b200_adjoint_solve (csrc/adjoint_solve.cu): prologue + device-side while loop, ONE read of
+        the controller block afterwards. Returns None when the loop graph could not be built (the caller takes the step-wise
+        route from scratch)."""
+        global _adjoint_solve_failed
+        lib, sp = native.lib(), native.stream_ptr()
+        N, C, H, W = self.shapes[0]
+        fws = fused_workspace(self.device, N, C, H, W)
+        fws.prepare(recognise_odefunc(self.func.func))
+        vws = _vjp_workspace(self.device, N, C, H, W)
+        given = self.first_step is not None
+        if given:
+            self.sums[0] = _dflt(0.01)                   # dopri5.py:81-82
+        rc = lib.node_b200_adjoint_solve(native.ptr(self.ctl), native.ptr(self.bufs), self.L, self.seg_off, self.seg_len, 4,
+                                         native.ptr(fws.buf), native.ptr(vws), float(self.tsign), native.layout()['ts32'], N, C, H, W,
+                                         native.ptr(self.partials), native.ptr(self.sums), native.ptr(self.flag),
+                                         native.ptr(self.t_dev), native.ptr(self.out), 1 if given else 0, sp)
+        if rc != 0:
+            torch.cuda.synchronize(self.device)
+            _adjoint_solve_failed = True
+            warnings.warn('node_b200_adjoint_solve: no device-side loop graph (CUDA error %d); the adjoint reads the controller '
+                          'back once per attempted step instead' % rc)
+            return None
+        view = native.CtlView(self.ctl)                                       # the one host read of the interval
+        if hasattr(self.func.target, 'nfe'):
+            self.func.target.nfe += view.i32('nfe')                           # model.py:340 counts every evaluation
+        last_stats.clear()
+        last_stats.update(route='generic', nfe=view.i32('nfe'), n_accept=view.i32('n_accept'), n_reject=view.i32('n_reject'),
+                          status=view.i32('status'), trace=view.trace(), adjoint_loop='device')
+        native.raise_for_status(view.i32('status'))
+        return tuple(self.out[:, o:o + n].reshape((self.T,) + s).clone() for o, n, s in zip(self.offs, self.lens, self.shapes))
+
     def run(self):
+        if self.one_call:
+            outs = self._run_one_call()
+            if outs is not None:
+                return outs
+            for b, y in zip(self._views(0), self.y0_kept):                   # start over on the step-wise route
+                b.copy_(y.detach())
+            native.check(native.lib().node_b200_ctl_init(*self.ctl_args, native.stream_ptr()), 'ctl_init')
         lib, sp = native.lib(), native.stream_ptr()
         Y0, Y1, F0, F1, K2, YMID, YI = 0, 1, 2, 3, 4, 9, 10
         nseg = len(self.lens)

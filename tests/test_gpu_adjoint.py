@@ -80,3 +80,65 @@ def test_adjoint_end_to_end(native_lib, golden, name):
         assert res[ref]['y0'] < gate_y and res[ref]['y0_l2'] < max(1e-3, cond_y), (ref, res[ref], gate_y)
         assert res[ref]['params'] < gate_p and res[ref]['params_l2'] < max(1e-3, cond_p), (ref, res[ref], gate_p)
     assert float((gt - rt).abs().max()) < max(gate_y, gate_p) * float(rt.abs().max()) + 1e-6
+
+
+def _adjoint_grads(func, h0, t, tol, grad_out, options=None):
+    from node_b200 import odeint_adjoint, solver
+    h = h0.clone().requires_grad_(True)
+    tt = t.clone().requires_grad_(True)
+    for p in func.parameters():
+        p.grad = None
+    func.nfe = 0
+    out = odeint_adjoint(func, h, tt, rtol=tol, atol=tol, method='dopri5', options=options)
+    nfe_f, func.nfe = func.nfe, 0
+    out.backward(grad_out)
+    st = dict(solver.last_stats)
+    return (out.detach(), h.grad.clone(), tt.grad.clone(), torch.cat([q.grad.reshape(-1) for q in func.parameters()]), nfe_f, func.nfe, st)
+
+
+@pytest.mark.parametrize('hw,n,times,tol,scale,opts', [
+    (8, 4, [0.0, 1.0], 1e-3, 1.0, None), (8, 33, [0.0, 1.0], 1e-4, 3.0, None), (8, 5, [0.0, 0.3, 1.0], 1e-3, 3.0, None),
+    (7, 3, [1.0, 0.0], 1e-3, 3.0, None), (6, 2, [0.0, 1.0], 1e-2, 3.0, dict(first_step=0.2)), (8, 600, [0.0, 1.0], 1e-3, 2.0, None)])
+def test_adjoint_interval_as_one_call(native_lib, monkeypatch, hw, n, times, tol, scale, opts):
+    """node_b200_adjoint_solve (device-side while loop, one controller read per interval) against the step-wise route (one read
+    per attempted step): the same kernels in the same order - gradients, counters and the step trace are bit-identical."""
+    from node_b200 import models
+    torch.manual_seed(hw * 100 + n)
+    func = models.ODEfunc(64).to(DEV)
+    with torch.no_grad():
+        for p in func.parameters():
+            p.mul_(scale)
+    h0 = torch.randn(n, 64, hw, hw, device=DEV)
+    t = torch.tensor(times, device=DEV)
+    go = torch.randn(len(times), n, 64, hw, hw, device=DEV)
+    monkeypatch.setenv('NODE_B200_ADJOINT_SOLVE', '1')
+    a = _adjoint_grads(func, h0, t, tol, go, opts)
+    b = _adjoint_grads(func, h0, t, tol, go, opts)           # the cached loop graph and buffers, second use
+    monkeypatch.setenv('NODE_B200_ADJOINT_SOLVE', '0')
+    c = _adjoint_grads(func, h0, t, tol, go, opts)
+    assert a[6].get('adjoint_loop') == 'device' and c[6].get('adjoint_loop') is None
+    for x in (b, c):
+        for i in range(4):
+            assert torch.equal(a[i], x[i]), (i, float((a[i] - x[i]).abs().max()))
+        assert a[4:6] == x[4:6]
+        assert list(a[6]['trace']['accepted']) == list(x[6]['trace']['accepted']) and list(a[6]['trace']['dt']) == list(x[6]['trace']['dt'])
+        assert (a[6]['n_accept'], a[6]['n_reject'], a[6]['nfe']) == (x[6]['n_accept'], x[6]['n_reject'], x[6]['nfe'])
+
+
+@pytest.mark.parametrize('name', ['adjoint_cifar_n4', 'adjoint_mnist_conv_n3', 'adjoint_cifar_oneshot_n2'])
+def test_adjoint_one_call_rejected_steps(native_lib, golden, monkeypatch, name):
+    """The golden cases reject 1-3 backward steps (commit kernel skipped, y / f kept, stale interpolant never used): the
+    device-looped interval equals the step-wise one bit for bit there too."""
+    g = golden(name)
+    func = load_odefunc(g, DEV).train()
+    h0, t, go = (torch.from_numpy(g[k]).to(DEV) for k in ('h0', 't', 'grad_out'))
+    tol = float(g['tol'])
+    monkeypatch.setenv('NODE_B200_ADJOINT_SOLVE', '1')
+    a = _adjoint_grads(func, h0, t, tol, go)
+    monkeypatch.setenv('NODE_B200_ADJOINT_SOLVE', '0')
+    c = _adjoint_grads(func, h0, t, tol, go)
+    assert a[6].get('adjoint_loop') == 'device' and c[6].get('adjoint_loop') is None
+    assert a[6]['n_reject'] >= 1 and [bool(v) for v in a[6]['trace']['accepted']] == [bool(v) for v in g['btr_acc']]
+    for i in range(4):
+        assert torch.equal(a[i], c[i]), (i, float((a[i] - c[i]).abs().max()))
+    assert a[4:6] == c[4:6] == (int(g['nfe_f']), int(g['nfe_b']))
