@@ -775,9 +775,28 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
     if method != 'dopri5':
         raise NotImplementedError("node_b200 implements method='dopri5' only (got %r)" % method)
     if _needs_grad(func, y0, t):
-        # The reference unrolls autograd through every solver op (train.py without --adjoint, model.py:359). Here the
-        # solver runs in CUDA kernels that record no graph: gradients come from the adjoint ODE instead - the two
-        # agree to the solver tolerance (the reference's own gradient_tests.py:98-116 checks exactly that).
+        # The reference unrolls autograd through every solver op (train.py without --adjoint, model.py:359). The solver kernels
+        # record no graph, so this request is served by node_b200.unrolled: the reference's solver loop recorded by autograd
+        # (controller terms included - the same gradient), every evaluation of the recognised dynamics and its VJP on the native
+        # kernels. NODE_B200_ODEINT_GRAD=adjoint serves it by the adjoint ODE instead (O(1) memory, a different gradient that
+        # agrees to the solver tolerance: gradient_tests.py:98-116).
+        if os.environ.get('NODE_B200_ODEINT_GRAD', 'unrolled') != 'adjoint':
+            for y in y0:
+                if not y.is_cuda:
+                    raise RuntimeError('node_b200 is a CUDA-only implementation of the dopri5 hot path: the state must live '
+                                       'on a B200 (got a %s tensor). There is no CPU fallback.' % y.device)
+            unknown = [k for k in options if k not in ('first_step', 'safety', 'ifactor', 'dfactor', 'max_num_steps')]
+            if unknown:
+                warnings.warn('Dopri5Solver: Unexpected arguments {}'.format({k: options[k] for k in unknown}))
+            from . import unrolled
+            user = func
+            call = (lambda tt, yy: (user(tt, yy[0]),)) if tensor_input else func
+            if tensor_input and isinstance(user, nn.Module):
+                call = _TensorFunc(user)
+            last_stats.clear()
+            with torch.cuda.device(y0[0].device):
+                out = unrolled.solve(call, y0, t, rtol, atol, options, stats=last_stats)
+            return out[0] if tensor_input else out
         if not isinstance(func, nn.Module):
             if not callable(func):
                 raise NotImplementedError('node_b200.odeint: gradients need a callable `func`')

@@ -75,15 +75,19 @@ def test_error_behaviour_matches_reference():
         odeint(f, [y0], t)                                        # misc.py:181
 
 
-def test_no_silent_autograd_through_odeint():
-    """Gradients through `odeint` with a plain callable (api_tests.py:30-38, train.py without --adjoint) are served by the adjoint
-    ODE: the modules the callable closes over are found, so their parameters are differentiated too - never silently dropped.
-    (No GPU here: the request must get as far as the CUDA-only check, not return a graph-less tensor.)"""
+def test_no_silent_autograd_through_odeint(monkeypatch):
+    """Gradients through `odeint` with a plain callable (api_tests.py:30-38, train.py without --adjoint) are never silently
+    dropped: the default serves them by the unrolled route (node_b200.unrolled), NODE_B200_ODEINT_GRAD=adjoint by the adjoint ODE,
+    where the modules the callable closes over are found so that their parameters are differentiated too. (No GPU here: either
+    request must get as far as the CUDA-only check, not return a graph-less tensor or run on the CPU.)"""
     from node_b200 import odeint, solver
     lin = nn.Linear(3, 3)
     f = lambda t, y: lin(y)
     assert solver._closure_modules(f) == [lin]
     assert solver._needs_grad(f, (torch.ones(3),), torch.tensor([0., 1.]))        # lin's parameters require grad
+    with pytest.raises(RuntimeError, match='CUDA-only'):
+        odeint(f, torch.ones(3, requires_grad=True), torch.tensor([0., 1.]))
+    monkeypatch.setenv('NODE_B200_ODEINT_GRAD', 'adjoint')
     with pytest.warns(UserWarning, match='adjoint'), pytest.raises(RuntimeError, match='CUDA-only'):
         odeint(f, torch.ones(3, requires_grad=True), torch.tensor([0., 1.]))
 

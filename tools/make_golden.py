@@ -253,6 +253,79 @@ def generic_cases():
     np.savez_compressed(os.path.join(GOLD, 'generic_f64.npz'), **rec)
 
 
+def unrolled_case(name, N, tol=1e-3, seed=0, in_ch=3, size=32, downsample='residual', times=None):
+    """SURVEY 8f-2: gradients of the reference's NON-adjoint odeint (autograd unrolled through the solver, controller included;
+    model.py:359 with adjoint=False) for the ODE-Net dynamics, in float32 and float64, and the check that node_b200.unrolled's
+    solver loop (plain torch ops around the dynamics) reproduces the reference's unrolled gradient BIT FOR BIT on CPU when it is
+    handed the same eager dynamics."""
+    import copy
+    sys.path.insert(0, os.path.join(ROOT, 'neural-ode-features_b200'))
+    from node_b200 import unrolled
+    torch.manual_seed(seed)
+    net = ref_model.ODENet(in_ch, n_filters=64, downsample=downsample, tol=tol, adjoint=False).train()
+    x = torch.rand(N, in_ch, size, size)
+    func = net.odeblock.odefunc
+    h0 = net.downsample(x).detach().requires_grad_(True)
+    t = (net.odeblock.integration_time if times is None else torch.tensor(times)).clone().requires_grad_(True)
+    func.nfe = 0
+    with RefTrace() as rt:
+        out = ref_tde.odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')
+    nfe = func.nfe
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(seed + 1))
+    out.backward(go)
+    params = list(func.parameters())
+    gp = torch.cat([q.grad.reshape(-1) for q in params])
+    gy, gt = h0.grad.clone(), t.grad.clone()
+    # node_b200.unrolled with the same eager dynamics
+    for q in params:
+        q.grad = None
+    h1 = h0.detach().clone().requires_grad_(True)
+    t1 = t.detach().clone().requires_grad_(True)
+    st = {}
+    mine = unrolled.solve(lambda tt, yy: (func(tt, yy[0]),), (h1,), t1, tol, tol, {}, stats=st)[0]
+    same(mine.detach(), out.detach(), name + ' unrolled forward')
+    mine.backward(go)
+    same(h1.grad, gy, name + ' unrolled grad_y0')
+    same(t1.grad, gt, name + ' unrolled grad_t')
+    same(torch.cat([q.grad.reshape(-1) for q in params]), gp, name + ' unrolled grad_params')
+    assert st['nfe'] == nfe and (st['n_accept'], st['n_reject']) == (sum(s[2] for s in rt.steps), sum(not s[2] for s in rt.steps))
+    # float64 self and the adjoint's gradient for scale
+    f64 = copy.deepcopy(func).double()
+    h64 = h0.detach().double().requires_grad_(True)
+    t64 = t.detach().double().requires_grad_(True)
+    o64 = ref_tde.odeint(f64, h64, t64, rtol=tol, atol=tol, method='dopri5')
+    o64.backward(go.double())
+    gp64 = torch.cat([q.grad.reshape(-1) for q in f64.parameters()])
+    r1 = float((gy.double() - h64.grad).abs().max() / h64.grad.abs().max())
+    r2 = float((gp.double() - gp64).abs().max() / gp64.abs().max())
+    for q in params:
+        q.grad = None
+    h2 = h0.detach().clone().requires_grad_(True)
+    oa = ref_tde.odeint_adjoint(func, h2, t.detach(), rtol=tol, atol=tol, method='dopri5')
+    oa.backward(go)
+    gpa = torch.cat([q.grad.reshape(-1) for q in params])
+    a1 = float((h2.grad - gy).abs().max() / gy.abs().max())
+    a2 = float((gpa - gp).abs().max() / gp.abs().max())
+    p = {k: v.detach() for k, v in odefunc_port.params_from_module(func).items()}
+    ts, dts, acc = trace_arrays(rt.steps)
+    rec = dict(seed=seed, N=N, tol=tol, t=t.detach().numpy(), h0=h0.detach().numpy(), out=out.detach().numpy(), grad_out=go.numpy(),
+               grad_y0=gy.numpy(), grad_params=gp.numpy(), grad_t=gt.numpy(), nfe=nfe, tr_t=ts, tr_dt=dts, tr_acc=acc,
+               grad_y0_f64=h64.grad.float().numpy(), grad_params_f64=gp64.float().numpy(), grad_t_f64=t64.grad.float().numpy(),
+               ref_err_y0=r1, ref_err_params=r2, adjoint_dev_y0=a1, adjoint_dev_params=a2)
+    rec.update({'p.' + k: v.numpy() for k, v in p.items()})
+    np.savez_compressed(os.path.join(GOLD, name + '.npz'), **rec)
+    print('%-28s N=%-3d nfe=%d steps=%d rejects=%d | fp32 vs fp64 self: y %.1e p %.1e | adjoint vs unrolled: y %.1e p %.1e' % (
+        name, N, nfe, len(ts), int((~acc).sum()), r1, r2, a1, a2))
+
+
+def unrolled_cases():
+    unrolled_case('unrolled_cifar_n4', 4)
+    unrolled_case('unrolled_cifar_n3_t3', 3, times=[0.0, 0.4, 1.0], seed=3)
+    unrolled_case('unrolled_cifar_rev_n2', 2, times=[1.0, 0.0], seed=4)
+    unrolled_case('unrolled_mnist_conv_n3', 3, in_ch=1, size=28, downsample='convolution', seed=1)     # 6x6
+    unrolled_case('unrolled_cifar_oneshot_n2', 2, downsample='one-shot', seed=2, tol=1e-2)              # 16x16
+
+
 def adjoint_cases():
     adjoint_case('adjoint_cifar_n4', 4)
     adjoint_case('adjoint_mnist_conv_n3', 3, in_ch=1, size=28, downsample='convolution')     # 6x6
@@ -266,6 +339,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'adjoint':
         adjoint_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'unrolled':
+        unrolled_cases()
+        sys.exit(0)
     mirror_case()
     generic_cases()
     odenet_case('cifar_res_n8', 3, 32, 'residual', 8)
@@ -278,4 +354,5 @@ if __name__ == '__main__':
     odenet_case('cifar_res_n128', 3, 32, 'residual', 128, store_full=False)   # SURVEY appendix B (seeds only)
     odenet_case('mnist_conv_n128', 1, 28, 'convolution', 128, store_full=False)  # BASELINE cfg1 (seeds only)
     adjoint_cases()
+    unrolled_cases()
     print('golden vectors written to', GOLD)
