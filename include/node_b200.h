@@ -357,6 +357,20 @@ int node_b200_groupnorm_relu_ex(const float* x, float* y, const float* gamma, co
                                 const float* add_tmap, const float* t_dev, float tsign, float post, int64_t N, int C, int groups,
                                 int HW, float eps, int relu, void* stream);
 
+/* Backward pieces of the WIDE dynamics' augmented system (adjoint.py:32-55 at n_filters = 128 / 192 / 256; csrc/wide_vjp.cu):
+ * groupnorm_backward_ex: (grad_in, grad_gamma[C], grad_beta[C]) of y = relu?(GroupNorm(x + add_bias[c] + tsign * t * add_tmap[c][pix]))
+ *   for any C / groups with (C / groups) * HW <= 4096; partials = 2 * N * C floats of scratch (per-image dgamma / dbeta, folded in
+ *   a fixed order). The ReLU mask is recomputed from x.
+ * batch_colsum: out[j] = sum_n v[n][j] (float64 accumulation, fixed order) - the bias / time-channel gradients' sum over the batch.
+ * pow2_scale: scale = 2^floor(log2(16384 / max)) from the bit pattern of max |v| (node_b200_absmax): the operand scale
+ *   node_b200_conv_wgrad expects for a non-negative activation. */
+int node_b200_groupnorm_backward_ex(const float* x, const float* grad_out, float* grad_in, const float* gamma, const float* beta,
+                                    const float* add_bias, const float* add_tmap, const float* t_dev, float tsign, float* partials,
+                                    float* grad_gamma, float* grad_beta, int64_t N, int C, int groups, int HW, float eps, int relu,
+                                    void* stream);
+int node_b200_batch_colsum(const float* v, float* out, int64_t N, int64_t cols, void* stream);
+int node_b200_pow2_scale(const unsigned* max_bits, float* scale, void* stream);
+
 /* wide_odefunc: one evaluation out = s * ODEfunc(s * t, y) of a C = 64 * nb model by ONE call (the sequence above); block_ws =
  * [2 convs][nb][nb] conv3x3 workspaces (conv3x3_prepare on W[64co:64co+64, 1+64ci:1+64ci+64]) block_ws_stride bytes apart,
  * bias / tmap = the convolutions' biases [C] and folded time maps [C,H,W], tmp_a / tmp_c = [N,C,H,W] scratch. */
@@ -364,6 +378,11 @@ int node_b200_wide_odefunc(void* block_ws, int64_t block_ws_stride, const float*
                            const float* g1w, const float* g1b, const float* g2w, const float* g2b, const float* g3w, const float* g3b,
                            const float* bias1, const float* tmap1, const float* bias2, const float* tmap2, const float* t_dev,
                            float tsign, int N, int C, int H, int W, void* stream);
+
+/* wide_conv_blocks: out[:, 64o:64o+64] = sum_i conv3x3(x[:, 64i:64i+64], block (o, i)) - the nb^2 block launches of ONE wide
+ * convolution by one call; block_ws = its nb x nb prepared workspaces (conv3x3_prepare), block_ws_stride bytes apart. */
+int node_b200_wide_conv_blocks(void* block_ws, int64_t block_ws_stride, const float* x, float* out, int N, int C, int H, int W,
+                               void* stream);
 
 /* wide8: the wide dynamics on 8x8 maps (C = 128 / 256) as ONE TMA-fed tcgen05 implicit GEMM over all channels per convolution
  * (csrc/wide8_engine.cu) instead of (C/64)^2 block launches. ODEfunc.forward (model.py:339-348) =

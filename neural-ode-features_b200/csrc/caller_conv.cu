@@ -244,3 +244,21 @@ extern "C" int node_b200_wide_odefunc(void* block_ws, int64_t block_ws_stride, c
   NODE_CUDA_OK((cudaError_t)convs(1, tmp_a, tmp_c));
   return node_b200_groupnorm_relu_ex(tmp_c, out, g3w, g3b, bias2, tmap2, t_dev, tsign, tsign < 0 ? -1.0f : 1.0f, N, C, 32, HW, 1e-5f, 0, stream);
 }
+
+// out[:, 64o:64o+64] = sum_i conv3x3(x[:, 64i:64i+64], block (o, i)) for a [N, C, H, W] tensor, C = 64 * nb: one call for the
+// nb^2 launches of one wide convolution; block_ws points at the nb x nb prepared workspaces of this convolution (forward weights,
+// or the transposed / flipped ones of the data gradient, node_b200/wide.py).
+extern "C" int node_b200_wide_conv_blocks(void* block_ws, int64_t block_ws_stride, const float* x, float* out, int N, int C, int H, int W,
+                                          void* stream) {
+  if (C % kC != 0 || C <= kC || N < 1) return (int)cudaErrorInvalidValue;
+  const int nb = C / kC, HW = H * W;
+  const int64_t stride = (int64_t)C * HW;
+  for (int o = 0; o < nb; ++o)
+    for (int i = 0; i < nb; ++i) {
+      char* ws = (char*)block_ws + ((int64_t)o * nb + i) * block_ws_stride;
+      float* dst = out + (int64_t)o * kC * HW;
+      const int rc = node_b200_conv3x3_forward_strided(ws, x + (int64_t)i * kC * HW, i ? dst : nullptr, dst, N, kC, H, W, stride, stride, stream);
+      if (rc != 0) return rc;
+    }
+  return 0;
+}

@@ -42,7 +42,8 @@ EXPORTS = (
     'node_b200_fold_reduce', 'node_b200_adjoint_step', 'node_b200_conv3x3_forward_strided', 'node_b200_groupnorm_relu_ex',
     'node_b200_wide_odefunc', 'node_b200_wide8_workspace_bytes', 'node_b200_wide8_operand_bytes', 'node_b200_wide8_prepare',
     'node_b200_wide8_gn_operand', 'node_b200_wide8_conv', 'node_b200_wide8_watchdog', 'node_b200_wide8_odefunc',
-    'node_b200_adjoint_solve', 'node_b200_adjoint_solve_reset',
+    'node_b200_adjoint_solve', 'node_b200_adjoint_solve_reset', 'node_b200_groupnorm_backward_ex', 'node_b200_batch_colsum',
+    'node_b200_pow2_scale', 'node_b200_wide_conv_blocks',
 )
 
 _lib = None
@@ -122,6 +123,10 @@ def _declare(lib):
     lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
     lib.node_b200_adjoint_solve.argtypes = [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
     lib.node_b200_adjoint_solve_reset.argtypes = []
+    lib.node_b200_groupnorm_backward_ex.argtypes = [_vp] * 8 + [_f, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp]
+    lib.node_b200_batch_colsum.argtypes = [_vp, _vp, _i64, _i64, _vp]
+    lib.node_b200_pow2_scale.argtypes = [_vp, _vp, _vp]
+    lib.node_b200_wide_conv_blocks.argtypes = [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]
 
 
 def lib():

@@ -859,8 +859,14 @@ class _AdjointFn(torch.autograd.Function):
         native_vjp = (n == 1 and os.environ.get('NODE_B200_NATIVE_VJP', '1') != '0' and recognise_odefunc(func) is not None
                       and _fusable_state(recognise_odefunc(func), (ans[0][0],))
                       and native.lib().node_b200_vjp_workspace_bytes(*[int(v) for v in ans[0].shape[1:]]) > 0)
+        from . import wide
+        wide_vjp = (not native_vjp and n == 1 and os.environ.get('NODE_B200_NATIVE_VJP', '1') != '0'
+                    and os.environ.get('NODE_B200_WIDE', '1') != '0' and os.environ.get('NODE_B200_FUSED', '1') != '0'
+                    and wide.serves(_unwrap(func), (ans[0][0],)))
         if native_vjp:
             augmented = _FusedAugmented(func)
+        elif wide_vjp:
+            augmented = wide.WideAugmented(func)    # n_filters = 128 / 192 / 256 (reproduce.sh:21-25 trains these with --adjoint)
         else:
             augmented.replicated_from = 2 * n       # adj_t, adj_params: sums over the (possibly sharded) batch
         with torch.no_grad():
@@ -874,6 +880,8 @@ class _AdjointFn(torch.autograd.Function):
                 if native_vjp:
                     func_i = (odefunc_forward(func, float(t_host[i]), ans_i[0].contiguous()),)
                     _unwrap(func).nfe += 1
+                elif wide_vjp:
+                    func_i = (augmented.dyn(float(t_host[i]), ans_i[0].contiguous()),)      # counts itself
                 else:
                     func_i = func(ti, ans_i)
                 d = sum(torch.dot(f.reshape(-1), g[i].reshape(-1)).view(1) for f, g in zip(func_i, grad_output))
@@ -892,7 +900,7 @@ class _AdjointFn(torch.autograd.Function):
                 adj_y = tuple(a + g[i - 1] for a, g in zip(adj_y, grad_output))
             tv.append(adj_t.reshape(1))
             time_vjps = torch.cat(tv[::-1]).to(t.dtype)
-        last_stats['adjoint_vjp'] = 'native' if native_vjp else 'autograd'
+        last_stats['adjoint_vjp'] = 'native' if native_vjp else ('native-wide' if wide_vjp else 'autograd')
         return (None, time_vjps, None, None, None, None, adj_p) + tuple(adj_y)
 
 

@@ -32,6 +32,22 @@ from . import native
 _SERVED_HW = ((8, 8), (7, 7), (15, 15), (13, 13))
 
 
+class WideAugmented(object):
+    """The adjoint's augmented dynamics (adjoint.py:32-55) of a wide ODEfunc for the generic route (solver._GenericSolve): state
+    (y, adj_y, adj_t, adj_params) -> (f, vjp_y, vjp_t, vjp_params), every convolution / GroupNorm (forward and backward) on this
+    repo's kernels - no autograd graph, no cuDNN."""
+
+    replicated_from = 2              # adj_t, adj_params are sums over the (possibly sharded) batch
+
+    def __init__(self, func):
+        self.func = func
+        self.target = func.base if hasattr(func, 'base') else func
+        self.dyn = WideDynamics.of(self.target)
+
+    def eval_into(self, t_dev, src, dst, tsign):
+        self.dyn.vjp_into(t_dev, src[0], src[1], dst, tsign)
+
+
 def recognise(func):
     """The reference's ODEfunc (model.py:326-348) with C = 128, 192, 256, ... fp32 CUDA parameters; returns C or None."""
     if not isinstance(func, nn.Module) or (type(func).__name__ != 'ODEfunc' and not getattr(func, '_node_b200_fusable', False)):
@@ -165,6 +181,137 @@ class WideDynamics(object):
             native.ptr(f.norm1.weight), native.ptr(f.norm1.bias), native.ptr(f.norm2.weight), native.ptr(f.norm2.bias),
             native.ptr(f.norm3.weight), native.ptr(f.norm3.bias), native.ptr(f.conv1._layer.bias), native.ptr(self._tmap[0]),
             native.ptr(f.conv2._layer.bias), native.ptr(self._tmap[1]), native.ptr(t32), float(tsign), N, C, H, W, sp()), 'wide_odefunc')
+        if hasattr(f, 'nfe'):
+            f.nfe += 1                                       # model.py:340 counts every evaluation
+
+    # ---- the adjoint's augmented dynamics (adjoint.py:32-55) -------------------------------------------------------------
+    def _prepare_vjp(self, H, W):
+        """Per parameter version: the data-gradient weight blocks (conv3x3 with W^T and flipped taps), validity matrix of the
+        folded time channel."""
+        self._prepare(H, W)
+        convs = [self.func.conv1._layer, self.func.conv2._layer]
+        key = (H, W) + tuple((c.weight.data_ptr(), c.weight._version) for c in convs)
+        if getattr(self, '_key_vjp', None) == key:
+            return
+        lib = native.lib()
+        dev = convs[0].weight.device
+        nbytes = lib.node_b200_resconv_workspace_bytes(64, H, W)
+        if not hasattr(self, '_wsd') or self._wsd.shape[-1] != nbytes or self._wsd.device != dev:
+            self._wsd = torch.zeros((2, self.nb, self.nb, nbytes), dtype=torch.uint8, device=dev)
+        for li, c in enumerate(convs):
+            wd = c.weight.detach()[:, 1:].flip(2, 3).transpose(0, 1)      # [ci, co, 3, 3]: dL/dx = conv3x3(dL/dc, wd)
+            for o in range(self.nb):
+                for i in range(self.nb):
+                    blk = wd[64 * o:64 * o + 64, 64 * i:64 * i + 64].contiguous()
+                    native.check(lib.node_b200_conv3x3_prepare(native.ptr(self._wsd[li, o, i]), 64, H, W, native.ptr(blk),
+                                                               native.stream_ptr()), 'conv3x3_prepare')
+        ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing='ij')
+        V = torch.zeros(H * W, 9, device=dev)
+        for ky in range(3):
+            for kx in range(3):
+                ok = (ys + ky - 1 >= 0) & (ys + ky - 1 < H) & (xs + kx - 1 >= 0) & (xs + kx - 1 < W)
+                V[:, ky * 3 + kx] = ok.reshape(-1).float()
+        self._valid = V                                                    # Tmap[c] = W[c, 0].view(9) @ V^T
+        self._key_vjp = key
+
+    def _conv(self, ws, x, out):
+        N, C, H, W = (int(v) for v in x.shape)
+        native.check(native.lib().node_b200_wide_conv_blocks(native.ptr(ws), int(ws.shape[-1]), native.ptr(x), native.ptr(out), N, C, H, W,
+                                                             native.stream_ptr()), 'wide_conv_blocks')
+
+    def _gn(self, x, out, norm, bias, tmap, t32, tsign, post, relu):
+        N, C, H, W = (int(v) for v in x.shape)
+        native.check(native.lib().node_b200_groupnorm_relu_ex(
+            native.ptr(x), native.ptr(out), native.ptr(norm.weight), native.ptr(norm.bias), native.ptr(bias), native.ptr(tmap),
+            native.ptr(t32), float(tsign), float(post), N, C, 32, H * W, 1e-5, relu, native.stream_ptr()), 'groupnorm_relu_ex')
+
+    def _gn_bwd(self, x, g, gx, norm, bias, tmap, t32, tsign, relu, dgamma, dbeta):
+        N, C, H, W = (int(v) for v in x.shape)
+        native.check(native.lib().node_b200_groupnorm_backward_ex(
+            native.ptr(x), native.ptr(g), native.ptr(gx), native.ptr(norm.weight), native.ptr(norm.bias), native.ptr(bias), native.ptr(tmap),
+            native.ptr(t32), float(tsign), native.ptr(self._v['part']), native.ptr(dgamma), native.ptr(dbeta), N, C, 32, H * W, 1e-5,
+            relu, native.stream_ptr()), 'groupnorm_backward_ex')
+
+    def _blocks(self, x, out):
+        """[N, C, H, W] -> [nb, N, 64, H, W] contiguous 64-channel blocks (the weight-gradient GEMM reads dense blocks)."""
+        N, C, H, W = x.shape
+        out.copy_(x.view(N, self.nb, 64, H, W).transpose(0, 1))
+        return out
+
+    def _conv_param_grads(self, li, act, gc, t32, tsign, w_out, b_out):
+        """dL/dW [C, C+1, 3, 3] and dL/db [C] of ConcatConv2d `li` from its input activation and the gradient at its output;
+        returns this convolution's share of dL/dt (device scalar)."""
+        from . import caller_grad
+        lib, v = native.lib(), self._v
+        N, C, H, W = (int(x) for x in act.shape)
+        nb = self.nb
+        ab, gb = self._blocks(act, v['ab']), self._blocks(gc, v['gb'])
+        native.check(lib.node_b200_absmax(native.ptr(act), act.numel(), native.ptr(v['bits']), native.stream_ptr()), 'absmax')
+        native.check(lib.node_b200_pow2_scale(native.ptr(v['bits']), native.ptr(v['scale']), native.stream_ptr()), 'pow2_scale')
+        sp = native._vp(v['scale'].data_ptr())
+        pairs = [(o, i) for o in range(nb) for i in range(nb)]
+        dws = []
+        for k in range(0, len(pairs), 6):                                  # node_b200_conv_wgrad serves up to 6 pairs per launch
+            chunk = pairs[k:k + 6]
+            dws.append(caller_grad.conv_wgrad([ab[i] for _, i in chunk], [gb[o] for o, _ in chunk], [sp] * len(chunk)))
+        dw = torch.cat(dws).view(nb, nb, 64, 64, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(C, C, 3, 3)
+        w_out[:, 1:].copy_(dw)
+        # bias and the folded time channel (model.py:320-323): S[c, pix] = sum_n gc[n, c, pix]
+        S = v['S']
+        native.check(lib.node_b200_batch_colsum(native.ptr(gc), native.ptr(S), N, C * H * W, native.stream_ptr()), 'batch_colsum')
+        S2 = S.view(C, H * W)
+        b_out.copy_(S2.sum(1))
+        tt = t32 * tsign
+        w_out[:, 0].copy_((tt * (S2 @ self._valid)).view(C, 3, 3))
+        return (S2 * self._tmap[li].view(C, H * W)).sum()
+
+    def vjp_into(self, t_dev, y, adj_y, dst, tsign):
+        """dst = tsign * (f, vjp_y, vjp_t, vjp_params)(tsign * t) of ODEfunc with cotangent -adj_y (adjoint.py:40-49; a reversed span
+        negates the whole augmented system and its time argument, misc.py:184-187), parameters in `func.parameters()` order
+        (misc.py:5-7)."""
+        f, lib = self.func, native.lib()
+        N, C, H, W = (int(v) for v in y.shape)
+        self._prepare_vjp(H, W)
+        v = getattr(self, '_v', None)
+        if v is None or v['a1'].shape != y.shape or v['a1'].device != y.device:
+            e = lambda: torch.empty_like(y)
+            v = self._v = dict(a1=e(), c1=e(), a2=e(), c2=e(), g0=e(), gc2=e(), gr=e(), gc1=e(),
+                               ab=torch.empty((self.nb, N, 64, H, W), device=y.device), gb=torch.empty((self.nb, N, 64, H, W), device=y.device),
+                               part=torch.empty(2 * N * C, device=y.device), S=torch.empty(C * H * W, device=y.device),
+                               bits=torch.zeros(1, dtype=torch.int32, device=y.device), scale=torch.ones(1, device=y.device))
+        t32 = t_dev if t_dev.dtype == torch.float32 else t_dev.float()
+        n1, n2, n3, cv1, cv2 = f.norm1, f.norm2, f.norm3, f.conv1._layer, f.conv2._layer
+        # forward, keeping the activations
+        self._gn(y, v['a1'], n1, None, None, t32, tsign, 1.0, 1)
+        self._conv(self._ws[0], v['a1'], v['c1'])
+        self._gn(v['c1'], v['a2'], n2, cv1.bias, self._tmap[0], t32, tsign, 1.0, 1)
+        self._conv(self._ws[1], v['a2'], v['c2'])
+        self._gn(v['c2'], dst[0], n3, cv2.bias, self._tmap[1], t32, tsign, -1.0 if tsign < 0 else 1.0, 0)
+        # backward with cotangent -tsign * adj_y on ODEfunc's output
+        P = dst[3]
+        o = [0]
+
+        def take(shape):
+            n = 1
+            for s in shape:
+                n *= s
+            view = P[o[0]:o[0] + n].view(shape)
+            o[0] += n
+            return view
+        g1w, g1b = take((C,)), take((C,))
+        w1, b1 = take((C, C + 1, 3, 3)), take((C,))
+        g2w, g2b = take((C,)), take((C,))
+        w2, b2 = take((C, C + 1, 3, 3)), take((C,))
+        g3w, g3b = take((C,)), take((C,))
+        torch.mul(adj_y, -1.0 if tsign > 0 else 1.0, out=v['g0'])
+        self._gn_bwd(v['c2'], v['g0'], v['gc2'], n3, cv2.bias, self._tmap[1], t32, tsign, 0, g3w, g3b)
+        vt = self._conv_param_grads(1, v['a2'], v['gc2'], t32, tsign, w2, b2)
+        self._conv(self._wsd[1], v['gc2'], v['gr'])
+        self._gn_bwd(v['c1'], v['gr'], v['gc1'], n2, cv1.bias, self._tmap[0], t32, tsign, 1, g2w, g2b)
+        vt = vt + self._conv_param_grads(0, v['a1'], v['gc1'], t32, tsign, w1, b1)
+        self._conv(self._wsd[0], v['gc1'], v['gr'])
+        self._gn_bwd(y, v['gr'], dst[1], n1, None, None, t32, tsign, 1, g1w, g1b)
+        dst[2].copy_(vt)            # cotangent already carries tsign: the reversed solve negates the whole augmented system (misc.py:186)
         if hasattr(f, 'nfe'):
             f.nfe += 1                                       # model.py:340 counts every evaluation
 

@@ -43,6 +43,6 @@ def load_odefunc(g, device):
     """A node_b200.models.ODEfunc carrying the golden file's weights."""
     import torch
     from node_b200 import models
-    f = models.ODEfunc(64)
+    f = models.ODEfunc(int(g['p.norm1.weight'].shape[0]))
     f.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith('p.')})
     return f.to(device).eval()

@@ -111,9 +111,9 @@ def mirror_case():
     print('models mirror: state_dict keys and seeded initial weights identical for 6 downsamplers')
 
 
-def adjoint_case(name, N, tol=1e-3, seed=0, in_ch=3, size=32, downsample='residual'):
+def adjoint_case(name, N, tol=1e-3, seed=0, in_ch=3, size=32, downsample='residual', n_filters=64):
     torch.manual_seed(seed)
-    net = ref_model.ODENet(in_ch, n_filters=64, downsample=downsample, tol=tol, adjoint=True).train()
+    net = ref_model.ODENet(in_ch, n_filters=n_filters, downsample=downsample, tol=tol, adjoint=True).train()
     x = torch.rand(N, in_ch, size, size)
     y = torch.randint(0, 10, (N,))
     func = net.odeblock.odefunc
@@ -202,6 +202,8 @@ def adjoint_case(name, N, tol=1e-3, seed=0, in_ch=3, size=32, downsample='residu
                btr_ratio=np.array([max(s[3]) for s in tr.steps]), hand_vjp_same_sequence=same_seq,
                sens_y0=sens_y, sens_params=sens_p, hand_vjp_dev_y0=e1, hand_vjp_dev_params=e2)
     rec.update({'p.' + k: v.numpy() for k, v in p.items()})
+    if n_filters > 64:                       # the wide fixtures keep the scalars (ref_err_*), not the float64 gradient arrays
+        rec.pop('grad_y0_f64'), rec.pop('grad_params_f64')
     np.savez_compressed(os.path.join(GOLD, name + '.npz'), **rec)
     print('%-28s N=%-4d nfe_f=%d nfe_b=%d bwd steps=%d rejects=%d  hand-VJP rel err y %.1e p %.1e' % (
         name, N, nfe_f, nfe_b, len(ts), int((~acc).sum()), e1, e2))
@@ -339,6 +341,10 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'adjoint':
         adjoint_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'wide':
+        adjoint_case('adjoint_cifar_c128_n2', 2, n_filters=128, seed=7)       # wide dynamics (reproduce.sh:21-25 trains 256 filters with --adjoint)
+        adjoint_case('adjoint_cifar_c256_n2', 2, n_filters=256, seed=8)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'unrolled':
         unrolled_cases()
         sys.exit(0)
@@ -354,5 +360,7 @@ if __name__ == '__main__':
     odenet_case('cifar_res_n128', 3, 32, 'residual', 128, store_full=False)   # SURVEY appendix B (seeds only)
     odenet_case('mnist_conv_n128', 1, 28, 'convolution', 128, store_full=False)  # BASELINE cfg1 (seeds only)
     adjoint_cases()
+    adjoint_case('adjoint_cifar_c128_n2', 2, n_filters=128, seed=7)
+    adjoint_case('adjoint_cifar_c256_n2', 2, n_filters=256, seed=8)
     unrolled_cases()
     print('golden vectors written to', GOLD)
