@@ -371,6 +371,17 @@ int node_b200_groupnorm_backward_ex(const float* x, const float* grad_out, float
 int node_b200_batch_colsum(const float* v, float* out, int64_t N, int64_t cols, void* stream);
 int node_b200_pow2_scale(const unsigned* max_bits, float* scale, void* stream);
 
+/* wide_vjp: ONE evaluation of the adjoint's augmented dynamics (adjoint.py:32-55) of a wide ODEfunc by one call - forward keeping the
+ * activations, GroupNorm backward x 3, data gradients (wide8 implicit GEMM on a raw operand image at 8x8 / C = 128, 256; block
+ * convolutions otherwise), weight gradients (64-channel block GEMMs), bias / time-channel gradients, vjp_t. p = host array of 38
+ * device pointers, dims = host array {N, C, H, W, block workspace stride, use_wide8}: indices documented in csrc/wide_vjp.cu.
+ * Outputs are tsign * (f, vjp_y, vjp_t, vjp_params)(tsign * t) with cotangent -adj_y (misc.py:184-187 for reversed spans).
+ * wide8_raw_operand: operand image of a SIGNED fp32 tensor at a scale found from max|x| (max_bits from node_b200_absmax); the
+ * following node_b200_wide8_conv(workspace, which, ...) uses it. */
+int node_b200_wide_vjp(void* const* host_ptrs, const int64_t* host_dims, float tsign, void* stream);
+int node_b200_wide8_raw_operand(void* workspace, int which, const float* x, void* operand, const unsigned* max_bits, int N, int C,
+                                void* stream);
+
 /* wide_odefunc: one evaluation out = s * ODEfunc(s * t, y) of a C = 64 * nb model by ONE call (the sequence above); block_ws =
  * [2 convs][nb][nb] conv3x3 workspaces (conv3x3_prepare on W[64co:64co+64, 1+64ci:1+64ci+64]) block_ws_stride bytes apart,
  * bias / tmap = the convolutions' biases [C] and folded time maps [C,H,W], tmp_a / tmp_c = [N,C,H,W] scratch. */

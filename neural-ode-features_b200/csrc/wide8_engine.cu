@@ -21,6 +21,7 @@
 // A super-tile (4 images) is 9 * C / 32 weight tiles = 864 MMAs at C = 256 (110k clocks at the f16 rate); persistent CTAs, one
 // per SM, take super-tiles round-robin.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "node_common.cuh"
 #include "ptx.cuh"
 
@@ -300,6 +301,47 @@ __global__ void __launch_bounds__(128) k_wide_gn_op(const float* __restrict__ x,
   }
 }
 
+// ---- raw operand (data gradients of the adjoint: a SIGNED fp32 tensor, no GroupNorm) ------------------------------------------
+// scal[3 * which] = sa = 2^floor(log2(16384 / max|x|)), scal[3 * which + 2] = 1 / (sa * sw): the operand scale is found from the
+// tensor itself (gradients have no a-priori bound), the weight scale sw stays the prepared one.
+__global__ void k_wide_dyn_scale(Ws w, int which, const unsigned* __restrict__ max_bits) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float m = __uint_as_float(*max_bits);
+  int e = m > 0.f ? (int)floorf(log2f(16384.0f / m)) : 0;
+  e = max(-40, min(40, e));
+  const float sa = exp2f((float)e);
+  w.scal[3 * which] = sa;
+  w.scal[3 * which + 2] = 1.0f / (sa * w.scal[3 * which + 1]);
+}
+
+// Same mapping as k_wide_gn_op: thread = (pixel, half of the stage's 32 channels) writes two complete hi / lo operand entries.
+__global__ void __launch_bounds__(128) k_wide_raw_op(const float* __restrict__ x, uint8_t* __restrict__ a16, const float* __restrict__ scale, int C) {
+  const int tid = threadIdx.x;
+  const int S = C >> 5;
+  const int img = blockIdx.x / S, stg = blockIdx.x % S;
+  const int px = tid & 63, h = tid >> 6, ch0 = 32 * stg + 16 * h;
+  const float* xp = x + ((size_t)img * C + ch0) * 64 + px;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __ldg(xp + i * 64);
+  const float sa = __ldg(scale);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float r0 = v[8 * k + 2 * e] * sa, r1 = v[8 * k + 2 * e + 1] * sa;
+      const __half2 hh = __floats2half2_rn(r0, r1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(r0 - hf.x, r1 - hf.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(a16 + operand_entry(img, S, 4 * stg + 2 * h + k, 0, px)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a16 + operand_entry(img, S, 4 * stg + 2 * h + k, 1, px)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ---- the convolution ----------------------------------------------------------------------------------------------------------
 struct ConvArgs {
   const uint8_t* a16;       // operand image [super-tile][stage][kStageB]
@@ -310,11 +352,17 @@ struct ConvArgs {
   int N;
 };
 
-template <int C>
+// CN = output channels (accumulator columns) per work unit: CN == C is the large-batch configuration (a weight tile is one bulk
+// copy, read once per 4 images); CN < C splits the output channels of a super-tile over C / CN CTAs so that a small batch (the
+// reference's 128: 32 super-tiles) still fills the 148 SMs - a unit's weight tile is then the CN rows of each of the 8 (part,
+// chunk) slabs (8 bulk copies into a dense [part][chunk][CN rows] image, LBO = 16 * CN).
+template <int C, int CN>
 __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
   constexpr int S = C / 32;
-  constexpr uint32_t kBTile = btile_bytes(C);
-  constexpr uint32_t kCols = 2 * C;               // two M tiles of C accumulator columns
+  constexpr int NSPLIT = C / CN;
+  constexpr uint32_t kBTile = btile_bytes(CN);
+  constexpr uint32_t kBTileFull = btile_bytes(C);
+  constexpr uint32_t kCols = 2 * CN;              // two M tiles of CN accumulator columns
   extern __shared__ uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t s0 = ptx::smem_u32(smem_raw);
@@ -335,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int NST = (a.N + kImgs - 1) / kImgs;
+  const int NU = NST * NSPLIT;                    // work units: (super-tile, output-channel split)
   bool timeout = false;
 
   if (warp == 0) {
@@ -342,7 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
     const bool lead = ptx::elect_one();
     uint32_t ai = 0, bi = 0;
 #pragma unroll 1
-    for (int st = blockIdx.x; st < NST; st += gridDim.x) {
+    for (int u = blockIdx.x; u < NU; u += gridDim.x) {
+      const int st = u / NSPLIT, co0 = (u % NSPLIT) * CN;
 #pragma unroll 1
       for (int s = 0; s < S; ++s, ++ai) {
         const uint32_t as = ai % kARing;
@@ -357,7 +407,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
           if (bi >= (uint32_t)kBRing && !timeout && !ptx::mbar_wait(bar_bfree + 8 * bs, ((bi / kBRing) - 1) & 1)) timeout = true;
           if (lead) {
             ptx::mbar_expect_tx(bar_bfull + 8 * bs, kBTile);
-            ptx::bulk_g2s(bring + bs * kBTile, a.w16 + ((size_t)s * 9 + tap) * kBTile, kBTile, bar_bfull + 8 * bs);
+            const uint8_t* src = a.w16 + ((size_t)s * 9 + tap) * kBTileFull;
+            if (NSPLIT == 1) {
+              ptx::bulk_g2s(bring + bs * kBTile, src, kBTile, bar_bfull + 8 * bs);
+            } else {
+#pragma unroll
+              for (int slab = 0; slab < 8; ++slab)        // (part, chunk) slabs of C rows x 16 B: rows co0 .. co0 + CN
+                ptx::bulk_g2s(bring + bs * kBTile + slab * (CN * 16), src + ((size_t)slab * C + co0) * 16, CN * 16, bar_bfull + 8 * bs);
+            }
           }
         }
       }
@@ -368,11 +425,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
     const bool lead = ptx::elect_one();
     constexpr uint32_t a_hiw = ((uint32_t)kSlotB >> 4) | (1u << 14);              // SBO = 144 B, descriptor version 1
     constexpr uint32_t b_hiw = (128u >> 4) | (1u << 14);                          // SBO = 128 B
-    constexpr uint32_t kId = idesc(C);
+    constexpr uint32_t kId = idesc(CN);
     auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
     uint32_t ai = 0, bi = 0, nacc = 0;
 #pragma unroll 1
-    for (int st = blockIdx.x; st < NST; st += gridDim.x, ++nacc) {
+    for (int u = blockIdx.x; u < NU; u += gridDim.x, ++nacc) {
       if (nacc > 0 && !timeout && !ptx::mbar_wait(bar_accfree, (nacc - 1) & 1)) timeout = true;
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -388,17 +445,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
           ptx::tc_fence_after();
           const int off = (tap / 3 - 1) * 2 * kSlotB + (tap % 3 - 1) * 16;
           const uint32_t a_tap = a_lo0 + (uint32_t)(off >> 4);                      // arithmetic shift: never borrows into the LBO field
-          const uint32_t b_lo0 = (((bring + bs * kBTile) & 0x3FFFFu) >> 4) | (((16u * C) >> 4) << 16);
+          const uint32_t b_lo0 = (((bring + bs * kBTile) & 0x3FFFFu) >> 4) | (((16u * CN) >> 4) << 16);
           if (lead) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-              const uint32_t d = tmem + (uint32_t)(mt * C);
+              const uint32_t d = tmem + (uint32_t)(mt * CN);
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t a_w = a_tap + (uint32_t)((mt * 18 * kSlotB + 2 * ks * kLBO) >> 4);
-                const uint32_t b_w = b_lo0 + (uint32_t)((2 * ks * 16 * C) >> 4);
+                const uint32_t b_w = b_lo0 + (uint32_t)((2 * ks * 16 * CN) >> 4);
                 const uint64_t a_hi = pack(a_w, a_hiw), a_lo = pack(a_w + (uint32_t)(kPartB >> 4), a_hiw);
-                const uint64_t b_hi = pack(b_w, b_hiw), b_lo = pack(b_w + (uint32_t)((4 * 16 * C) >> 4), b_hiw);
+                const uint64_t b_hi = pack(b_w, b_hiw), b_lo = pack(b_w + (uint32_t)((4 * 16 * CN) >> 4), b_hiw);
                 ptx::mma_f16_ss(d, a_hi, b_hi, kId, (s == 0 && tap == 0 && ks == 0) ? 0u : 1u);
                 ptx::mma_f16_ss(d, a_lo, b_hi, kId, 1u);
                 ptx::mma_f16_ss(d, a_hi, b_lo, kId, 1u);
@@ -422,15 +479,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
     const float inv = __ldg(a.inv);
     uint32_t nacc = 0;
 #pragma unroll 1
-    for (int st = blockIdx.x; st < NST; st += gridDim.x, ++nacc) {
+    for (int u = blockIdx.x; u < NU; u += gridDim.x, ++nacc) {
+      const int st = u / NSPLIT, co0 = (u % NSPLIT) * CN;
       if (!timeout && !ptx::mbar_wait_relaxed(bar_accfull, nacc & 1)) timeout = true;
       ptx::tc_fence_after();
       const int img = st * kImgs + mt * 2 + (g & 1);
       const bool valid = img < a.N;
-      float* o = a.out + ((size_t)(valid ? img : 0) * C) * 64 + pix;
-      const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(mt * C);
+      float* o = a.out + ((size_t)(valid ? img : 0) * C + co0) * 64 + pix;
+      const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(mt * CN);
 #pragma unroll 1
-      for (int b = 0; b < C / 32; ++b) {
+      for (int b = 0; b < CN / 32; ++b) {
         uint32_t v[32];
         ptx::tmem_ld32(t0 + 32u * b, v);
         ptx::tc_wait_ld();
@@ -450,15 +508,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_wide_conv(const ConvArgs a) {
   if (warp == 0) ptx::tmem_dealloc(tmem, kCols);
 }
 
+template <int C, int CN>
+static int launch_conv_split(const ConvArgs& a, cudaStream_t st) {
+  constexpr size_t smem = conv_smem(CN);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  NODE_SET_SMEM_ONCE((k_wide_conv<C, CN>), smem);
+  const int NU = ((a.N + kImgs - 1) / kImgs) * (C / CN);
+  const int grid = NU < 148 ? NU : 148;
+  k_wide_conv<C, CN><<<grid, kThreads, smem, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+// small batches: split the output channels until the units fill the SMs (NODE_B200_WIDE8_CN = 0 / 64 / 128 overrides)
 template <int C>
 static int launch_conv(const ConvArgs& a, cudaStream_t st) {
-  constexpr size_t smem = conv_smem(C);
-  static_assert(smem <= 227 * 1024, "shared memory budget");
-  NODE_SET_SMEM_ONCE((k_wide_conv<C>), smem);
   const int NST = (a.N + kImgs - 1) / kImgs;
-  const int grid = NST < 148 ? NST : 148;
-  k_wide_conv<C><<<grid, kThreads, smem, st>>>(a);
-  return (int)cudaGetLastError();
+  int cn = C;
+  if (NST * 2 <= 148) cn = C / 2;
+  if (NST * 4 <= 148 + 20 && C >= 256) cn = C / 4;
+  const char* e = getenv("NODE_B200_WIDE8_CN");
+  if (e != nullptr && atoi(e) > 0) cn = atoi(e);
+  if (cn == 64 && C >= 128) return launch_conv_split<C, 64>(a, st);
+  if (cn == 128 && C >= 256) return launch_conv_split<C, 128>(a, st);
+  return launch_conv_split<C, C>(a, st);
 }
 
 static int launch_gn(const float* x, uint8_t* a16, float* y, const float* gamma, const float* beta, const float* add_bias, const float* add_tmap,
@@ -509,6 +581,17 @@ extern "C" int node_b200_wide8_gn_operand(void* workspace, int which, const floa
   w8::Ws w; w8::ws_layout(workspace, C, &w);
   const float* tmap = (add_bias != nullptr && which == 1) ? w.tmap : nullptr;           // GN2 follows conv1 (Tmap1)
   return w8::launch_gn(x, (uint8_t*)operand, nullptr, gamma, beta, add_bias, tmap, t_dev, tsign, w.scal + 3 * which, 1.f, N, C, (cudaStream_t)stream);
+}
+
+extern "C" int node_b200_wide8_raw_operand(void* workspace, int which, const float* x, void* operand, const unsigned* max_bits, int N, int C,
+                                           void* stream) {
+  if (N < 1 || (C != 128 && C != 256) || which < 0 || which > 1) return (int)cudaErrorInvalidValue;
+  w8::Ws w; w8::ws_layout(workspace, C, &w);
+  cudaStream_t st = (cudaStream_t)stream;
+  w8::k_wide_dyn_scale<<<1, 32, 0, st>>>(w, which, max_bits);
+  NODE_CUDA_OK(cudaGetLastError());
+  w8::k_wide_raw_op<<<(unsigned)((int64_t)N * (C / 32)), 128, 0, st>>>(x, (uint8_t*)operand, w.scal + 3 * which, C);
+  return (int)cudaGetLastError();
 }
 
 extern "C" int node_b200_wide8_conv(void* workspace, int which, const void* operand, float* out, int N, int C, void* stream) {

@@ -43,7 +43,7 @@ EXPORTS = (
     'node_b200_wide_odefunc', 'node_b200_wide8_workspace_bytes', 'node_b200_wide8_operand_bytes', 'node_b200_wide8_prepare',
     'node_b200_wide8_gn_operand', 'node_b200_wide8_conv', 'node_b200_wide8_watchdog', 'node_b200_wide8_odefunc',
     'node_b200_adjoint_solve', 'node_b200_adjoint_solve_reset', 'node_b200_groupnorm_backward_ex', 'node_b200_batch_colsum',
-    'node_b200_pow2_scale', 'node_b200_wide_conv_blocks',
+    'node_b200_pow2_scale', 'node_b200_wide_conv_blocks', 'node_b200_wide_vjp', 'node_b200_wide8_raw_operand',
 )
 
 _lib = None
@@ -127,6 +127,8 @@ def _declare(lib):
     lib.node_b200_batch_colsum.argtypes = [_vp, _vp, _i64, _i64, _vp]
     lib.node_b200_pow2_scale.argtypes = [_vp, _vp, _vp]
     lib.node_b200_wide_conv_blocks.argtypes = [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]
+    lib.node_b200_wide_vjp.argtypes = [_vp, _vp, _f, _vp]
+    lib.node_b200_wide8_raw_operand.argtypes = [_vp, _i, _vp, _vp, _vp, _i, _i, _vp]
 
 
 def lib():

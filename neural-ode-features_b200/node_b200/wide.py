@@ -214,104 +214,68 @@ class WideDynamics(object):
         self._valid = V                                                    # Tmap[c] = W[c, 0].view(9) @ V^T
         self._key_vjp = key
 
-    def _conv(self, ws, x, out):
-        N, C, H, W = (int(v) for v in x.shape)
-        native.check(native.lib().node_b200_wide_conv_blocks(native.ptr(ws), int(ws.shape[-1]), native.ptr(x), native.ptr(out), N, C, H, W,
-                                                             native.stream_ptr()), 'wide_conv_blocks')
-
-    def _gn(self, x, out, norm, bias, tmap, t32, tsign, post, relu):
-        N, C, H, W = (int(v) for v in x.shape)
-        native.check(native.lib().node_b200_groupnorm_relu_ex(
-            native.ptr(x), native.ptr(out), native.ptr(norm.weight), native.ptr(norm.bias), native.ptr(bias), native.ptr(tmap),
-            native.ptr(t32), float(tsign), float(post), N, C, 32, H * W, 1e-5, relu, native.stream_ptr()), 'groupnorm_relu_ex')
-
-    def _gn_bwd(self, x, g, gx, norm, bias, tmap, t32, tsign, relu, dgamma, dbeta):
-        N, C, H, W = (int(v) for v in x.shape)
-        native.check(native.lib().node_b200_groupnorm_backward_ex(
-            native.ptr(x), native.ptr(g), native.ptr(gx), native.ptr(norm.weight), native.ptr(norm.bias), native.ptr(bias), native.ptr(tmap),
-            native.ptr(t32), float(tsign), native.ptr(self._v['part']), native.ptr(dgamma), native.ptr(dbeta), N, C, 32, H * W, 1e-5,
-            relu, native.stream_ptr()), 'groupnorm_backward_ex')
-
-    def _blocks(self, x, out):
-        """[N, C, H, W] -> [nb, N, 64, H, W] contiguous 64-channel blocks (the weight-gradient GEMM reads dense blocks)."""
-        N, C, H, W = x.shape
-        out.copy_(x.view(N, self.nb, 64, H, W).transpose(0, 1))
-        return out
-
-    def _conv_param_grads(self, li, act, gc, t32, tsign, w_out, b_out):
-        """dL/dW [C, C+1, 3, 3] and dL/db [C] of ConcatConv2d `li` from its input activation and the gradient at its output;
-        returns this convolution's share of dL/dt (device scalar)."""
-        from . import caller_grad
-        lib, v = native.lib(), self._v
-        N, C, H, W = (int(x) for x in act.shape)
-        nb = self.nb
-        ab, gb = self._blocks(act, v['ab']), self._blocks(gc, v['gb'])
-        native.check(lib.node_b200_absmax(native.ptr(act), act.numel(), native.ptr(v['bits']), native.stream_ptr()), 'absmax')
-        native.check(lib.node_b200_pow2_scale(native.ptr(v['bits']), native.ptr(v['scale']), native.stream_ptr()), 'pow2_scale')
-        sp = native._vp(v['scale'].data_ptr())
-        pairs = [(o, i) for o in range(nb) for i in range(nb)]
-        dws = []
-        for k in range(0, len(pairs), 6):                                  # node_b200_conv_wgrad serves up to 6 pairs per launch
-            chunk = pairs[k:k + 6]
-            dws.append(caller_grad.conv_wgrad([ab[i] for _, i in chunk], [gb[o] for o, _ in chunk], [sp] * len(chunk)))
-        dw = torch.cat(dws).view(nb, nb, 64, 64, 3, 3).permute(0, 2, 1, 3, 4, 5).reshape(C, C, 3, 3)
-        w_out[:, 1:].copy_(dw)
-        # bias and the folded time channel (model.py:320-323): S[c, pix] = sum_n gc[n, c, pix]
-        S = v['S']
-        native.check(lib.node_b200_batch_colsum(native.ptr(gc), native.ptr(S), N, C * H * W, native.stream_ptr()), 'batch_colsum')
-        S2 = S.view(C, H * W)
-        b_out.copy_(S2.sum(1))
-        tt = t32 * tsign
-        w_out[:, 0].copy_((tt * (S2 @ self._valid)).view(C, 3, 3))
-        return (S2 * self._tmap[li].view(C, H * W)).sum()
+    def _prepare8_dgrad(self):
+        """wide8 workspace of the data gradients: the same engine on W^T with flipped taps (the time plane has no data gradient)."""
+        f = self.func
+        ps = [f.conv1._layer.weight, f.conv2._layer.weight]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, '_key8d', None) == key:
+            return
+        lib = native.lib()
+        dev = ps[0].device
+        nbytes = lib.node_b200_wide8_workspace_bytes(self.C, 8, 8)
+        if not hasattr(self, '_ws8d') or self._ws8d.device != dev:
+            self._ws8d = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        wd = []
+        for p in ps:
+            full = torch.zeros_like(p)
+            full[:, 1:] = p.detach()[:, 1:].flip(2, 3).transpose(0, 1)
+            wd.append(full)
+        native.check(lib.node_b200_wide8_prepare(native.ptr(self._ws8d), self.C, 8, 8, native.ptr(wd[0]), native.ptr(wd[1]),
+                                                 native.ptr(f.norm1.weight), native.ptr(f.norm1.bias), native.ptr(f.norm2.weight),
+                                                 native.ptr(f.norm2.bias), native.stream_ptr()), 'wide8_prepare (data gradient)')
+        self._key8d = key
 
     def vjp_into(self, t_dev, y, adj_y, dst, tsign):
         """dst = tsign * (f, vjp_y, vjp_t, vjp_params)(tsign * t) of ODEfunc with cotangent -adj_y (adjoint.py:40-49; a reversed span
         negates the whole augmented system and its time argument, misc.py:184-187), parameters in `func.parameters()` order
-        (misc.py:5-7)."""
+        (misc.py:5-7) - one C call (node_b200_wide_vjp, csrc/wide_vjp.cu)."""
         f, lib = self.func, native.lib()
         N, C, H, W = (int(v) for v in y.shape)
-        self._prepare_vjp(H, W)
+        w8 = self._wide8(H, W)
+        if w8:
+            self._prepare8()
+            self._prepare8_dgrad()
+            if getattr(self, '_tmap8_key', None) != self._key8:          # time maps for the GroupNorm / bias kernels (fp32 [C, 8, 8])
+                ones = torch.ones(1, 1, H, W, device=y.device)
+                self._tmap = [F.conv2d(ones, c.weight.detach()[:, :1], padding=1)[0].contiguous() for c in (f.conv1._layer, f.conv2._layer)]
+                self._tmap8_key = self._key8
+        else:
+            self._prepare_vjp(H, W)
         v = getattr(self, '_v', None)
         if v is None or v['a1'].shape != y.shape or v['a1'].device != y.device:
             e = lambda: torch.empty_like(y)
-            v = self._v = dict(a1=e(), c1=e(), a2=e(), c2=e(), g0=e(), gc2=e(), gr=e(), gc1=e(),
-                               ab=torch.empty((self.nb, N, 64, H, W), device=y.device), gb=torch.empty((self.nb, N, 64, H, W), device=y.device),
-                               part=torch.empty(2 * N * C, device=y.device), S=torch.empty(C * H * W, device=y.device),
-                               bits=torch.zeros(1, dtype=torch.int32, device=y.device), scale=torch.ones(1, device=y.device))
+            dev = y.device
+            v = self._v = dict(a1=e(), c1=e(), a2=e(), c2=e(), gc2=e(), gr=e(), gc1=e(),
+                               ab=torch.empty((self.nb, N, 64, H, W), device=dev), gb=torch.empty((self.nb, N, 64, H, W), device=dev),
+                               part=torch.empty(2 * N * C, device=dev), S=torch.empty(C * H * W, device=dev),
+                               bits=torch.zeros(2, dtype=torch.int32, device=dev), scale=torch.ones(1, device=dev),
+                               wg=torch.empty(max(lib.node_b200_conv_wgrad_workspace_bytes(k) for k in range(1, 7)), dtype=torch.uint8, device=dev),
+                               dw=torch.empty(self.nb * self.nb * 64 * 64 * 9, device=dev),
+                               vt=torch.zeros(2 * C, dtype=torch.float64, device=dev))
+            if w8:
+                v['op'] = torch.zeros(lib.node_b200_wide8_operand_bytes(N, C), dtype=torch.uint8, device=dev)   # halo entries stay zero
         t32 = t_dev if t_dev.dtype == torch.float32 else t_dev.float()
         n1, n2, n3, cv1, cv2 = f.norm1, f.norm2, f.norm3, f.conv1._layer, f.conv2._layer
-        # forward, keeping the activations
-        self._gn(y, v['a1'], n1, None, None, t32, tsign, 1.0, 1)
-        self._conv(self._ws[0], v['a1'], v['c1'])
-        self._gn(v['c1'], v['a2'], n2, cv1.bias, self._tmap[0], t32, tsign, 1.0, 1)
-        self._conv(self._ws[1], v['a2'], v['c2'])
-        self._gn(v['c2'], dst[0], n3, cv2.bias, self._tmap[1], t32, tsign, -1.0 if tsign < 0 else 1.0, 0)
-        # backward with cotangent -tsign * adj_y on ODEfunc's output
-        P = dst[3]
-        o = [0]
-
-        def take(shape):
-            n = 1
-            for s in shape:
-                n *= s
-            view = P[o[0]:o[0] + n].view(shape)
-            o[0] += n
-            return view
-        g1w, g1b = take((C,)), take((C,))
-        w1, b1 = take((C, C + 1, 3, 3)), take((C,))
-        g2w, g2b = take((C,)), take((C,))
-        w2, b2 = take((C, C + 1, 3, 3)), take((C,))
-        g3w, g3b = take((C,)), take((C,))
-        torch.mul(adj_y, -1.0 if tsign > 0 else 1.0, out=v['g0'])
-        self._gn_bwd(v['c2'], v['g0'], v['gc2'], n3, cv2.bias, self._tmap[1], t32, tsign, 0, g3w, g3b)
-        vt = self._conv_param_grads(1, v['a2'], v['gc2'], t32, tsign, w2, b2)
-        self._conv(self._wsd[1], v['gc2'], v['gr'])
-        self._gn_bwd(v['c1'], v['gr'], v['gc1'], n2, cv1.bias, self._tmap[0], t32, tsign, 1, g2w, g2b)
-        vt = vt + self._conv_param_grads(0, v['a1'], v['gc1'], t32, tsign, w1, b1)
-        self._conv(self._wsd[0], v['gc1'], v['gr'])
-        self._gn_bwd(y, v['gr'], dst[1], n1, None, None, t32, tsign, 1, g1w, g1b)
-        dst[2].copy_(vt)            # cotangent already carries tsign: the reversed solve negates the whole augmented system (misc.py:186)
+        tensors = [y, adj_y, t32, dst[0], dst[1], dst[2], dst[3], n1.weight, n1.bias, n2.weight, n2.bias, n3.weight, n3.bias,
+                   cv1.bias, cv2.bias, self._tmap[0], self._tmap[1], None if w8 else self._ws, None if w8 else self._wsd,
+                   self._ws8 if w8 else None, self._ws8d if w8 else None, v.get('op'), v['a1'], v['c1'], v['a2'], v['c2'], v['gc2'],
+                   v['gr'], v['gc1'], v['ab'], v['gb'], v['part'], v['S'], v['bits'], v['scale'], v['wg'], v['dw'], v['vt']]
+        for x in (y, adj_y, dst[0], dst[1], dst[3]):
+            assert x.is_contiguous()
+        ptrs = (native._vp * len(tensors))(*[x.data_ptr() if x is not None else 0 for x in tensors])
+        dims = native.host_i64([N, C, H, W, 0 if w8 else int(self._ws.shape[-1]), 1 if w8 else 0])
+        native.check(lib.node_b200_wide_vjp(ptrs, dims, float(tsign), native.stream_ptr()), 'wide_vjp')
         if hasattr(f, 'nfe'):
             f.nfe += 1                                       # model.py:340 counts every evaluation
 

@@ -37,7 +37,7 @@ def test_wide_dynamics_match_module(native_lib, C, hw, n):
     assert f.nfe == 6
 
 
-@pytest.mark.parametrize('C,n', [(256, 1), (256, 5), (256, 8), (128, 3), (256, 601), (128, 594)])
+@pytest.mark.parametrize('C,n', [(256, 1), (256, 5), (256, 8), (128, 3), (256, 601), (128, 594), (256, 200), (256, 128), (128, 130)])
 def test_wide8_conv_pieces(native_lib, C, n):
     """wide8 engine, piece by piece: operand image + implicit GEMM against GroupNorm -> ReLU -> cuDNN fp32 convolution."""
     import torch.nn.functional as F
@@ -141,7 +141,8 @@ def _autograd_augmented(f, t, y, adj, tsign):
     return tsign * fe.detach(), tsign * g[1], tsign * g[0], tsign * torch.cat([q.reshape(-1) for q in g[2:]])
 
 
-@pytest.mark.parametrize('C,hw,n,tsign', [(128, 8, 3, 1), (256, 8, 5, 1), (256, 8, 4, -1), (128, 7, 2, -1), (192, 8, 2, 1), (256, 8, 70, 1)])
+@pytest.mark.parametrize('C,hw,n,tsign', [(128, 8, 3, 1), (256, 8, 5, 1), (256, 8, 4, -1), (128, 7, 2, -1), (192, 8, 2, 1), (256, 8, 70, 1),
+                                          (256, 8, 300, -1), (128, 8, 129, 1), (256, 7, 33, 1)])
 def test_wide_augmented_dynamics(native_lib, C, hw, n, tsign):
     """One evaluation of the adjoint's augmented dynamics of a wide ODEfunc (node_b200.wide.WideAugmented: GroupNorm backward, data
     gradients and weight gradients on this repo's kernels) against float64 autograd of the eager module."""
