@@ -507,6 +507,66 @@ def other_configs(dev):
         finally:
             os.environ.pop('NODE_B200_WIDE', None)
         del x, h0
+        # the paper's CIFAR TRAINING setting (reproduce.sh:21-25: --filters 256 --adjoint --batch-size 128 --dropout 0.5): one SGD step,
+        # the ODE block's adjoint on the native wide augmented dynamics (node_b200_wide_vjp) vs the autograd / cuDNN route
+        try:
+            def wide_step(netw, optw, xw, yw):
+                optw.zero_grad(set_to_none=True)
+                with torch.enable_grad():
+                    torch.nn.functional.cross_entropy(netw(xw), yw).backward()
+                optw.step()
+            res = {}
+            for bt in (128, 1024):
+                for mode in ('1', '0'):
+                    os.environ['NODE_B200_NATIVE_VJP'] = mode
+                    torch.manual_seed(0)
+                    netw = models.ODENet(3, n_filters=256, downsample='residual', tol=TOL, adjoint=True, dropout=0.5).train().to(dev)
+                    optw = torch.optim.SGD(netw.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+                    xw = torch.rand(bt, 3, 32, 32, device=dev)
+                    yw = torch.randint(0, 10, (bt,), device=dev)
+                    for _ in range(2):
+                        wide_step(netw, optw, xw, yw)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        wide_step(netw, optw, xw, yw)
+                    torch.cuda.synchronize()
+                    res['b%d_%s' % (bt, 'native' if mode == '1' else 'autograd_cudnn')] = dict(
+                        images_per_s=3 * bt / (time.perf_counter() - t0), adjoint_vjp=solver.last_stats.get('adjoint_vjp'))
+                    del netw, optw, xw, yw
+            res['note'] = ('whole training step at 256 filters; ODE block forward (wide8) and adjoint (node_b200_wide_vjp) on this '
+                           "repo's kernels, the 256-filter downsampler / classifier are PyTorch (the caller kernels serve 64 filters)")
+            out['n_filters_256_train_step'] = res
+        except Exception as exc:
+            out['n_filters_256_train_step'] = dict(error=repr(exc))
+        finally:
+            os.environ.pop('NODE_B200_NATIVE_VJP', None)
+        # training WITHOUT --adjoint (train.py:221 default): gradients through the unrolled solver (node_b200.unrolled:
+        # recorded solver loop, native dynamics + VJP kernels) at the reference's batch of 128
+        try:
+            torch.manual_seed(0)
+            netu = models.ODENet(3, n_filters=64, downsample='residual', tol=TOL, adjoint=False, dropout=0.5).train().to(dev)
+            optu = torch.optim.SGD(netu.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+            xu = torch.rand(128, 3, 32, 32, device=dev)
+            yu = torch.randint(0, 10, (128,), device=dev)
+
+            def ustep():
+                optu.zero_grad(set_to_none=True)
+                with torch.enable_grad():
+                    torch.nn.functional.cross_entropy(netu(xu), yu).backward()
+                optu.step()
+            for _ in range(2):
+                ustep()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ustep()
+            torch.cuda.synchronize()
+            out['unrolled_train_step_b128'] = dict(images_per_s=5 * 128 / (time.perf_counter() - t0), route=solver.last_stats.get('route'),
+                                                   note='odeint (non-adjoint) under autograd: the reference\'s unrolled gradient, controller terms included')
+            del netu, optu
+        except Exception as exc:
+            out['unrolled_train_step_b128'] = dict(error=repr(exc))
         # batched independent solvers (evaluate.py:109-126 runs batch_size = 1 to record the NFE of every image)
         try:
             from node_b200 import each

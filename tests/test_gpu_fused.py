@@ -147,12 +147,15 @@ def test_fused_reversed_time(native_lib, golden):
 # odeint_adjoint end to end: tests/test_gpu_adjoint.py (every shape, gates derived from the reference's own fp32-vs-fp64 distance)
 
 
-def test_training_without_adjoint_flag_gets_adjoint_gradients(native_lib):
-    """train.py's default (no --adjoint, model.py:359) asks odeint itself for gradients: served by the adjoint ODE."""
+def test_training_without_adjoint_flag(native_lib, monkeypatch):
+    """train.py's default (no --adjoint, model.py:359) asks odeint itself for gradients: served by the unrolled route (the
+    reference's own gradient, tests/test_gpu_unrolled.py); NODE_B200_ODEINT_GRAD=adjoint serves it by the adjoint ODE, which then
+    equals the --adjoint model's gradient. The whole ODENet trains either way (finite gradients for every parameter)."""
     import warnings
-    from node_b200 import models
+    from node_b200 import models, solver
     grads = {}
-    for adjoint in (False, True):
+    for mode, adjoint in (('unrolled', False), ('adjoint', False), ('adjoint', True)):
+        monkeypatch.setenv('NODE_B200_ODEINT_GRAD', mode)
         torch.manual_seed(0)
         net = models.ODENet(3, n_filters=64, downsample='residual', tol=1e-3, adjoint=adjoint).train().to(DEV)
         x = torch.rand(8, 3, 32, 32, generator=torch.Generator().manual_seed(5)).to(DEV)
@@ -160,11 +163,18 @@ def test_training_without_adjoint_flag_gets_adjoint_gradients(native_lib):
         with warnings.catch_warnings():
             warnings.simplefilter('ignore')
             loss = torch.nn.functional.cross_entropy(net(x), y)
+        if mode == 'unrolled':
+            assert solver.last_stats['route'] == 'unrolled'
         loss.backward()
-        grads[adjoint] = [p.grad.clone() for p in net.parameters()]
-        assert all(g is not None and torch.isfinite(g).all() for g in grads[adjoint])
-    for a, b in zip(grads[False], grads[True]):            # same kernels; cuDNN's backward is not bit-reproducible
+        grads[(mode, adjoint)] = [p.grad.clone() for p in net.parameters()]
+        assert all(g is not None and torch.isfinite(g).all() for g in grads[(mode, adjoint)])
+    for a, b in zip(grads[('adjoint', False)], grads[('adjoint', True)]):      # same kernels; cuDNN's backward is not bit-reproducible
         assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-9
+    # unrolled vs adjoint: two DIFFERENT gradients of the same loss at tol 1e-3 (the reference's own two are 1.2e-1 .. 5.5e-1 apart in
+    # max norm on the golden problems, tests/golden/unrolled_*.npz `adjoint_dev_*`) that point the same way (cosine 0.98 here)
+    va = torch.cat([g.reshape(-1) for g in grads[('unrolled', False)]])
+    vb = torch.cat([g.reshape(-1) for g in grads[('adjoint', True)]])
+    assert float(torch.dot(va, vb) / (va.norm() * vb.norm())) > 0.95
 
 
 def test_cuda_graph_replay_of_the_solve(native_lib, golden, monkeypatch):
