@@ -95,7 +95,8 @@ int node_b200_ctl_init(node_ctl_t* ctl, int dtype, int n_seg, const double* host
 /* K2 - stage combination  out = y0 + sum_j (h*c_j)*k_j  (rk_common.py:49-51, misc.py:22-25).
  * `which` selects the coefficient row: 0..5 = beta row of stage i+1, 6 = C_MID (dopri5.py:33-42),
  * 7 = initial-step probe y0 + h0*f0 (misc.py:133). h is read from ctl: the current attempt's for rows 0..5,
- * the last ACCEPTED step's for row 6 (call it after the controller), h0 for row 7. n_k pointers in ks. */
+ * the last ACCEPTED step's for row 6 (call it after the controller), h0 for row 7. n_k pointers in ks. Row 6 only feeds the
+ * dense output: it returns at once unless the controller scheduled outputs for the accepted step (ctl.out_hi > ctl.out_lo). */
 int node_b200_rk_stage_combine(const node_ctl_t* ctl, int dtype, int which, void* out, const void* y0,
                                const void* const* host_ks, int n_k, int64_t numel, void* stream);
 

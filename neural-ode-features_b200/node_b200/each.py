@@ -75,7 +75,7 @@ def odeint_each(func, y0, t, rtol=1e-7, atol=1e-9, method=None, lanes=16, steps=
     E = C * H * W
     target = _solver._unwrap(func)
     if steps is None:
-        steps = _solver._step_guess.get(('each', id(target)), 8)
+        steps = _solver._step_guess.get(('each', target), 8)
     steps = int(steps)
     use_graph = os.environ.get('NODE_B200_GRAPH', 'auto') != '0'
     out = torch.empty((T, N, C, H, W), dtype=torch.float32, device=dev)
@@ -133,7 +133,7 @@ def odeint_each(func, y0, t, rtol=1e-7, atol=1e-9, method=None, lanes=16, steps=
         most = max(most, st['n_accept'] + st['n_reject'])
         total += st['nfe']
         stats.append(st)
-    _solver._step_guess[('each', id(target))] = most + 1
+    _solver._step_guess[('each', target)] = most + 1
     if hasattr(target, 'nfe'):
         target.nfe += total
     _solver.last_stats.clear()

@@ -33,7 +33,56 @@ last_stats = {}          # filled after every solve: nfe, n_accept, n_reject, tr
 PROFILE_STEP_EVENTS = None
 _t_cache = {}
 _ws_cache = {}
-_step_guess = {}
+class _nvtx(object):
+    """NVTX range around the solver's entry points (SURVEY 5 tracing) when NODE_B200_NVTX=1: nsys / ncu --nvtx timelines then
+    show `node_b200.solve`, `node_b200.adjoint_backward`, `node_b200.unrolled` around the kernels they enqueue."""
+
+    def __init__(self, name):
+        self.name = name
+        self.on = os.environ.get('NODE_B200_NVTX', '0') == '1' and torch.cuda.is_available()
+
+    def __enter__(self):
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+class _StepGuess(object):
+    """Attempted-step counts of the last solve per dynamics object (sizes the enqueue-ahead / captured graphs). Keyed by the
+    object itself through a weak reference, so an entry dies with its module instead of being inherited by whatever object
+    is allocated at the same address next."""
+
+    def __init__(self):
+        self._d = weakref.WeakKeyDictionary()
+        self._plain = {}
+
+    def _slot(self, key):
+        tag, obj = key if isinstance(key, tuple) else (None, key)
+        try:
+            per = self._d.setdefault(obj, {})
+        except TypeError:                      # not weak-referenceable (a builtin callable): fall back to its id
+            per = self._plain.setdefault(id(obj), {})
+        return per, tag
+
+    def get(self, key, default=None):
+        per, tag = self._slot(key)
+        return per.get(tag, default)
+
+    def __setitem__(self, key, value):
+        per, tag = self._slot(key)
+        per[tag] = value
+
+    def clear(self):
+        self._d = weakref.WeakKeyDictionary()
+        self._plain = {}
+
+
+_step_guess = _StepGuess()
+_slow_shape_warned = set()
 _warned_grad_bridge = False
 
 
@@ -351,6 +400,10 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     ws.prepare(params)
     out = torch.empty((T,) + tuple(y.shape), dtype=y.dtype, device=y.device)
     lib = native.lib()
+    if (int(H), int(W)) not in _slow_shape_warned and lib.node_b200_vjp_workspace_bytes(int(N), int(C), int(H), int(W)) <= 0:
+        _slow_shape_warned.add((int(H), int(W)))
+        warnings.warn('node_b200: %dx%d feature maps are served by the first-generation fused kernel (about 3x slower per step than '
+                      'the tcgen05 step engine, which is tiled for 6x6, 7x7, 8x8, 14x14 and 16x16 maps)' % (H, W))
     conv_mode = _conv_mode()
     group = dist_state.group()
     th = native.host_f64(t_host)
@@ -361,7 +414,7 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
     events = PROFILE_STEP_EVENTS
     peer = group is not None and dist_state.peer_active()          # sums all-reduced inside the fold kernel (peer memory)
     if (group is None or peer) and events is None:
-        guess = _step_guess.get(id(_unwrap(func)))
+        guess = _step_guess.get(_unwrap(func))
         graph = None
         if guess is not None and _graph_wanted(N, T) and not peer:
             # Launch-bound sizes: the whole enqueue sequence (f0, probe, `guess` attempted steps with their controllers
@@ -407,7 +460,7 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
         phase(0); reduce()
         phase(1); reduce()
         phase(2)
-        guess = _step_guess.get(id(_unwrap(func)), 8)
+        guess = _step_guess.get(_unwrap(func), 8)
         mine = []
         while True:
             for _ in range(guess):
@@ -426,7 +479,7 @@ def _solve_fused(func, params, y0, t_host, tsign, rtol, atol):
             guess = 4
         if events is not None:         # keep only launches that did work (steps after `done` are no-ops)
             events.extend(mine[:view.i32('n_attempt')])
-    _step_guess[id(_unwrap(func))] = view.i32('n_attempt') + 1
+    _step_guess[_unwrap(func)] = view.i32('n_attempt') + 1
     nfe = view.i32('nfe')
     target = _unwrap(func)
     if hasattr(target, 'nfe'):
@@ -734,7 +787,7 @@ def _solve(func, y0, t, rtol, atol, options):
     unknown = [k for k in options if k not in _DOPRI5_OPTIONS]
     if unknown:
         warnings.warn('Dopri5Solver: Unexpected arguments {}'.format({k: options[k] for k in unknown}))
-    with torch.no_grad():
+    with torch.no_grad(), _nvtx('node_b200.solve'):
         params = recognise_odefunc(func)
         plain = not options and not _is_iterable(rtol) and not _is_iterable(atol)
         if params is not None and plain and _fusable_state(params, y0) and len(t_host) <= 1024:
@@ -794,7 +847,7 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
             if tensor_input and isinstance(user, nn.Module):
                 call = _TensorFunc(user)
             last_stats.clear()
-            with torch.cuda.device(y0[0].device):
+            with torch.cuda.device(y0[0].device), _nvtx('node_b200.unrolled'):
                 out = unrolled.solve(call, y0, t, rtol, atol, options, stats=last_stats)
             return out[0] if tensor_input else out
         if not isinstance(func, nn.Module):
@@ -869,7 +922,7 @@ class _AdjointFn(torch.autograd.Function):
             augmented = wide.WideAugmented(func)    # n_filters = 128 / 192 / 256 (reproduce.sh:21-25 trains these with --adjoint)
         else:
             augmented.replicated_from = 2 * n       # adj_t, adj_params: sums over the (possibly sharded) batch
-        with torch.no_grad():
+        with torch.no_grad(), _nvtx('node_b200.adjoint_backward'):
             adj_y = tuple(g[-1] for g in grad_output)
             adj_p = torch.zeros_like(flat_params)
             adj_t = torch.zeros((), dtype=ans[0].dtype, device=ans[0].device)

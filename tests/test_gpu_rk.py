@@ -54,6 +54,7 @@ def test_stage_combine_and_error_norm_match_reference_arithmetic(native_lib, dty
     _poke(ctl, native, 'h64', float(h), np.float64)
     _poke(ctl, native, 'it_h32', float(h), np.float32)
     _poke(ctl, native, 'it_h64', float(h), np.float64)
+    _poke(ctl, native, 'out_hi', 1, np.int32)            # row 6 (mid-point) returns at once unless the controller scheduled outputs
     dy0, dks = y0.to(DEV), [k.to(DEV) for k in ks]
     out = torch.empty_like(dy0)
     for row in range(6):
