@@ -447,7 +447,7 @@ __device__ __forceinline__ void produce_conv_job(const StepSmem& sm, const Jobs&
 
 template <class T, int NSLOT>
 __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& jb, uint32_t tmem, int s, uint32_t job, uint32_t nth,
-                                               bool split, bool& timeout) {
+                                               bool split, bool& timeout, int mt_used) {
   const bool lead = ptx::elect_one();
   if (!timeout && !ptx::mbar_wait(sm.bar_turn + 8 * s, nth & 1)) timeout = true;   // my slot's nth turn
 #ifdef NODE_STEP_DEBUG
@@ -482,6 +482,7 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
     if (lead) {
 #pragma unroll
       for (int mt = 0; mt < T::MT; ++mt) {
+        if (mt >= mt_used) continue;           // an M tile that holds no valid image (a batch-1 solve fills one of two): nothing to multiply
         const uint32_t d = tmem + (uint32_t)((s * T::MT + mt) * 128);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -513,7 +514,7 @@ __device__ __forceinline__ void issue_conv_job(const StepSmem& sm, const Jobs& j
 // Publish the A image and run the conv job on the tensor core; returns when the accumulators are complete.
 template <class T, int NSLOT>
 __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, const Jobs& jb, const uint16_t* __restrict__ w16,
-                                         uint32_t tmem, uint32_t& njob, uint32_t nfull, bool& timeout, bool split) {
+                                         uint32_t tmem, uint32_t& njob, uint32_t nfull, bool& timeout, bool split, int mt_used = 1 << 20) {
   const uint32_t job = njob < nfull ? njob * NSLOT + me.slot : jb.jobs_full + (njob - nfull);   // global index of my slot's njob-th job
   ptx::fence_proxy_async();          // my rows of the A image -> visible to the tensor core
   ptx::tc_fence_before();            // my tcgen05.ld of the previous accumulators are done
@@ -525,7 +526,8 @@ __device__ __forceinline__ void conv_run(const StepSmem& sm, const Who& me, cons
   const int wu = __shfl_sync(0xffffffffu, me.warp, 0);     // shuffles: tell the compiler these values are warp-uniform
   if (wu == 0)
     issue_conv_job<T, NSLOT>(sm, jb, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, me.slot, 0),
-                             __shfl_sync(0xffffffffu, job, 0), __shfl_sync(0xffffffffu, njob, 0), split, timeout);
+                             __shfl_sync(0xffffffffu, job, 0), __shfl_sync(0xffffffffu, njob, 0), split, timeout,
+                             __shfl_sync(0xffffffffu, mt_used, 0));
   else if (wu == 1)
     produce_conv_job<T, NSLOT>(sm, jb, w16, __shfl_sync(0xffffffffu, me.slot, 0), __shfl_sync(0xffffffffu, job, 0),
                                __shfl_sync(0xffffffffu, njob, 0), timeout);
@@ -735,6 +737,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
       const int img = st * T::G + me.img_l;
       const bool valid = me.inimg && img < a.g.N;
       const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+      const int nvalid = min(T::G, a.g.N - st * T::G);                      // images of this super-tile (CTA-slot uniform)
+      const int mt_used = min(T::MT, (nvalid * T::IS + 127) / 128);         // M tiles that hold one
       float x[32];
 
 #pragma unroll 1
@@ -804,7 +808,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
           affine_to_A<T>(sm, me, hb, x, valid, split);
           NODE_STAMP(3);
         }
-        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split, mt_used);
         NODE_STAMP(4);
 
         // ---- conv1 epilogue -> GN2 -> ReLU -> A image of conv2 (model.py:343-346)
@@ -818,7 +822,7 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
           NODE_STAMP(7);
         }
         make_tb<T>(sm, me, 1, t);
-        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split);
+        conv_run<T, NSLOT>(sm, me, jb, w.w16, tmem, njob, nfull, timeout, split, mt_used);
         NODE_STAMP(8);
 
         // ---- conv2 epilogue -> GN3 -> k_{ev+2} (model.py:346-348), and the norms that feed the controller

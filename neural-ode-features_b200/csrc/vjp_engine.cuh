@@ -198,7 +198,7 @@ __device__ __forceinline__ void vjp_produce_job(const VjpSmem& sm, const uint16_
 
 template <class T>
 __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t job,
-                                              bool& timeout) {
+                                              bool& timeout, int mt_used) {
   // whole first warp, warp-uniform arguments, asynchronous instructions by one elected lane (see step_engine.cuh)
   const bool lead = ptx::elect_one();
   ptx::tc_fence_after();
@@ -217,6 +217,7 @@ __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, uint32_t tmem, 
     if (lead) {
 #pragma unroll
       for (int mt = 0; mt < T::MT; ++mt) {
+        if (mt >= mt_used) continue;           // M tile without a valid image (batch 1: one of two)
         const uint32_t d = tmem + dcol + (uint32_t)(mt * 64);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -237,14 +238,14 @@ __device__ __forceinline__ void vjp_issue_job(const VjpSmem& sm, uint32_t tmem, 
 
 template <class T>
 __device__ __forceinline__ void vjp_conv_run(const VjpSmem& sm, const Who& me, uint32_t total, const uint16_t* __restrict__ w16,
-                                             uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t& njob, bool& timeout) {
+                                             uint32_t tmem, uint32_t dcol, uint32_t idesc, uint32_t& njob, bool& timeout, int mt_used) {
   ptx::fence_proxy_async();
   ptx::tc_fence_before();
   slot_sync(0, T::P);
   const int wu = __shfl_sync(0xffffffffu, me.warp, 0);     // shuffles: tell the compiler these values are warp-uniform
   if (wu == 0)
     vjp_issue_job<T>(sm, __shfl_sync(0xffffffffu, tmem, 0), __shfl_sync(0xffffffffu, dcol, 0), __shfl_sync(0xffffffffu, idesc, 0),
-                     __shfl_sync(0xffffffffu, njob, 0), timeout);
+                     __shfl_sync(0xffffffffu, njob, 0), timeout, __shfl_sync(0xffffffffu, mt_used, 0));
   else if (wu == 1)
     vjp_produce_job(sm, w16, __shfl_sync(0xffffffffu, njob, 0), __shfl_sync(0xffffffffu, total, 0), timeout);
   if (!timeout && !ptx::mbar_wait_relaxed(sm.s.bar_acc, njob & 1)) timeout = true;
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
     const int img = st * T::G + me.img_l;
     const bool valid = me.inimg && img < a.g.N;
     const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
+    const int mt_used = min(T::MT, (min(T::G, a.g.N - st * T::G) * T::IS + 127) / 128);    // M tiles that hold a valid image
     float x[32], g[32];
 
     // ---- forward: y -> GN1 -> ReLU -> conv1 (model.py:341-343)
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       gn_stats<T>(st1, me, hb, x, valid, a.eps);
       act_to_A<T>(sm, me, hb, x, 0, w.scal[0], valid, a.R[0], p0);
     }
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC1, kIdF16N64, njob, timeout);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC1, kIdF16N64, njob, timeout, mt_used);
     // ---- c1 -> GN2 -> ReLU -> conv2 (model.py:344-346)
 #pragma unroll 1
     for (int hb = 0; hb < 2; ++hb) {
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
       gn_stats<T>(st2, me, hb, x, valid, a.eps);
       act_to_A<T>(sm, me, hb, x, 1, w.scal[1], valid, a.R[1], p0);
     }
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout, mt_used);
     // ---- c2 -> GN3 = f; backward of GN3 with cotangent -a (adjoint.py:43)
     float gmax = 0.f, ginv = 1.f;
 #pragma unroll 1
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
     }
     gc_max[1] = fmaxf(gc_max[1], gmax);
     grad_finalize_A<T>(sm, me, grad_scale<T>(sm, me, gmax, ginv), valid);
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);      // dL/dr2 over c2's columns
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout, mt_used);      // dL/dr2 over c2's columns
     const float mul2 = ginv * inv_sw2;
     gmax = 0.f;
     // ---- ReLU mask of GN2's output, backward of GN2
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
     }
     gc_max[0] = fmaxf(gc_max[0], gmax);
     grad_finalize_A<T>(sm, me, grad_scale<T>(sm, me, gmax, ginv), valid);
-    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout);      // dL/dr1
+    vjp_conv_run<T>(sm, me, total, w.w16, tmem, kColC2, kIdF16N64, njob, timeout, mt_used);      // dL/dr1
     const float mul1 = ginv * inv_sw1;
     // ---- ReLU mask of GN1's output, backward of GN1 -> vjp_y
 #pragma unroll 1
