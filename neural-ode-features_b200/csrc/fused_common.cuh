@@ -1,5 +1,6 @@
 // Shared declarations of the fused ODE-Net route: workspace layout, launch arguments, geometry.
 #pragma once
+#include <cstdlib>
 #include "node_common.cuh"
 #include "ptx.cuh"
 
@@ -39,7 +40,7 @@ struct FusedWs {
   float* Y[2]; float* F[2]; float* K[5]; float* YMID;
 };
 
-struct Geo { int N, H, W, HW, G, MT, ngroups; };
+struct Geo { int N, H, W, HW, G, MT, ngroups, gs; };    // gs: images per super-tile the strip engines use for this batch (strip_gs)
 
 struct FusedArgs {
   FusedWs w; Geo g;
@@ -88,6 +89,7 @@ static int64_t ws_layout(void* base, int N, int C, int H, int W, FusedWs* out) {
   return o;
 }
 
+static int strip_gs(int N, int H, int W);
 static bool make_geo(int N, int C, int H, int W, Geo* g) {
   if (C != kC || N < 1 || H < 1 || W < 1) return false;
   const int HW = H * W;
@@ -96,6 +98,7 @@ static bool make_geo(int N, int C, int H, int W, Geo* g) {
   g->G = HW <= 128 ? 128 / HW : 1;
   g->MT = (g->G * HW + 127) / 128;
   g->ngroups = (N + g->G - 1) / g->G;
+  g->gs = strip_gs(N, H, W);
   return true;
 }
 
@@ -143,6 +146,18 @@ __host__ __device__ constexpr int strip_images(int H, int W) {
   const int Wp = W + 1, IS = (H + 1) * Wp, SPAN = (H - 1) * Wp + W;
   const int MT = SPAN <= 256 ? 2 : (SPAN + 127) / 128;
   return (MT * 128 - SPAN) / IS + 1;
+}
+
+// Images per super-tile actually used by the strip engines (k_step, k_vjp): a super-tile can hold strip_images() of them, but a
+// small batch is spread over the SMs first - at the reference's batch of 128 every CTA gets ONE image and, with the M tiles that
+// hold no image skipped by the issuer, a convolution job is half the MMAs (the evaluation is a dependent chain: 30 -> 25 us).
+// NODE_B200_STRIP_GS=0 keeps full super-tiles.
+static int strip_gs(int N, int H, int W) {
+  const int G = strip_images(H, W);
+  static const char* e = getenv("NODE_B200_STRIP_GS");
+  if (e != nullptr && e[0] == '0') return G;
+  const int gs = (N + kMaxGrid - 1) / kMaxGrid;
+  return gs < 1 ? 1 : (gs > G ? G : gs);
 }
 
 // f16 engine (odefunc_step.cu)

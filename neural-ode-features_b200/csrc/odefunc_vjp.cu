@@ -215,7 +215,8 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   // grid sizes the two kernels used (same rules as their launchers)
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;
-  const int nst_vjp = use_dense ? grid_dense : (NST < kMaxGrid ? NST : kMaxGrid);
+  const int NSTV = (N + a.g.gs - 1) / a.g.gs;              // k_vjp's super-tiles hold a.g.gs images (strip_gs)
+  const int nst_vjp = use_dense ? grid_dense : (NSTV < kMaxGrid ? NSTV : kMaxGrid);
   const int nsplit = (H == 8 && W == 8 && wgrad8_enabled()) ? wgrad8_splits(N, 2) : (NST < kWgSplits ? NST : kWgSplits);
   k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
                                                               vjp_t, vjp_params);

@@ -685,7 +685,8 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
   const uint32_t tmem = *sm.tmem_slot;
 
   // ---- super-tile schedule: stream u = (cta, slot) takes super-tiles u, u + stride, ...
-  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int gs = a.g.gs;                                // images per super-tile for this batch (<= T::G)
+  const int NST = (a.g.N + gs - 1) / gs;
   const int stride = gridDim.x * NSLOT;
   const int nevals = a.mode == MODE_STEP ? 6 : 1;
   const bool split = a.conv_mode == CONV_F16X3;
@@ -734,10 +735,10 @@ __global__ void __launch_bounds__(NSLOT * Tile<H_, W_>::P, 1) k_step(const Fused
 
 #pragma unroll 1
     for (int st = u0; st < NST; st += stride) {
-      const int img = st * T::G + me.img_l;
-      const bool valid = me.inimg && img < a.g.N;
+      const int img = st * gs + me.img_l;
+      const bool valid = me.inimg && me.img_l < gs && img < a.g.N;
       const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
-      const int nvalid = min(T::G, a.g.N - st * T::G);                      // images of this super-tile (CTA-slot uniform)
+      const int nvalid = min(gs, a.g.N - st * gs);                          // images of this super-tile (CTA-slot uniform)
       const int mt_used = min(T::MT, (nvalid * T::IS + 127) / 128);         // M tiles that hold one
       float x[32];
 
@@ -943,7 +944,7 @@ static int launch_step_shape(const FusedArgs& a, cudaStream_t st) {
   constexpr size_t smem = step_smem_bytes(T::A_PART, NSLOT, T::NWARP, T::G);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   NODE_SET_SMEM_ONCE((k_step<H_, W_, NSLOT>), smem);
-  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int NST = (a.g.N + a.g.gs - 1) / a.g.gs;
   int grid = (NST + NSLOT - 1) / NSLOT;
   if (grid > kMaxGrid) grid = kMaxGrid;
   k_step<H_, W_, NSLOT><<<grid, NSLOT * T::P, smem, st>>>(a);
@@ -958,7 +959,7 @@ static int launch_step_slots(const FusedArgs& a, cudaStream_t st) {
   using T = Tile<H_, W_>;
   constexpr bool two = step_smem_bytes(T::A_PART, 2, T::NWARP, T::G) <= 227 * 1024 && 2 * T::MT * 128 <= 512;
   if constexpr (two) {
-    const int NST = (a.g.N + T::G - 1) / T::G;
+    const int NST = (a.g.N + a.g.gs - 1) / a.g.gs;
     static const char* force = getenv("NODE_B200_SLOTS");          // "1": always one slot (tuning aid)
     if (NST > kMaxGrid && !(force != nullptr && force[0] == '1')) return launch_step_shape<H_, W_, 2>(a, st);
   }

@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
   const uint32_t tmem = *sm.s.tmem_slot;
   constexpr uint32_t kColC1 = 0, kColC2 = T::MT * 64;
 
-  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int gs = a.g.gs;                                // images per super-tile for this batch (<= T::G)
+  const int NST = (a.g.N + gs - 1) / gs;
   const int nst = (int)blockIdx.x < NST ? (NST - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const uint32_t total = (uint32_t)nst * 4u * 9u;
   if (tid == 0)                     // the first tiles of the weight sequence; later ones are requested by the producer warp
@@ -400,10 +401,10 @@ __global__ void __launch_bounds__(Tile<H_, W_>::P, 1) k_vjp(const VjpArgs a) {
 
 #pragma unroll 1
   for (int st = blockIdx.x; st < NST; st += gridDim.x) {
-    const int img = st * T::G + me.img_l;
-    const bool valid = me.inimg && img < a.g.N;
+    const int img = st * gs + me.img_l;
+    const bool valid = me.inimg && me.img_l < gs && img < a.g.N;
     const size_t goff = valid ? (size_t)img * kC * HW + me.pix : (size_t)(me.inimg ? me.pix : 0);
-    const int mt_used = min(T::MT, (min(T::G, a.g.N - st * T::G) * T::IS + 127) / 128);    // M tiles that hold a valid image
+    const int mt_used = min(T::MT, (min(gs, a.g.N - st * gs) * T::IS + 127) / 128);        // M tiles that hold a valid image
     float x[32], g[32];
 
     // ---- forward: y -> GN1 -> ReLU -> conv1 (model.py:341-343)
@@ -561,7 +562,7 @@ static int launch_vjp_shape(const VjpArgs& a, cudaStream_t st) {
   static_assert(2 * T::MT * 64 <= kTmemCols, "tensor memory budget");
   static_assert(T::G == strip_images(H_, W_), "strip_images out of sync");
   NODE_SET_SMEM_ONCE((k_vjp<H_, W_>), smem);
-  const int NST = (a.g.N + T::G - 1) / T::G;
+  const int NST = (a.g.N + a.g.gs - 1) / a.g.gs;
   const int grid = NST < kMaxGrid ? NST : kMaxGrid;
   k_vjp<H_, W_><<<grid, T::P, smem, st>>>(a);
   return (int)cudaGetLastError();
