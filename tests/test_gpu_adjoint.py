@@ -142,3 +142,30 @@ def test_adjoint_one_call_rejected_steps(native_lib, golden, monkeypatch, name):
     for i in range(4):
         assert torch.equal(a[i], c[i]), (i, float((a[i] - c[i]).abs().max()))
     assert a[4:6] == c[4:6] == (int(g['nfe_f']), int(g['nfe_b']))
+
+
+def test_adjoint_device_loop_terminates_on_solver_errors(native_lib):
+    """The device-side while loop must end when the controller raises a status (dopri5.py:89 max_num_steps, dopri5.py:102 non-finite
+    state) - the error surfaces as the reference's AssertionError after the one read of the interval."""
+    from node_b200 import models, odeint_adjoint, solver
+    torch.manual_seed(3)
+    func = models.ODEfunc(64).to(DEV)
+    with torch.no_grad():
+        for p in func.parameters():
+            p.mul_(3.0)
+    y1 = torch.randn(4, 64, 8, 8, device=DEV)
+    P = sum(p.numel() for p in func.parameters())
+    aug0 = (y1, torch.randn_like(y1), torch.zeros((), device=DEV), torch.zeros(P, device=DEV))
+    span = torch.tensor([1.0, 0.0], dtype=torch.float64)
+    aug = solver._FusedAugmented(solver._TensorFunc(func))
+    with torch.no_grad():
+        sol = solver._solve(aug, aug0, span, 1e-4, 1e-4, {})
+        assert solver.last_stats.get('adjoint_loop') == 'device' and solver.last_stats['n_accept'] + solver.last_stats['n_reject'] > 2
+        with pytest.raises(AssertionError, match='max_num_steps'):
+            solver._solve(aug, aug0, span, 1e-4, 1e-4, dict(max_num_steps=2))
+        bad = (y1, torch.full_like(y1, float('inf')), aug0[2], aug0[3])
+        with pytest.raises(AssertionError, match='non-finite'):
+            solver._solve(aug, bad, span, 1e-3, 1e-3, {})
+        again = solver._solve(aug, aug0, span, 1e-4, 1e-4, {})                 # and the cached loop graph still serves
+    for a, b in zip(sol, again):
+        assert torch.equal(a, b)
