@@ -290,9 +290,16 @@ def invalidate_caches():
     for ws in _ws_cache.values():
         ws.param_key = None
         ws.param_refs = None
-    from . import caller_ops
+    from . import caller_ops, wide
     caller_ops._resconv_ws.clear()
     caller_ops._convs2_ws.clear()
+    for dyn in list(wide.WideDynamics._cache.values()):          # prepared weight images of the wide dynamics (forward and adjoint)
+        for key in ('_key', '_key8', '_key8d', '_key_vjp', '_tmap8_key'):
+            if hasattr(dyn, key):
+                delattr(dyn, key)
+    if _adjoint_bufs:
+        _adjoint_bufs.clear()
+        native.lib().node_b200_adjoint_solve_reset()             # loop graphs point at the buffers just released
 
 
 def fused_workspace(device, N, C, H, W):
