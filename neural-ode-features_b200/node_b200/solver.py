@@ -853,6 +853,14 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
             call = (lambda tt, yy: (user(tt, yy[0]),)) if tensor_input else func
             if tensor_input and isinstance(user, nn.Module):
                 call = _TensorFunc(user)
+            params = recognise_odefunc(user) if (tensor_input and isinstance(user, nn.Module)) else None
+            if (params is not None and not options and not _is_iterable(rtol) and not _is_iterable(atol) and _fusable_state(params, y0)
+                    and native.lib().node_b200_vjp_workspace_bytes(*[int(v) for v in y0[0].shape]) > 0
+                    and os.environ.get('NODE_B200_ODEINT_GRAD', 'unrolled') != 'unrolled-eager'):
+                # The recognised dynamics: the forward is the fused solve (no graph, O(1) memory, full speed - evaluate.py:109 calls
+                # the model with gradients enabled and never calls backward); the unrolled graph is recorded only if a gradient is
+                # actually asked for (unrolled.LazyUnrolled: replay under autograd inside backward).
+                return unrolled.LazyUnrolled.apply(user, call, t, rtol, atol, y0[0], *tuple(user.parameters()))
             last_stats.clear()
             with torch.cuda.device(y0[0].device), _nvtx('node_b200.unrolled'):
                 out = unrolled.solve(call, y0, t, rtol, atol, options, stats=last_stats)

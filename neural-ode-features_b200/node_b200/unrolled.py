@@ -188,3 +188,42 @@ def solve(func, y0, t, rtol, atol, options, stats=None):
 
 def _lin(cs, xs):                              # misc.py:27-30 `_dot_product`
     return sum([c * x for c, x in zip(cs, xs)])
+
+
+class LazyUnrolled(torch.autograd.Function):
+    """`odeint` of the recognised ODE-Net dynamics with gradients enabled: forward = the fused solve (the route every no-grad call
+    takes: one C call, no autograd graph, the reference's NFE), backward = the unrolled gradient of `solve` above, recorded and
+    differentiated on demand (the replay re-integrates from y0 with the same arithmetic, so it takes the same step sequence; its
+    evaluations are not counted in `func.nfe` a second time - the reference's backward does not evaluate `func` either). A model
+    that is only ever called forward under enable_grad (evaluate.py:109-126, foolbox predictions) never pays for a graph."""
+
+    @staticmethod
+    def forward(ctx, module, call, t, rtol, atol, y0, *params):
+        ctx.module, ctx.call, ctx.rtol, ctx.atol = module, call, rtol, atol
+        with torch.no_grad():
+            out = _solver._solve(call, (y0,), t, rtol, atol, {})[0]
+        ctx.save_for_backward(t, y0)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        t, y0 = ctx.saved_tensors
+        module = ctx.module
+        params = tuple(module.parameters())
+        nfe = getattr(module, 'nfe', None)
+        stats = {}
+        with torch.enable_grad(), torch.cuda.device(y0.device):
+            y = y0.detach().requires_grad_(True)
+            tt = t.detach().requires_grad_(True) if t.is_floating_point() else t
+            out = solve(ctx.call, (y,), tt, ctx.rtol, ctx.atol, {}, stats=stats)[0]
+            wanted = [y] + ([tt] if tt.requires_grad else []) + [p for p in params if p.requires_grad]
+            grads = list(torch.autograd.grad(out, wanted, grad_out, allow_unused=True))
+        if nfe is not None:
+            module.nfe = nfe
+        _solver.last_stats['grad_route'] = 'unrolled'
+        _solver.last_stats['replay'] = stats
+        gy = grads.pop(0)
+        gt = grads.pop(0) if tt.requires_grad else None
+        gp = [grads.pop(0) if p.requires_grad else None for p in params]
+        return (None, None, gt, None, None, gy) + tuple(gp)

@@ -22,9 +22,13 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
+@pytest.mark.parametrize('mode', ['lazy', 'unrolled-eager'])
 @pytest.mark.parametrize('name', CASES)
-def test_unrolled_gradients_against_reference(native_lib, golden, name, monkeypatch):
+def test_unrolled_gradients_against_reference(native_lib, golden, name, mode, monkeypatch):
+    """mode 'lazy' (default for the recognised dynamics): forward = the fused solve, the unrolled graph is recorded inside backward;
+    'unrolled-eager': the graph is recorded during the forward (what plain callables get). Same gradient, same gates."""
     from node_b200 import odeint, solver
+    monkeypatch.setenv('NODE_B200_ODEINT_GRAD', 'unrolled' if mode == 'lazy' else mode)
     calls = {'vjp': 0, 'fwd': 0}
     vjp0, fwd0 = solver.odefunc_vjp, solver.odefunc_forward
     monkeypatch.setattr(solver, 'odefunc_vjp', lambda *a, **k: (calls.__setitem__('vjp', calls['vjp'] + 1), vjp0(*a, **k))[1])
@@ -37,14 +41,22 @@ def test_unrolled_gradients_against_reference(native_lib, golden, name, monkeypa
     func.nfe = 0
     out = odeint(func, h0, t, rtol=tol, atol=tol, method='dopri5')
     st = dict(solver.last_stats)
-    assert st['route'] == 'unrolled' and out.requires_grad
     nfe = int(g['nfe'])
     acc = [bool(a) for a in g['tr_acc']]
+    assert out.requires_grad
     assert func.nfe == nfe == st['nfe'] and (st['n_accept'], st['n_reject']) == (acc.count(True), acc.count(False))
-    assert calls['fwd'] == nfe and calls['vjp'] == 0                   # every evaluation on the native kernel
+    if mode == 'lazy':
+        assert st['route'] == 'fused' and calls == {'vjp': 0, 'fwd': 0}   # one C call, no graph yet
+    else:
+        assert st['route'] == 'unrolled'
+        assert calls['fwd'] == nfe and calls['vjp'] == 0                   # every evaluation on the native kernel
     assert rel(out.detach().cpu(), torch.from_numpy(g['out'])) < 1e-4
     out.backward(torch.from_numpy(g['grad_out']).to(DEV))
-    assert calls['vjp'] == nfe                                         # every VJP on the native kernels
+    assert calls['vjp'] == nfe and calls['fwd'] == nfe                 # every evaluation and VJP on the native kernels
+    assert func.nfe == nfe                                             # the replay inside backward is not counted again
+    if mode == 'lazy':
+        rp = solver.last_stats['replay']
+        assert solver.last_stats['grad_route'] == 'unrolled' and (rp['nfe'], rp['n_accept'], rp['n_reject']) == (nfe, acc.count(True), acc.count(False))
     gy, gt = h0.grad.cpu(), t.grad.cpu()
     gp = torch.cat([q.grad.reshape(-1) for q in func.parameters()]).cpu()
     res = dict(vs_ref_fp32=dict(y0=rel(gy, torch.from_numpy(g['grad_y0'])), params=rel(gp, torch.from_numpy(g['grad_params'])),
@@ -53,7 +65,7 @@ def test_unrolled_gradients_against_reference(native_lib, golden, name, monkeypa
                                 t=rel(gt, torch.from_numpy(g['grad_t_f64']))),
                ref_fp32_vs_fp64=dict(y0=float(g['ref_err_y0']), params=float(g['ref_err_params'])),
                ref_adjoint_vs_unrolled=dict(y0=float(g['adjoint_dev_y0']), params=float(g['adjoint_dev_params'])))
-    RESULTS[name] = res
+    RESULTS[name + ':' + mode] = res
     print('\n%s: %s' % (name, json.dumps(res)))
     os.makedirs('gpurun_out', exist_ok=True)
     json.dump(RESULTS, open('gpurun_out/unrolled_parity.json', 'w'), indent=1)
