@@ -344,6 +344,20 @@ int node_b200_adjoint_solve(void* ctl, float* bufs, int64_t row_elems, const int
                             int first_step_given, void* stream);
 int node_b200_adjoint_solve_reset(void);
 
+/* Linear combinations with device-resident coefficients - the autograd nodes of the unrolled route (node_b200/unrolled.py; the
+ * reference records `y + sum((h*c_j)*k_j)` (misc.py:22-25), the Hermite fit (interp.py:5-35) and the interpolant (interp.py:54-65)
+ * as one ATen multiply + one ATen add per term). dtype NODE_F32 / NODE_F64, n <= 7 sources of numel elements, coef = n values of
+ * that dtype on the device. Same rounding as the reference's op sequence (every product and addition rounds separately, left to
+ * right from 0, then base + sum).
+ * lincomb: out = base + sum_j coef[j] * src_j (base may be null); lincomb_scale: dst_j = coef[j] * g (null dst skipped);
+ * lincomb_dots: dots[j] = sum_e src_j[e] * g[e] (float64 accumulation, fixed order; partial = lincomb_scratch_doubles() doubles). */
+int node_b200_lincomb(int dtype, void* out, const void* base, const void* const* host_srcs, const void* coef, int n, int64_t numel,
+                      void* stream);
+int node_b200_lincomb_scale(int dtype, void* const* host_dsts, const void* g, const void* coef, int n, int64_t numel, void* stream);
+int node_b200_lincomb_dots(int dtype, const void* const* host_srcs, const void* g, int n, int64_t numel, double* partial, void* dots,
+                           void* stream);
+int64_t node_b200_lincomb_scratch_doubles(void);
+
 /* Wide dynamics (n_filters = 128, 192, 256: the paper's CIFAR setting, reproduce.sh:21): ODEfunc.forward (model.py:339-348) as
  * 64-channel blocks on the tcgen05 engine instead of cuDNN.
  * conv3x3_forward_strided = conv3x3_forward on a 64-channel block of a wider tensor: x / (addend, out) point at the block's

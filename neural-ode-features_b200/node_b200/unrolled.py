@@ -49,6 +49,73 @@ class _NativeDynamics(torch.autograd.Function):
         return (None, vt.to(t.dtype).reshape(t.shape), vy) + tuple(grads)
 
 
+class _LinComb(torch.autograd.Function):
+    """out = base + sum_j coef[j] * src_j as ONE autograd node on the native kernels (csrc/lincomb.cu): the reference records one
+    multiply and one add per term (misc.py:22-30); the forward rounds exactly like that op sequence, the backward is one pass for
+    the sources' gradients (coef[j] * g) and one for the coefficients' (float64 dot products, fixed order)."""
+
+    @staticmethod
+    def forward(ctx, coef, base, *srcs):
+        native = _solver.native
+        lib = native.lib()
+        srcs = tuple(v.contiguous() for v in srcs)
+        ref = srcs[0]
+        code = native.F32 if ref.dtype == torch.float32 else native.F64
+        coef = coef.to(ref.dtype).contiguous()
+        b = base.contiguous() if base is not None else None
+        out = torch.empty_like(ref)
+        arr = (native._vp * len(srcs))(*[v.data_ptr() for v in srcs])
+        with native.device_guard(ref.device):
+            native.check(lib.node_b200_lincomb(code, native.ptr(out), native.ptr(b), arr, native.ptr(coef), len(srcs), ref.numel(),
+                                               native.stream_ptr()), 'lincomb')
+        ctx.save_for_backward(coef, *srcs)
+        ctx.code, ctx.has_base = code, base is not None
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        native = _solver.native
+        lib = native.lib()
+        coef, *srcs = ctx.saved_tensors
+        g = g.contiguous()
+        need = ctx.needs_input_grad
+        n = len(srcs)
+        with native.device_guard(g.device):
+            gs = [torch.empty_like(g) if need[2 + j] else None for j in range(n)]
+            if any(v is not None for v in gs):
+                arr = (native._vp * n)(*[v.data_ptr() if v is not None else 0 for v in gs])
+                native.check(lib.node_b200_lincomb_scale(ctx.code, arr, native.ptr(g), native.ptr(coef), n, g.numel(), native.stream_ptr()),
+                             'lincomb_scale')
+            gc = None
+            if need[0]:
+                gc = torch.empty(n, dtype=g.dtype, device=g.device)
+                part = torch.empty(int(lib.node_b200_lincomb_scratch_doubles()), dtype=torch.float64, device=g.device)
+                arr = (native._vp * n)(*[v.data_ptr() for v in srcs])
+                native.check(lib.node_b200_lincomb_dots(ctx.code, arr, native.ptr(g), n, g.numel(), native.ptr(part), native.ptr(gc),
+                                                        native.stream_ptr()), 'lincomb_dots')
+        return (gc, g if (ctx.has_base and need[1]) else None) + tuple(gs)
+
+
+_cvecs = {}
+
+
+def _cvec(values, like):
+    """The constants of a combination as a device vector in the state dtype (a Python double times a tensor rounds the double to the
+    tensor's dtype first, so `h * _cvec(c)` equals the reference's `h * c` element by element)."""
+    key = (tuple(values), like.dtype, str(like.device))
+    v = _cvecs.get(key)
+    if v is None:
+        v = _cvecs[key] = torch.tensor([float(c) for c in values], dtype=like.dtype, device=like.device)
+    return v
+
+
+def _native_nodes(ys):
+    import os
+    return (os.environ.get('NODE_B200_UNROLLED_NODES', '1') != '0'
+            and all(y.is_cuda and y.dtype in (torch.float32, torch.float64) and y.numel() > 0 for y in ys))
+
+
 def _dynamics(func):
     """callable(t, tuple_state) -> tuple; the recognised ODE-Net dynamics go through the native kernels."""
     base = _solver._unwrap(func) if isinstance(func, nn.Module) else func
@@ -127,6 +194,7 @@ def solve(func, y0, t, rtol, atol, options, stats=None):
     t0 = t1 = t[0]
     coeffs = [ys] * 5
     outs = [ys]
+    nat = _native_nodes(ys)            # CUDA states: every combination below is ONE native autograd node instead of 2 ATen ops per term
     n_acc = n_rej = 0
     for i in range(1, len(t)):
         steps = 0
@@ -141,23 +209,33 @@ def solve(func, y0, t, rtol, atol, options, stats=None):
             yi = ys
             for a_i, b_i in zip(_ALPHA, _BETA):                      # rk_common.py:49-52
                 ti = s + a_i * h                                     # node creation order as in the reference: it fixes
-                yi = tuple(y + _wsum(h, b_i, k) for y, k in zip(ys, ks))   # the order in which autograd sums into h
+                if nat:
+                    yi = tuple(_LinComb.apply(h * _cvec(b_i, y), y, *k) for y, k in zip(ys, ks))
+                else:
+                    yi = tuple(y + _wsum(h, b_i, k) for y, k in zip(ys, ks))   # the order in which autograd sums into h
                 for k, v in zip(ks, f(ti, yi)):
                     k.append(v)
             nfe += 6
             y1, f1 = yi, tuple(k[-1] for k in ks)                    # FSAL (rk_common.py:54-58)
             ratios = []
             for k, a, b, rt, at in zip(ks, ys, y1, rtol, atol):      # misc.py:146-157
-                q = _wsum(h, _C_ERR, k) / (at + rt * torch.max(torch.abs(a), torch.abs(b)))
+                err = _LinComb.apply(h * _cvec(_C_ERR, a), None, *k) if nat else _wsum(h, _C_ERR, k)
+                q = err / (at + rt * torch.max(torch.abs(a), torch.abs(b)))
                 ratios.append(torch.mean(q * q))
             accept = bool((torch.stack([r.detach() for r in ratios]) <= 1).all())     # dopri5.py:109
             if accept:
                 t_next = start + dt                                                     # dopri5.py:112, before the fit
                 hf = dt.type_as(ys[0])                                                  # dopri5.py:41: its own cast node
-                ymid = [y + _wsum(hf, _C_MID, k) for y, k in zip(ys, ks)]               # dopri5.py:39-45, interp.py:5-35
-                fit = lambda cs, m: tuple(_lin(cs, v) for v in zip(k1, f1, ys, y1, m))
-                coeffs = [fit([-2 * hf, 2 * hf, -8, -8, 16], ymid), fit([5 * hf, -3 * hf, 18, 14, -32], ymid),
-                          fit([-4 * hf, hf, -11, -5, 16], ymid), tuple(hf * v for v in k1), ys]
+                if nat:
+                    ymid = [_LinComb.apply(hf * _cvec(_C_MID, y), y, *k) for y, k in zip(ys, ks)]
+                    fit = lambda ch, c0, m: tuple(_LinComb.apply(hf * _cvec(ch, v[0]) + _cvec(c0, v[0]), None, *v) for v in zip(k1, f1, ys, y1, m))
+                    coeffs = [fit((-2, 2, 0, 0, 0), (0, 0, -8, -8, 16), ymid), fit((5, -3, 0, 0, 0), (0, 0, 18, 14, -32), ymid),
+                              fit((-4, 1, 0, 0, 0), (0, 0, -11, -5, 16), ymid), tuple(hf * v for v in k1), ys]
+                else:
+                    ymid = [y + _wsum(hf, _C_MID, k) for y, k in zip(ys, ks)]           # dopri5.py:39-45, interp.py:5-35
+                    fit = lambda cs, m: tuple(_lin(cs, v) for v in zip(k1, f1, ys, y1, m))
+                    coeffs = [fit([-2 * hf, 2 * hf, -8, -8, 16], ymid), fit([5 * hf, -3 * hf, 18, 14, -32], ymid),
+                              fit([-4 * hf, hf, -11, -5, 16], ymid), tuple(hf * v for v in k1), ys]
                 t0, t1 = start, t_next
                 ys, k1 = y1, f1
                 n_acc += 1
@@ -180,7 +258,10 @@ def solve(func, y0, t, rtol, atol, options, stats=None):
         for _ in range(2, 5):
             pw.append(pw[-1] * x)
         pw = pw[::-1]
-        outs.append(tuple(_lin(pw, per) for per in zip(*coeffs)))
+        if nat:
+            outs.append(tuple(_LinComb.apply(torch.stack(pw), None, *per) for per in zip(*coeffs)))
+        else:
+            outs.append(tuple(_lin(pw, per) for per in zip(*coeffs)))
     if stats is not None:
         stats.update(route='unrolled', nfe=nfe, n_accept=n_acc, n_reject=n_rej)
     return tuple(torch.stack(v) for v in zip(*outs))

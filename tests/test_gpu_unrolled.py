@@ -113,3 +113,38 @@ def test_unrolled_plain_callable_and_tuple(native_lib):
     t = torch.tensor([0.0, 0.5, 1.2], dtype=torch.float64, device=DEV, requires_grad=True)
     fn = lambda a, b: odeint(f, (a, a * 2), b, rtol=1e-9, atol=1e-11, method='dopri5')[1]
     assert torch.autograd.gradcheck(fn, (y0, t))
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_native_combination_nodes_equal_recorded_aten_ops(native_lib, monkeypatch, dtype):
+    """csrc/lincomb.cu: every `y + sum((h*c_j)*k_j)` / Hermite fit / interpolant of the recorded loop as ONE native autograd node:
+    the forward is bit-identical to the op-by-op ATen recording (same rounding order), gradients agree to rounding."""
+    from node_b200 import odeint, models, solver
+    torch.manual_seed(1)
+    if dtype == torch.float32:
+        func = models.ODEfunc(64).to(DEV)
+        y0 = torch.randn(3, 64, 8, 8, device=DEV)
+        tol = 1e-3
+    else:
+        A = torch.randn(5, 5, dtype=dtype, device=DEV) * 0.6
+        func = lambda t, y: torch.tanh(y @ A) * (1 + t)
+        y0 = torch.randn(4, 5, dtype=dtype, device=DEV)
+        tol = 1e-7
+    t = torch.tensor([0.0, 0.4, 1.0], dtype=dtype, device=DEV)
+    res = {}
+    for nodes in ('1', '0'):
+        monkeypatch.setenv('NODE_B200_UNROLLED_NODES', nodes)
+        monkeypatch.setenv('NODE_B200_ODEINT_GRAD', 'unrolled-eager')
+        y = y0.clone().requires_grad_(True)
+        tt = t.clone().requires_grad_(True)
+        out = odeint(func, y, tt, rtol=tol, atol=tol, method='dopri5')
+        st = dict(solver.last_stats)
+        out.backward(torch.ones_like(out) / out.numel())
+        res[nodes] = (out.detach(), y.grad.clone(), tt.grad.clone(), st)
+    a, b = res['1'], res['0']
+    assert torch.equal(a[0], b[0])
+    assert (a[3]['nfe'], a[3]['n_accept'], a[3]['n_reject']) == (b[3]['nfe'], b[3]['n_accept'], b[3]['n_reject'])
+    # grad_t of the fp32 case is a sum of 10^4 signed terms per stage time (cancellation): its relative rounding noise is the 1e-2 the
+    # goldens record between two fp32 evaluations of it; grad_y0 is not such a sum
+    lim_y, lim_t = (2e-5, 5e-2) if dtype == torch.float32 else (1e-11, 1e-9)
+    assert rel(a[1], b[1]) < lim_y and rel(a[2], b[2]) < lim_t, (rel(a[1], b[1]), rel(a[2], b[2]))

@@ -1,6 +1,6 @@
 #!/bin/bash
 python -c "import sys; sys.path.insert(0,'.'); import __graft_entry__ as g; print('stale', g._stale())"
-timeout 600 python -m pytest tests/test_gpu_unrolled.py tests/test_gpu_fused.py tests/test_gpu_reference_suite.py -x -q 2>&1 | tail -6
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 timeout 300 python - <<'PY'
 import os, sys, time
 sys.path.insert(0, '.')
@@ -25,3 +25,4 @@ for mode in ('nodes', 'aten', 'adjoint'):
     torch.cuda.synchronize()
     print(mode, 'train step b128: %.2f ms' % ((time.perf_counter() - t0) / 10 * 1e3), flush=True)
 PY
+timeout 200 python tools/pgd_latency.py 2>&1 | grep "^1 1\|^128 1"
