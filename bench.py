@@ -211,7 +211,7 @@ def workload_config(args, sample_note=None):
              solver='dopri5 rtol=atol=1e-3', conv_mode=os.environ.get('NODE_B200_CONV', 'f16x3'),
              downsample_classifier='own CUDA kernels for the stem (conv+GN+ReLU), the ResBlock heads (3x3 s2 + 1x1 s2, tcgen05) and '
                                    'tails (GN->ReLU->conv3x3->add, tcgen05) and the remaining GroupNorm->ReLU pairs; pooling / linear: PyTorch',
-             batch_note='per-GPU batch sized to whole rounds of the persistent step kernel: 74 CTA pairs x 2 CTAs x 2 virtual slots x 4 images x 4 rounds',
+             batch_note='per-GPU batch sized to whole rounds of the persistent step kernel: 74 CTA pairs x 2 CTAs x 2 virtual slots x 4 images = 1184 images per round, %d rounds' % max(1, args.batch // 1184) if args.batch % 1184 == 0 else 'per-GPU batch %d (not a multiple of the 1184-image round of the persistent step kernel)' % args.batch,
              parallelism='dp%d batch shard, error-norm allreduce' % args.gpus,
              l2='inputs larger than L2 (state %d MB per tensor, ~10 live tensors)' % (args.batch * 64 * 64 * 4 // 2 ** 20))
     if sample_note:          # the reference arm: the oracle port on the host CPU, none of the kernels above
@@ -633,8 +633,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('NODE_B200_BENCH_BATCH', 4736)),
-                    help='per-GPU batch; 4736 = 148 SMs x 2 virtual slots x 4 images per super-tile x 4 rounds (no tail round)')
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('NODE_B200_BENCH_BATCH', 9472)),
+                    help='per-GPU batch; 9472 = 8 rounds of 148 SMs x 2 virtual slots x 4 images per super-tile (no tail round; 4736 = 4 rounds: -3 %% throughput)')
     ap.add_argument('--cpu-sample', type=int, default=0, help='images per step of the reference arm / cpu_baseline (0 = the whole per-GPU batch)')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--skip-cpu', action='store_true')
