@@ -777,7 +777,10 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get('k_step_dram_bytes_per_launch')
+        tj = json.load(open(tpath))                       # one ncu --set full capture; scaled to this run's batch per launch
+        traffic = tj.get('k_step_dram_bytes_per_launch')
+        if tj.get('k_step_dram_bytes_per_image') and tj.get('batch_of_capture') != B:
+            traffic = int(tj['k_step_dram_bytes_per_image'] * B)
     roof = dict(bound='tensor', kernel='k_step8 (dense 8x8 tiling on CTA pairs, tcgen05.mma.cta_group::2; 6 dopri5 stages = 12 '
                                        'implicit-GEMM convs per launch)',
                 achieved=flops_per_launch / k_avg / 1e12, peak=tf32_peak, unit='TFLOP/s',
