@@ -339,9 +339,15 @@ int node_b200_adjoint_step(void* ctl, float* bufs, int64_t row_elems, int cur, c
  * buffers alive and at the same addresses to reuse them); adjoint_solve_reset drops them. The caller reads ctl back ONCE,
  * after the call, for status / counters / trace. */
 int node_b200_adjoint_solve(void* ctl, float* bufs, int64_t row_elems, const int64_t* host_seg_off, const int64_t* host_seg_len,
-                            int n_seg, void* workspace, void* vjp_workspace, float tsign, int64_t ts32_offset_bytes, int N, int C,
-                            int H, int W, double* partials, double* sums, int* nonfinite_flag, const double* t_out, float* out,
-                            int first_step_given, void* stream);
+                            int n_seg, void* workspace, void* vjp_workspace, void* vjp_workspace2, float tsign,
+                            int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums, int* nonfinite_flag,
+                            const double* t_out, float* out, int first_step_given, void* stream);
+/* vjp_workspace2 (a second node_b200_vjp_workspace_bytes buffer, or null): when given, the weight-gradient GEMM + fold of stage i
+ * run on a side branch of the loop graph under stage i + 1's k_vjp (small batches: the interval is a dependent chain).
+ * odefunc_vjp_split: node_b200_odefunc_vjp with that second part on side_stream, ordered after the first by fork_event. */
+int node_b200_odefunc_vjp_split(void* workspace, void* vjp_workspace, const float* y, const float* adj_y, const float* t_dev,
+                                float tsign, float* f_out, float* vjp_y, float* vjp_t, float* vjp_params, int N, int C, int H, int W,
+                                void* stream, void* side_stream, void* fork_event);
 int node_b200_adjoint_solve_reset(void);
 
 /* Linear combinations with device-resident coefficients - the autograd nodes of the unrolled route (node_b200/unrolled.py; the

@@ -15,6 +15,9 @@
 extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const float* y, const float* adj_y, const float* t_dev,
                                      float tsign, float* f_out, float* vjp_y, float* vjp_t, float* vjp_params, int N, int C,
                                      int H, int W, void* stream);
+extern "C" int node_b200_odefunc_vjp_split(void* workspace, void* vjp_workspace, const float* y, const float* adj_y, const float* t_dev,
+                                           float tsign, float* f_out, float* vjp_y, float* vjp_t, float* vjp_params, int N, int C, int H,
+                                           int W, void* stream, void* side_stream, void* fork_event);
 
 namespace node {
 
@@ -41,7 +44,7 @@ __global__ void k_adjoint_continue(cudaGraphConditionalHandle h, const node_ctl_
 }
 
 struct AdjointSolveKey {
-  void *ctl, *bufs, *workspace, *vjp_workspace, *partials, *sums, *flag, *t_out, *out;
+  void *ctl, *bufs, *workspace, *vjp_workspace, *vjp_workspace2, *partials, *sums, *flag, *t_out, *out;
   int64_t row_elems, ts32_off, seg_off[4], seg_len[4];
   float tsign;
   int N, C, H, W, device;
@@ -57,6 +60,24 @@ constexpr size_t kMaxAdjointGraphs = 16;
 
 using namespace node;
 
+// Side stream + events of the overlapped body (per device, created once; inside the capture they become graph edges)
+struct AdjointSide { cudaStream_t stream; cudaEvent_t fork[6], done[6], join; bool ok; };
+static AdjointSide g_adjoint_side[64];
+
+static AdjointSide* adjoint_side(int device) {
+  if (device < 0 || device >= 64) return nullptr;
+  AdjointSide& s = g_adjoint_side[device];
+  if (!s.ok) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 6; ++i)
+      if (cudaEventCreateWithFlags(&s.fork[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.ok = true;
+  }
+  return &s;
+}
+
 // the body of the loop: one attempted step, rows (Y0, F0) -> (Y1, F1), controller, dense output, commit
 static int adjoint_enqueue_attempt(const AdjointSolveKey& k, cudaStream_t st) {
   node_ctl_t* ctl = (node_ctl_t*)k.ctl;
@@ -67,13 +88,39 @@ static int adjoint_enqueue_attempt(const AdjointSolveKey& k, cudaStream_t st) {
   const void* kp[7];
   for (int i = 0; i < 7; ++i) kp[i] = row(ks[i]);
   const float* ts32 = (const float*)((const char*)k.ctl + k.ts32_off);
-  for (int i = 0; i < 6; ++i) {
-    float* dst = row(i < 5 ? YI : Y1);
-    NODE_CUDA_OK((cudaError_t)node_b200_rk_stage_combine(ctl, NODE_F32, i, dst, row(Y0), kp, i + 1, k.row_elems, st));
-    float* o = row(ks[i + 1]);
-    NODE_CUDA_OK((cudaError_t)node_b200_odefunc_vjp(k.workspace, k.vjp_workspace, dst + k.seg_off[0], dst + k.seg_off[1], ts32 + (i + 1),
-                                                    k.tsign, o + k.seg_off[0], o + k.seg_off[1], o + k.seg_off[2], o + k.seg_off[3],
-                                                    k.N, k.C, k.H, k.W, st));
+  AdjointSide* side = k.vjp_workspace2 != nullptr ? adjoint_side(k.device) : nullptr;
+  if (side != nullptr) {
+    // Small batches (a dependent chain of ~100 us evaluations): the weight-gradient GEMM and the fold into (vjp_t, vjp_params) of
+    // stage i run on a side branch under stage i + 1's k_vjp - nothing on the main branch reads the parameter / time adjoints
+    // (adjoint.py:35) until the error norm. Stage combinations on the main branch cover the (y, adj_y) members only; the
+    // (adj_t, adj_params) members are combined once, for y1, on the side branch. Two VJP workspaces alternate, so stage i + 1's
+    // k_vjp does not overwrite the operands stage i's GEMM is reading.
+    const int64_t n_state = k.seg_off[2], n_par = k.row_elems - k.seg_off[2];
+    const void* kpar[7];
+    for (int i = 0; i < 7; ++i) kpar[i] = row(ks[i]) + n_state;
+    void* vws[2] = {k.vjp_workspace, k.vjp_workspace2};
+    for (int i = 0; i < 6; ++i) {
+      float* dst = row(i < 5 ? YI : Y1);
+      NODE_CUDA_OK((cudaError_t)node_b200_rk_stage_combine(ctl, NODE_F32, i, dst, row(Y0), kp, i + 1, n_state, st));
+      if (i >= 2) NODE_CUDA_OK(cudaStreamWaitEvent(st, side->done[i - 2], 0));      // this workspace's previous GEMM has read its operands
+      float* o = row(ks[i + 1]);
+      NODE_CUDA_OK((cudaError_t)node_b200_odefunc_vjp_split(k.workspace, vws[i & 1], dst + k.seg_off[0], dst + k.seg_off[1], ts32 + (i + 1),
+                                                            k.tsign, o + k.seg_off[0], o + k.seg_off[1], o + k.seg_off[2], o + k.seg_off[3],
+                                                            k.N, k.C, k.H, k.W, st, side->stream, side->fork[i]));
+      NODE_CUDA_OK(cudaEventRecord(side->done[i], side->stream));
+    }
+    NODE_CUDA_OK((cudaError_t)node_b200_rk_stage_combine(ctl, NODE_F32, 5, row(Y1) + n_state, row(Y0) + n_state, kpar, 6, n_par, side->stream));
+    NODE_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    NODE_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));
+  } else {
+    for (int i = 0; i < 6; ++i) {
+      float* dst = row(i < 5 ? YI : Y1);
+      NODE_CUDA_OK((cudaError_t)node_b200_rk_stage_combine(ctl, NODE_F32, i, dst, row(Y0), kp, i + 1, k.row_elems, st));
+      float* o = row(ks[i + 1]);
+      NODE_CUDA_OK((cudaError_t)node_b200_odefunc_vjp(k.workspace, k.vjp_workspace, dst + k.seg_off[0], dst + k.seg_off[1], ts32 + (i + 1),
+                                                      k.tsign, o + k.seg_off[0], o + k.seg_off[1], o + k.seg_off[2], o + k.seg_off[3],
+                                                      k.N, k.C, k.H, k.W, st));
+    }
   }
   NODE_CUDA_OK((cudaError_t)node_b200_rk_error_norm(ctl, NODE_F32, row(Y0), row(Y1), kp, k.seg_off, k.seg_len, 4, (double*)k.partials,
                                                     (int*)k.flag, st));
@@ -128,13 +175,14 @@ static int adjoint_build_graph(const AdjointSolveKey& k, AdjointSolveGraph* out)
 }
 
 extern "C" int node_b200_adjoint_solve(void* ctl_v, float* bufs, int64_t row_elems, const int64_t* seg_off, const int64_t* seg_len,
-                                       int n_seg, void* workspace, void* vjp_workspace, float tsign, int64_t ts32_offset_bytes,
-                                       int N, int C, int H, int W, double* partials, double* sums, int* nonfinite_flag,
-                                       const double* t_out, float* out, int first_step_given, void* stream) {
+                                       int n_seg, void* workspace, void* vjp_workspace, void* vjp_workspace2, float tsign,
+                                       int64_t ts32_offset_bytes, int N, int C, int H, int W, double* partials, double* sums,
+                                       int* nonfinite_flag, const double* t_out, float* out, int first_step_given, void* stream) {
   if (n_seg != 4 || row_elems % 4 != 0) return (int)cudaErrorInvalidValue;
   AdjointSolveKey k;
   memset(&k, 0, sizeof(k));
-  k.ctl = ctl_v; k.bufs = bufs; k.workspace = workspace; k.vjp_workspace = vjp_workspace; k.partials = partials; k.sums = sums;
+  k.ctl = ctl_v; k.bufs = bufs; k.workspace = workspace; k.vjp_workspace = vjp_workspace; k.vjp_workspace2 = vjp_workspace2;
+  k.partials = partials; k.sums = sums;
   k.flag = nonfinite_flag; k.t_out = (void*)t_out; k.out = out; k.row_elems = row_elems; k.ts32_off = ts32_offset_bytes;
   for (int i = 0; i < 4; ++i) { k.seg_off[i] = seg_off[i]; k.seg_len[i] = seg_len[i]; }
   k.tsign = tsign; k.N = N; k.C = C; k.H = H; k.W = W;

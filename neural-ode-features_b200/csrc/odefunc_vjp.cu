@@ -185,19 +185,22 @@ extern "C" int node_b200_wgrad(void* vjp_workspace, const float* r1, const float
   return (int)cudaErrorInvalidValue;
 }
 
-extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const float* y, const float* adj_y,
-                                     const float* t_dev, float tsign, float* f_out, float* vjp_y, float* vjp_t,
-                                     float* vjp_params, int N, int C, int H, int W, void* stream) {
+// The evaluation in two parts, so that a caller may run the second one on a side stream: (1) k_vjp - forward recompute, data
+// gradients, the operands of the weight gradient; (2) k_wgrad + the fold into (vjp_t, vjp_params), which nothing but the stage
+// combination of the parameter adjoint reads (adjoint.py:35: augmented_dynamics never looks at adj_t / adj_params).
+struct VjpLaunch { VjpWs v; float tsign; bool use_dense; int grid_dense; int gs; };
+
+static int vjp_part1(void* workspace, void* vjp_workspace, const float* y, const float* adj_y, const float* t_dev, float tsign,
+                     float* f_out, float* vjp_y, int N, int C, int H, int W, cudaStream_t st, VjpLaunch* L) {
   VjpArgs a{};
   if (!make_geo(N, C, H, W, &a.g) || !step_engine_supports(H, W)) return (int)cudaErrorInvalidValue;
   ws_layout(workspace, N, C, H, W, &a.w);
-  VjpWs v;
+  VjpWs& v = L->v;
   vjp_ws_layout(vjp_workspace, N, C, H, W, &v);
   a.y = y; a.adj = adj_y; a.f_out = f_out; a.vy_out = vjp_y;
   a.R[0] = v.R[0]; a.R[1] = v.R[1]; a.GC[0] = v.GC[0]; a.GC[1] = v.GC[1];
   a.chan_part = v.chan_part; a.t_part = v.t_part; a.t_dev = t_dev; a.tsign = tsign < 0 ? -1.f : 1.f; a.eps = 1e-5f;
   a.gc_max = v.gc_max;
-  cudaStream_t st = (cudaStream_t)stream;
   NODE_CUDA_OK(cudaMemsetAsync(v.gc_max, 0, 16, st));
   g_wgrad_scal = a.w.scal;
   int rc, grid_dense = 0;
@@ -209,18 +212,47 @@ extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const
   else if (H == 6 && W == 6) rc = launch_vjp_6x6(a, st);
   else if (H == 14 && W == 14) rc = launch_vjp_14x14(a, st);
   else rc = launch_vjp_16x16(a, st);
-  if (rc != 0) return rc;
-  rc = node_b200_wgrad(vjp_workspace, v.R[0], v.GC[0], v.R[1], v.GC[1], N, C, H, W, stream);
+  L->tsign = a.tsign; L->use_dense = use_dense; L->grid_dense = grid_dense; L->gs = a.g.gs;
+  return rc;
+}
+
+static int vjp_part2(void* vjp_workspace, const VjpLaunch& L, const float* t_dev, float* vjp_t, float* vjp_params, int N, int C, int H,
+                     int W, cudaStream_t st) {
+  const VjpWs& v = L.v;
+  int rc = node_b200_wgrad(vjp_workspace, v.R[0], v.GC[0], v.R[1], v.GC[1], N, C, H, W, (void*)st);
   if (rc != 0) return rc;
   // grid sizes the two kernels used (same rules as their launchers)
   const int per = strip_images(H, W);
   const int NST = (N + per - 1) / per;
-  const int NSTV = (N + a.g.gs - 1) / a.g.gs;              // k_vjp's super-tiles hold a.g.gs images (strip_gs)
-  const int nst_vjp = use_dense ? grid_dense : (NSTV < kMaxGrid ? NSTV : kMaxGrid);
+  const int NSTV = (N + L.gs - 1) / L.gs;                  // k_vjp's super-tiles hold gs images (strip_gs)
+  const int nst_vjp = L.use_dense ? L.grid_dense : (NSTV < kMaxGrid ? NSTV : kMaxGrid);
   const int nsplit = (H == 8 && W == 8 && wgrad8_enabled()) ? wgrad8_splits(N, 2) : (NST < kWgSplits ? NST : kWgSplits);
-  k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, a.tsign,
+  k_vjp_finalize<<<(kNParam + 1 + 255) / 256, 256, 0, st>>>(v.wpart, nsplit, v.chan_part, nst_vjp, v.t_part, t_dev, L.tsign,
                                                               vjp_t, vjp_params);
   return (int)cudaGetLastError();
+}
+
+extern "C" int node_b200_odefunc_vjp(void* workspace, void* vjp_workspace, const float* y, const float* adj_y,
+                                     const float* t_dev, float tsign, float* f_out, float* vjp_y, float* vjp_t,
+                                     float* vjp_params, int N, int C, int H, int W, void* stream) {
+  VjpLaunch L;
+  const int rc = vjp_part1(workspace, vjp_workspace, y, adj_y, t_dev, tsign, f_out, vjp_y, N, C, H, W, (cudaStream_t)stream, &L);
+  if (rc != 0) return rc;
+  return vjp_part2(vjp_workspace, L, t_dev, vjp_t, vjp_params, N, C, H, W, (cudaStream_t)stream);
+}
+
+// The same evaluation with its second part on `side_stream`, ordered after the first by `fork` (an event the caller owns; inside a
+// stream capture the pair becomes a graph edge). The caller joins `side_stream` before anything reads vjp_t / vjp_params or
+// rewrites this vjp_workspace.
+extern "C" int node_b200_odefunc_vjp_split(void* workspace, void* vjp_workspace, const float* y, const float* adj_y, const float* t_dev,
+                                           float tsign, float* f_out, float* vjp_y, float* vjp_t, float* vjp_params, int N, int C, int H,
+                                           int W, void* stream, void* side_stream, void* fork_event) {
+  VjpLaunch L;
+  const int rc = vjp_part1(workspace, vjp_workspace, y, adj_y, t_dev, tsign, f_out, vjp_y, N, C, H, W, (cudaStream_t)stream, &L);
+  if (rc != 0) return rc;
+  NODE_CUDA_OK(cudaEventRecord((cudaEvent_t)fork_event, (cudaStream_t)stream));
+  NODE_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)side_stream, (cudaEvent_t)fork_event, 0));
+  return vjp_part2(vjp_workspace, L, t_dev, vjp_t, vjp_params, N, C, H, W, (cudaStream_t)side_stream);
 }
 
 // ---- weight gradients of the callers' 3x3 stride-1 convolutions (model.py:119-178 under autograd) ------------------

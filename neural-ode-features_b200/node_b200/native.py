@@ -45,6 +45,7 @@ EXPORTS = (
     'node_b200_adjoint_solve', 'node_b200_adjoint_solve_reset', 'node_b200_groupnorm_backward_ex', 'node_b200_batch_colsum',
     'node_b200_pow2_scale', 'node_b200_wide_conv_blocks', 'node_b200_wide_vjp', 'node_b200_wide8_raw_operand',
     'node_b200_lincomb', 'node_b200_lincomb_scale', 'node_b200_lincomb_dots', 'node_b200_lincomb_scratch_doubles',
+    'node_b200_odefunc_vjp_split',
 )
 
 _lib = None
@@ -122,7 +123,8 @@ def _declare(lib):
     lib.node_b200_wide8_watchdog.argtypes = [_vp, _i, _vp]
     lib.node_b200_wide8_odefunc.argtypes = [_vp] * 14 + [_f, _i, _i, _vp]
     lib.node_b200_adjoint_step.argtypes = [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
-    lib.node_b200_adjoint_solve.argtypes = [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+    lib.node_b200_adjoint_solve.argtypes = [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _f, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+    lib.node_b200_odefunc_vjp_split.argtypes = [_vp] * 5 + [_f] + [_vp] * 4 + [_i, _i, _i, _i, _vp, _vp, _vp]
     lib.node_b200_adjoint_solve_reset.argtypes = []
     lib.node_b200_groupnorm_backward_ex.argtypes = [_vp] * 8 + [_f, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _i, _vp]
     lib.node_b200_batch_colsum.argtypes = [_vp, _vp, _i64, _i64, _vp]

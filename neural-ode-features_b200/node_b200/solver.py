@@ -338,14 +338,14 @@ _adjoint_solve_failed = False
 N_PARAMS_64 = 2 * (64 * 65 * 9 + 64) + 6 * 64
 
 
-def _vjp_workspace(device, N, C, H, W):
-    key = (str(device), N, C, H, W)
+def _vjp_workspace(device, N, C, H, W, slot=0):
+    key = (str(device), N, C, H, W, slot)
     buf = _vjp_ws_cache.get(key)
     if buf is None:
         nbytes = native.lib().node_b200_vjp_workspace_bytes(N, C, H, W)
         if nbytes <= 0:
             raise ValueError('shape [%d,%d,%d,%d] is not supported by the fused VJP kernels' % (N, C, H, W))
-        if len(_vjp_ws_cache) > 4:
+        if len(_vjp_ws_cache) > 8:
             _vjp_ws_cache.clear()
         buf = _vjp_ws_cache[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
     return buf
@@ -657,11 +657,17 @@ class _GenericSolve(object):
         fws = fused_workspace(self.device, N, C, H, W)
         fws.prepare(recognise_odefunc(self.func.func))
         vws = _vjp_workspace(self.device, N, C, H, W)
+        # few images (PGD, evaluate.py nfe: SMs are idle beside k_vjp's handful of CTAs): a second VJP workspace lets the weight-gradient
+        # GEMM of a stage run under the next stage's k_vjp. Measured 1-5 % of a batch-1 training step; nothing at batch 128, where
+        # k_vjp's 128 one-image CTAs leave the GEMM no SM to run on.
+        overlap = N <= 64 and os.environ.get('NODE_B200_ADJOINT_OVERLAP', '1') != '0'
+        vws2 = _vjp_workspace(self.device, N, C, H, W, slot=1) if overlap else None
         given = self.first_step is not None
         if given:
             self.sums[0] = _dflt(0.01)                   # dopri5.py:81-82
         rc = lib.node_b200_adjoint_solve(native.ptr(self.ctl), native.ptr(self.bufs), self.L, self.seg_off, self.seg_len, 4,
-                                         native.ptr(fws.buf), native.ptr(vws), float(self.tsign), native.layout()['ts32'], N, C, H, W,
+                                         native.ptr(fws.buf), native.ptr(vws), native.ptr(vws2), float(self.tsign), native.layout()['ts32'],
+                                         N, C, H, W,
                                          native.ptr(self.partials), native.ptr(self.sums), native.ptr(self.flag),
                                          native.ptr(self.t_dev), native.ptr(self.out), 1 if given else 0, sp)
         if rc != 0:
