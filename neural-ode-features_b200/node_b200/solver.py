@@ -11,6 +11,10 @@ Two routes, both device-only (no CPU path, no eager fallback):
     definition); stage combination, error norm, controller, initial step and dense output are the
     CUDA kernels K2-K6, with one host read of the controller block per attempted step instead of
     the reference's >= 9 syncs.
+Around them (round 2): the wide route (128 / 192 / 256 filters: wide.py), the adjoint's backward interval
+as one C call with a device-side loop (node_b200_adjoint_solve), gradients through the non-adjoint
+`odeint` (unrolled.py: the reference's unrolled gradient, fused forward + lazily recorded replay for the
+recognised dynamics), N independent per-sample solves (each.py).
 """
 import os
 import warnings
